@@ -1,0 +1,118 @@
+"""ctypes binding of libtcn_b200.so (include/tcn_b200.h).
+
+There is no fallback: if the shared library is missing, or a tensor is not a CUDA tensor, the
+call raises.  Build with ``python -m computervision_codes_b200.build`` (or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libtcn_b200.so")
+
+_lib = None
+
+
+class TcnError(RuntimeError):
+    pass
+
+
+class TapGemmArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("ldx", C.c_int), ("x_unpadded", C.c_int),
+        ("colscale", C.c_void_p), ("colscale_ld", C.c_int),
+        ("wf", C.c_void_p), ("bias", C.c_void_p),
+        ("y", C.c_void_p), ("ldy", C.c_int),
+        ("residual", C.c_void_p), ("ldr", C.c_int),
+        ("relu_mask", C.c_void_p), ("ldm", C.c_int),
+        ("meta", C.c_void_p), ("nblk", C.c_int),
+        ("c_in", C.c_int), ("n_out", C.c_int), ("ntaps", C.c_int), ("shift", C.c_int * 3),
+        ("relu", C.c_int),
+        ("drop_p", C.c_float), ("drop_seed", C.c_uint), ("drop_stream", C.c_uint),
+    ]
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [
+        ("g", C.c_void_p), ("ldg", C.c_int), ("g_cols", C.c_int),
+        ("x", C.c_void_p), ("ldx", C.c_int), ("x_unpadded", C.c_int),
+        ("colscale", C.c_void_p), ("colscale_ld", C.c_int),
+        ("meta", C.c_void_p), ("nblk", C.c_int),
+        ("n_out", C.c_int), ("c_in", C.c_int), ("ntaps", C.c_int), ("shift", C.c_int * 3),
+        ("dw", C.c_void_p), ("db", C.c_void_p),
+    ]
+
+
+class BceArgs(C.Structure):
+    _fields_ = [
+        ("logits", C.c_void_p), ("ldl", C.c_int),
+        ("labels", C.c_void_p), ("ldlab", C.c_int), ("lab_unpadded", C.c_int),
+        ("meta", C.c_void_p), ("nrows", C.c_int), ("ncols", C.c_int), ("zero_cols", C.c_int),
+        ("pos_w", C.c_void_p), ("col_scale", C.c_void_p), ("col_unit", C.c_void_p), ("col_head", C.c_void_p),
+        ("row_scale", C.c_float),
+        ("loss", C.c_void_p),
+        ("dl", C.c_void_p), ("lddl", C.c_int), ("grad_scale", C.c_float),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/tcn_b200.h declares
+SIGNATURES = {
+    "tcn_version": (C.c_int, []),
+    "tcn_last_error": (C.c_char_p, []),
+    "tcn_device_info": (C.c_int, [C.POINTER(C.c_int)] * 4),
+    "tcn_prep_weight_floats": (C.c_longlong, [C.c_int] * 4),
+    "tcn_prep_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "tcn_tapgemm": (C.c_int, [C.POINTER(TapGemmArgs), C.c_void_p]),
+    "tcn_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
+    "tcn_bce_rows": (C.c_int, [C.POINTER(BceArgs), C.c_void_p]),
+    "tcn_kd_kl_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                 C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
+    "tcn_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_float, C.c_void_p, C.c_float,
+                          C.c_void_p]),
+    "tcn_ce_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
+                              C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
+    "tcn_dropout_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
+                                    C.c_uint, C.c_uint, C.c_void_p]),
+    "tcn_dropout_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_uint, C.c_uint, C.c_void_p]),
+    "tcn_sgd_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+}
+
+
+def load():
+    """Load the shared library once; raise if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TcnError(
+            f"{LIB_PATH} not found: the CUDA library has not been built "
+            "(run `python -m computervision_codes_b200.build`); there is no CPU or PyTorch fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().tcn_last_error().decode("utf-8", "replace")
+        raise TcnError(f"{what or 'tcn_b200'} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise TcnError("tcn_b200 kernels need CUDA tensors; there is no CPU fallback")
+    return t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

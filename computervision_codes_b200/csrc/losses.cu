@@ -1,0 +1,310 @@
+// Per-frame heads' losses and their gradients: warp-per-row kernels with shuffle reductions.
+//
+//   bce_rows_kernel   : sigmoid-BCE with optional pos_weight over (rows x K) logits, several heads
+//                       concatenated along K, each column carrying its own 1/K_head * head_weight;
+//                       restates nn.BCEWithLogitsLoss as composed by
+//                       MT4MTLKD/Temporal_tenco/run.py:190-212 and TERL/0_5fold_TCN_black/run.py:307-343.
+//   kd_kl_rows_kernel : DistillKL (MT4MTLKD/Spatial_cnn/run.py:284-295) against sigmoid(teacher logits)
+//                       (run.py:180-182): loss and closed-form gradient T*(softmax(s/T) - p_t)/N.
+//   mse_kernel        : nn.MSELoss feature-KD (Spatial_cnn/run.py:187-191,328).
+//   ce_rows_kernel    : softmax cross-entropy for the 7-way phase head (no reference counterpart).
+#include "common.cuh"
+
+namespace tcn {
+
+constexpr int kMaxHeads = 8;
+
+struct BceDev {
+  const float* logits;
+  int ldl;
+  const uint8_t* labels;
+  int ldlab;
+  int lab_unpadded;
+  const BlkMeta* meta;  // nullptr: plain (nrows x K) problem, row_scale_const applies
+  int nrows;            // padded rows (meta) or plain rows
+  int ncols;
+  int zero_cols;  // dL columns [ncols, zero_cols) are written as zeros
+  const float* pos_w;      // [ncols] or nullptr
+  const float* col_scale;  // [ncols]  head_weight / K_head
+  const int* col_head;     // [ncols]  head index < kMaxHeads
+  float row_scale_const;   // plain mode: 1 / nrows ; meta mode: 1 / num_seqs (times 1/T_seq per row)
+  float* loss;             // [kMaxHeads] accumulated with atomicAdd: sum over rows/cols of row_scale*col_scale/head_w-free
+  float* dL;               // nullable
+  int lddl;
+  float grad_scale;
+};
+
+// loss[h] accumulates  sum_{r, c in head h} row_scale(r) * col_unit(c) * bce(r, c),  col_unit = 1 / K_head
+// (so that loss[h] is the reference's mean-BCE of head h, averaged over the sequences of the batch);
+// dL carries the full chain factor col_scale(c) (= head_weight / K_head) * row_scale(r) * grad_scale.
+__global__ void __launch_bounds__(256) bce_rows_kernel(const BceDev p, const float* __restrict__ col_unit) {
+  __shared__ float red[8][kMaxHeads];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float part[kMaxHeads];
+#pragma unroll
+  for (int h = 0; h < kMaxHeads; ++h) part[h] = 0.f;
+
+  for (int row = blockIdx.x * 8 + warp; row < p.nrows; row += gridDim.x * 8) {
+    float rs = p.row_scale_const;
+    int lrow = row;
+    if (p.meta != nullptr) {
+      const BlkMeta m = p.meta[row / kBlkRows];
+      if (row >= m.hi) continue;
+      rs = p.row_scale_const / (float)(m.hi - m.lo);
+      if (p.lab_unpadded) lrow = row + m.in_delta;
+    }
+    const float* x = p.logits + (size_t)row * p.ldl;
+    const uint8_t* y = p.labels + (size_t)lrow * p.ldlab;
+    for (int c = lane; c < p.zero_cols; c += 32) {
+      if (c < p.ncols) {
+        const float xv = x[c];
+        const float yv = y[c] ? 1.f : 0.f;
+        const float pw = p.pos_w ? __ldg(p.pos_w + c) : 1.f;
+        // (1 - y) x + (1 + (pw - 1) y) (log1p(exp(-|x|)) + max(-x, 0))      [torch's stable form]
+        const float lw = 1.f + (pw - 1.f) * yv;
+        const float sp = log1pf(expf(-fabsf(xv))) + fmaxf(-xv, 0.f);
+        const float l = (1.f - yv) * xv + lw * sp;
+        const int h = __ldg(p.col_head + c);
+        const float lu = rs * __ldg(col_unit + c) * l;
+#pragma unroll
+        for (int k = 0; k < kMaxHeads; ++k) part[k] += (k == h) ? lu : 0.f;
+        if (p.dL != nullptr) {
+          const float sg = 1.f / (1.f + expf(-xv));
+          const float gr = sg * (pw * yv + 1.f - yv) - pw * yv;
+          p.dL[(size_t)row * p.lddl + c] = gr * rs * __ldg(p.col_scale + c) * p.grad_scale;
+        }
+      } else if (p.dL != nullptr) {
+        p.dL[(size_t)row * p.lddl + c] = 0.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < kMaxHeads; ++h) {
+    const float v = warp_sum(part[h]);
+    if (lane == 0) red[warp][h] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kMaxHeads) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    if (v != 0.f) atomicAdd(p.loss + threadIdx.x, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- DistillKL
+__global__ void __launch_bounds__(256) kd_kl_rows_kernel(const float* __restrict__ ys, int lds,
+                                                         const float* __restrict__ yt, int ldt, int teacher_sigmoid,
+                                                         int nrows, int K, float T, float* loss, float loss_scale,
+                                                         float* gys, int ldg, float grad_scale) {
+  __shared__ float red[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float invT = 1.f / T;
+  float part = 0.f;
+  for (int row = blockIdx.x * 8 + warp; row < nrows; row += gridDim.x * 8) {
+    const float* s = ys + (size_t)row * lds;
+    const float* tp = yt + (size_t)row * ldt;
+    float ms = -INFINITY, mt = -INFINITY;
+    for (int c = lane; c < K; c += 32) {
+      const float tv = teacher_sigmoid ? 1.f / (1.f + expf(-tp[c])) : tp[c];
+      ms = fmaxf(ms, s[c] * invT);
+      mt = fmaxf(mt, tv * invT);
+    }
+    ms = warp_max(ms);
+    mt = warp_max(mt);
+    float zs = 0.f, zt = 0.f;
+    for (int c = lane; c < K; c += 32) {
+      const float tv = teacher_sigmoid ? 1.f / (1.f + expf(-tp[c])) : tp[c];
+      zs += expf(s[c] * invT - ms);
+      zt += expf(tv * invT - mt);
+    }
+    zs = warp_sum(zs);
+    zt = warp_sum(zt);
+    const float lzs = logf(zs), lzt = logf(zt);
+    for (int c = lane; c < K; c += 32) {
+      const float tv = teacher_sigmoid ? 1.f / (1.f + expf(-tp[c])) : tp[c];
+      const float lps = s[c] * invT - ms - lzs;
+      const float lpt = tv * invT - mt - lzt;
+      const float pt = expf(lpt);
+      part += pt * (lpt - lps);
+      if (gys != nullptr) gys[(size_t)row * ldg + c] = T * (expf(lps) - pt) / (float)nrows * grad_scale;
+    }
+  }
+  part = warp_sum(part);
+  if (lane == 0) red[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w];
+    atomicAdd(loss, v * T * T / (float)nrows * loss_scale);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- MSE
+__global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ a, const float* __restrict__ b, long n,
+                                                  float* loss, float loss_scale, float* ga, float grad_scale) {
+  __shared__ float red[8];
+  float part = 0.f;
+  const float inv = 1.f / (float)n;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float d = a[i] - b[i];
+    part += d * d;
+    if (ga != nullptr) ga[i] = 2.f * d * inv * grad_scale;
+  }
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w];
+    atomicAdd(loss, v * inv * loss_scale);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- softmax CE
+__global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ tgt,
+                                                      const BlkMeta* meta, int tgt_unpadded, int nrows, int K,
+                                                      float row_scale_const, float* loss, float* gx, int ldg,
+                                                      float grad_scale) {
+  __shared__ float red[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float part = 0.f;
+  for (int row = blockIdx.x * 8 + warp; row < nrows; row += gridDim.x * 8) {
+    float rs = row_scale_const;
+    int trow = row;
+    if (meta != nullptr) {
+      const BlkMeta m = meta[row / kBlkRows];
+      if (row >= m.hi) continue;
+      rs = row_scale_const / (float)(m.hi - m.lo);
+      if (tgt_unpadded) trow = row + m.in_delta;
+    }
+    const float* xr = x + (size_t)row * ldx;
+    float mx = -INFINITY;
+    for (int c = lane; c < K; c += 32) mx = fmaxf(mx, xr[c]);
+    mx = warp_max(mx);
+    float z = 0.f;
+    for (int c = lane; c < K; c += 32) z += expf(xr[c] - mx);
+    z = warp_sum(z);
+    const float lz = logf(z);
+    const int tg = tgt[trow];
+    for (int c = lane; c < K; c += 32) {
+      const float lp = xr[c] - mx - lz;
+      if (c == tg) part += -lp * rs;
+      if (gx != nullptr) gx[(size_t)row * ldg + c] = (expf(lp) - (c == tg ? 1.f : 0.f)) * rs * grad_scale;
+    }
+  }
+  part = warp_sum(part);
+  if (lane == 0) red[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w];
+    atomicAdd(loss, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- dropout helpers / SGD
+__global__ void dropout_apply_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int nrows,
+                                     int ncols, uint32_t thresh, float scale, uint32_t seed, uint32_t stream) {
+  const long total = (long)nrows * ncols;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / ncols), col = (int)(i - (long)row * ncols);
+    const float v = x[(size_t)row * ldx + col];
+    y[(size_t)row * ldy + col] = (drop_hash(seed, stream, (uint32_t)row, (uint32_t)col) >= thresh) ? v * scale : 0.f;
+  }
+}
+
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ keep, int nrows, int ncols, uint32_t thresh, uint32_t seed,
+                                    uint32_t stream) {
+  const long total = (long)nrows * ncols;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / ncols), col = (int)(i - (long)row * ncols);
+    keep[i] = (drop_hash(seed, stream, (uint32_t)row, (uint32_t)col) >= thresh) ? 1 : 0;
+  }
+}
+
+// torch.optim.SGD(lr, weight_decay) without momentum (Temporal_tenco/run.py:345-346): p -= lr * (g + wd * p)
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, long n, float lr, float wd,
+                           float grad_scale) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float w = p[i];
+    p[i] = w - lr * (g[i] * grad_scale + wd * w);
+  }
+}
+
+}  // namespace tcn
+
+using namespace tcn;
+
+static inline int grid_for(long n, int per_block, int cap) {
+  long b = (n + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > cap) b = cap;
+  return (int)b;
+}
+
+extern "C" int tcn_bce_rows(const tcn_bce_args* a, tcn_stream_t stream) {
+  TCN_REQUIRE(a && a->logits && a->labels && a->loss && a->col_scale && a->col_head && a->col_unit,
+              "tcn_bce_rows: null pointer");
+  TCN_REQUIRE(a->nrows > 0 && a->ncols > 0 && a->ldl >= a->ncols, "tcn_bce_rows: bad shape");
+  TCN_REQUIRE(a->zero_cols >= a->ncols && (a->dl == nullptr || a->lddl >= a->zero_cols),
+              "tcn_bce_rows: zero_cols must be in [ncols, lddl]");
+  BceDev p;
+  p.logits = a->logits; p.ldl = a->ldl; p.labels = a->labels; p.ldlab = a->ldlab; p.lab_unpadded = a->lab_unpadded;
+  p.meta = reinterpret_cast<const BlkMeta*>(a->meta); p.nrows = a->nrows; p.ncols = a->ncols;
+  p.zero_cols = a->zero_cols; p.pos_w = a->pos_w; p.col_scale = a->col_scale; p.col_head = a->col_head;
+  p.row_scale_const = a->row_scale; p.loss = a->loss; p.dL = a->dl; p.lddl = a->lddl; p.grad_scale = a->grad_scale;
+  bce_rows_kernel<<<grid_for(a->nrows, 8, num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(p, a->col_unit);
+  return check_launch("bce_rows_kernel");
+}
+
+extern "C" int tcn_kd_kl_rows(const float* ys, int lds, const float* yt, int ldt, int teacher_sigmoid, int nrows,
+                              int K, float T, float* loss, float loss_scale, float* gys, int ldg, float grad_scale,
+                              tcn_stream_t stream) {
+  TCN_REQUIRE(ys && yt && loss && nrows > 0 && K > 0 && T > 0.f, "tcn_kd_kl_rows: bad arguments");
+  kd_kl_rows_kernel<<<grid_for(nrows, 8, num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(
+      ys, lds, yt, ldt, teacher_sigmoid, nrows, K, T, loss, loss_scale, gys, ldg, grad_scale);
+  return check_launch("kd_kl_rows_kernel");
+}
+
+extern "C" int tcn_mse(const float* a, const float* b, long long n, float* loss, float loss_scale, float* ga,
+                       float grad_scale, tcn_stream_t stream) {
+  TCN_REQUIRE(a && b && loss && n > 0, "tcn_mse: bad arguments");
+  mse_kernel<<<grid_for(n, 1024, num_sms() * 4), 256, 0, (cudaStream_t)stream>>>(a, b, (long)n, loss, loss_scale, ga,
+                                                                                grad_scale);
+  return check_launch("mse_kernel");
+}
+
+extern "C" int tcn_ce_rows(const float* x, int ldx, const int* target, const int* meta, int tgt_unpadded, int nrows,
+                           int K, float row_scale, float* loss, float* gx, int ldg, float grad_scale,
+                           tcn_stream_t stream) {
+  TCN_REQUIRE(x && target && loss && nrows > 0 && K > 0, "tcn_ce_rows: bad arguments");
+  ce_rows_kernel<<<grid_for(nrows, 8, num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(
+      x, ldx, target, reinterpret_cast<const BlkMeta*>(meta), tgt_unpadded, nrows, K, row_scale, loss, gx, ldg,
+      grad_scale);
+  return check_launch("ce_rows_kernel");
+}
+
+extern "C" int tcn_dropout_apply(const float* x, int ldx, float* y, int ldy, int nrows, int ncols, float p,
+                                 unsigned seed, unsigned stream_id, tcn_stream_t stream) {
+  TCN_REQUIRE(x && y && nrows > 0 && ncols > 0 && p > 0.f && p < 1.f, "tcn_dropout_apply: bad arguments");
+  dropout_apply_kernel<<<grid_for((long)nrows * ncols, 1024, num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(
+      x, ldx, y, ldy, nrows, ncols, drop_thresh(p), 1.f / (1.f - p), seed, stream_id);
+  return check_launch("dropout_apply_kernel");
+}
+
+extern "C" int tcn_dropout_mask(unsigned char* keep, int nrows, int ncols, float p, unsigned seed, unsigned stream_id,
+                                tcn_stream_t stream) {
+  TCN_REQUIRE(keep && nrows > 0 && ncols > 0 && p > 0.f && p < 1.f, "tcn_dropout_mask: bad arguments");
+  dropout_mask_kernel<<<grid_for((long)nrows * ncols, 1024, num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(
+      keep, nrows, ncols, drop_thresh(p), seed, stream_id);
+  return check_launch("dropout_mask_kernel");
+}
+
+extern "C" int tcn_sgd_step(float* params, const float* grads, long long n, float lr, float weight_decay,
+                            float grad_scale, tcn_stream_t stream) {
+  TCN_REQUIRE(params && grads && n > 0, "tcn_sgd_step: bad arguments");
+  sgd_kernel<<<grid_for(n, 1024, num_sms() * 4), 256, 0, (cudaStream_t)stream>>>(params, grads, (long)n, lr,
+                                                                                weight_decay, grad_scale);
+  return check_launch("sgd_kernel");
+}

@@ -1,0 +1,60 @@
+// Library runtime: error strings, device queries.
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace tcn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+    return TCN_ERR_CUDA;
+  }
+  return TCN_OK;
+}
+
+int num_sms() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
+    cached = prop.multiProcessorCount;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+}  // namespace tcn
+
+extern "C" int tcn_version(void) { return TCN_VERSION; }
+extern "C" const char* tcn_last_error(void) { return tcn::g_err; }
+
+extern "C" int tcn_device_info(int* cc_major, int* cc_minor, int* nsm, int* built_for_sm) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  cudaDeviceProp prop;
+  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    tcn::set_error("tcn_device_info: CUDA error %d (%s)", (int)e, cudaGetErrorString(e));
+    cudaGetLastError();
+    return TCN_ERR_CUDA;
+  }
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (nsm) *nsm = prop.multiProcessorCount;
+  if (built_for_sm) *built_for_sm = 100;
+  return TCN_OK;
+}

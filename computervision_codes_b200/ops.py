@@ -1,0 +1,191 @@
+"""Thin Python wrappers over the C ABI (one call = one kernel launch) and the autograd Functions
+built from them.  All tensors are fp32 CUDA tensors in the packed time-major layout (layout.py)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .layout import SeqLayout, round_up
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------ raw launches
+def prep_weight(w: torch.Tensor, transpose: bool = False) -> torch.Tensor:
+    """torch Conv1d / Linear weight (n_out, c_in[, ntaps]) -> fragment-ordered hi/lo buffer."""
+    lib = _lib.load()
+    w = _f32c(w.detach())
+    n_out, c_in = w.shape[0], w.shape[1]
+    ntaps = w.shape[2] if w.dim() == 3 else 1
+    n = lib.tcn_prep_weight_floats(n_out, c_in, ntaps, int(transpose))
+    wf = torch.empty(n, device=w.device, dtype=torch.float32)
+    _lib.check(lib.tcn_prep_weight(_lib.ptr(w), n_out, c_in, ntaps, int(transpose), _lib.ptr(wf), _lib.stream_ptr()),
+               "tcn_prep_weight")
+    return wf
+
+
+def tapgemm(x, wf, lay: SeqLayout, c_in, n_out, shifts=(0,), bias=None, out=None, ldy=None, residual=None,
+            relu_mask=None, relu=False, drop_p=0.0, seed=0, stream_id=0, x_unpadded=False, colscale=None):
+    lib = _lib.load()
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    if ldy is None:
+        ldy = round_up(n_out, 4)
+    if out is None:
+        out = torch.zeros(lay.rows, ldy, device=x.device, dtype=torch.float32)
+    a = _lib.TapGemmArgs()
+    a.x, a.ldx, a.x_unpadded = _lib.ptr(x), x.shape[1], int(x_unpadded)
+    a.colscale, a.colscale_ld = _lib.ptr(colscale), (colscale.shape[1] if colscale is not None else 0)
+    a.wf, a.bias = _lib.ptr(wf), _lib.ptr(bias)
+    a.y, a.ldy = _lib.ptr(out), out.shape[1]
+    a.residual, a.ldr = _lib.ptr(residual), (residual.shape[1] if residual is not None else 0)
+    a.relu_mask, a.ldm = _lib.ptr(relu_mask), (relu_mask.shape[1] if relu_mask is not None else 0)
+    a.meta, a.nblk = _lib.ptr(lay.meta), lay.nblk
+    a.c_in, a.n_out, a.ntaps = c_in, n_out, len(shifts)
+    for i, s in enumerate(shifts):
+        a.shift[i] = int(s)
+    a.relu = int(relu)
+    a.drop_p, a.drop_seed, a.drop_stream = float(drop_p), int(seed) & 0xFFFFFFFF, int(stream_id) & 0xFFFFFFFF
+    _lib.check(lib.tcn_tapgemm(C.byref(a), _lib.stream_ptr()), "tcn_tapgemm")
+    return out
+
+
+def wgrad(g, x, lay: SeqLayout, n_out, c_in, shifts, dw, db=None, x_unpadded=False, colscale=None):
+    """dw (n_out, c_in, ntaps) += ..., db (n_out,) += ...  (accumulating, fp32 atomics)."""
+    lib = _lib.load()
+    assert g.is_contiguous() and x.is_contiguous() and dw.is_contiguous()
+    a = _lib.WgradArgs()
+    a.g, a.ldg, a.g_cols = _lib.ptr(g), g.shape[1], min(round_up(n_out, 4), g.shape[1])
+    a.x, a.ldx, a.x_unpadded = _lib.ptr(x), x.shape[1], int(x_unpadded)
+    a.colscale, a.colscale_ld = _lib.ptr(colscale), (colscale.shape[1] if colscale is not None else 0)
+    a.meta, a.nblk = _lib.ptr(lay.meta), lay.nblk
+    a.n_out, a.c_in, a.ntaps = n_out, c_in, len(shifts)
+    for i, s in enumerate(shifts):
+        a.shift[i] = int(s)
+    a.dw, a.db = _lib.ptr(dw), _lib.ptr(db)
+    _lib.check(lib.tcn_wgrad(C.byref(a), _lib.stream_ptr()), "tcn_wgrad")
+
+
+def dropout_apply(x, p, seed, stream_id):
+    lib = _lib.load()
+    y = torch.empty_like(x)
+    _lib.check(lib.tcn_dropout_apply(_lib.ptr(x), x.shape[1], _lib.ptr(y), y.shape[1], x.shape[0], x.shape[1],
+                                     float(p), int(seed) & 0xFFFFFFFF, int(stream_id) & 0xFFFFFFFF,
+                                     _lib.stream_ptr()), "tcn_dropout_apply")
+    return y
+
+
+def dropout_keep_mask(nrows, ncols, p, seed, stream_id, device):
+    """The keep-mask the kernels use for (seed, stream_id): uint8 (nrows, ncols).  For tests."""
+    lib = _lib.load()
+    keep = torch.empty(nrows, ncols, device=device, dtype=torch.uint8)
+    _lib.check(lib.tcn_dropout_mask(_lib.ptr(keep), nrows, ncols, float(p), int(seed) & 0xFFFFFFFF,
+                                    int(stream_id) & 0xFFFFFFFF, _lib.stream_ptr()), "tcn_dropout_mask")
+    return keep
+
+
+def sgd_step(params_flat, grads_flat, lr, weight_decay=0.0, grad_scale=1.0):
+    lib = _lib.load()
+    _lib.check(lib.tcn_sgd_step(_lib.ptr(params_flat), _lib.ptr(grads_flat), params_flat.numel(), float(lr),
+                                float(weight_decay), float(grad_scale), _lib.stream_ptr()), "tcn_sgd_step")
+
+
+def tap_shifts(dilation: int, causal: bool):
+    d = int(dilation)
+    return (-2 * d, -d, 0) if causal else (-d, 0, d)
+
+
+def new_seed() -> int:
+    return int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+
+
+# ------------------------------------------------------------------------------------ autograd
+class TapGemmFn(torch.autograd.Function):
+    """y = sum_tap x[r + s_tap] W[:, :, tap]^T + bias (+ residual), packed time-major rows."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, lay, shifts, x_unpadded, colscale):
+        x = _f32c(x)
+        n_out, c_in = weight.shape[0], weight.shape[1]
+        wf = prep_weight(weight)
+        res = _f32c(residual) if residual is not None else None
+        y = tapgemm(x, wf, lay, c_in, n_out, shifts, bias=_f32c(bias.detach()) if bias is not None else None,
+                    residual=res, x_unpadded=x_unpadded, colscale=colscale)
+        ctx.save_for_backward(x, weight)
+        ctx.lay, ctx.shifts, ctx.x_unpadded, ctx.colscale = lay, tuple(shifts), x_unpadded, colscale
+        ctx.has_bias, ctx.has_res = bias is not None, residual is not None
+        ctx.res_ld = res.shape[1] if res is not None else 0
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        lay, shifts = ctx.lay, ctx.shifts
+        gy = _f32c(gy)
+        n_out, c_in = weight.shape[0], weight.shape[1]
+        gx = gw = gb = gres = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            gw = torch.zeros_like(weight, dtype=torch.float32).contiguous()
+            gb = torch.zeros(n_out, device=gy.device, dtype=torch.float32) if ctx.has_bias else None
+            wgrad(gy, x, lay, n_out, c_in, shifts, gw.view(n_out, c_in, -1), gb, x_unpadded=ctx.x_unpadded,
+                  colscale=ctx.colscale)
+        if ctx.needs_input_grad[0]:
+            assert not ctx.x_unpadded, "input gradient for unpadded inputs is not needed on this path"
+            wft = prep_weight(weight, transpose=True)
+            gx = tapgemm(gy, wft, lay, min(round_up(n_out, 4), gy.shape[1]), c_in, tuple(-s for s in shifts),
+                         ldy=x.shape[1])
+        if ctx.has_res and ctx.needs_input_grad[3]:
+            gres = gy if gy.shape[1] == ctx.res_ld else gy[:, :ctx.res_ld]
+        return gx, gw, gb, gres, None, None, None, None
+
+
+def tap_linear(x, weight, bias, lay, shifts=(0,), residual=None, x_unpadded=False, colscale=None):
+    return TapGemmFn.apply(x, weight, bias, residual, lay, tuple(shifts), x_unpadded, colscale)
+
+
+class DilatedResidualFn(torch.autograd.Function):
+    """y = x + Dropout_p(W2 relu(W1 (*)_d x + b1) + b2)   (network.py:178-198), packed rows x C.
+
+    Forward keeps x and h = relu(u); backward regenerates the dropout mask from (seed, stream id).
+    """
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, lay, dilation, causal, p, seed, stream_id):
+        x = _f32c(x)
+        Cc = w1.shape[0]
+        shifts = tap_shifts(dilation, causal)
+        h = tapgemm(x, prep_weight(w1), lay, Cc, Cc, shifts, bias=_f32c(b1.detach()), relu=True)
+        y = tapgemm(h, prep_weight(w2), lay, Cc, Cc, (0,), bias=_f32c(b2.detach()), residual=x, drop_p=p, seed=seed,
+                    stream_id=stream_id)
+        ctx.save_for_backward(x, h, w1, w2)
+        ctx.lay, ctx.shifts, ctx.p, ctx.seed, ctx.stream_id = lay, shifts, p, seed, stream_id
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, h, w1, w2 = ctx.saved_tensors
+        lay, shifts, p = ctx.lay, ctx.shifts, ctx.p
+        gy = _f32c(gy)
+        Cc = w1.shape[0]
+        gv = dropout_apply(gy, p, ctx.seed, ctx.stream_id) if p > 0 else gy
+        gw2 = torch.zeros(Cc, Cc, 1, device=gy.device, dtype=torch.float32)
+        gb2 = torch.zeros(Cc, device=gy.device, dtype=torch.float32)
+        wgrad(gv, h, lay, Cc, Cc, (0,), gw2, gb2)
+        gu = tapgemm(gv, prep_weight(w2, transpose=True), lay, Cc, Cc, (0,), relu_mask=h)
+        gw1 = torch.zeros(Cc, Cc, 3, device=gy.device, dtype=torch.float32)
+        gb1 = torch.zeros(Cc, device=gy.device, dtype=torch.float32)
+        wgrad(gu, x, lay, Cc, Cc, shifts, gw1, gb1)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = tapgemm(gu, prep_weight(w1, transpose=True), lay, Cc, Cc, tuple(-s for s in shifts), residual=gy)
+        return gx, gw1, gb1, gw2.view_as(w2), gb2, None, None, None, None, None, None
+
+
+def dilated_residual(x, w1, b1, w2, b2, lay, dilation, causal=False, p=0.0, seed=0, stream_id=0):
+    return DilatedResidualFn.apply(x, w1, b1, w2, b2, lay, int(dilation), bool(causal), float(p), int(seed),
+                                   int(stream_id))

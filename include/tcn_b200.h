@@ -1,0 +1,133 @@
+/* tcn_b200 -- C ABI of the B200-native temporal-head library (libtcn_b200.so).
+ *
+ * The reference (CIAM-Group/ComputerVision_Codes) has no FFI: its interface for this path is the
+ * nn.Module constructor / forward / state_dict of
+ *   MT4MTLKD/Temporal_tenco/network.py   (== TERL/0_5fold_TCN_black/network.py)
+ *   MT4MTLKD/Temporal_mstct/MSTCT/*.py, MT4MTLKD/Temporal_mstct/network.py
+ * and the loss arithmetic inlined in the run scripts.  Each entry point below names the reference
+ * symbol (file:line, relative to the reference root) whose arithmetic it replaces; the Python
+ * mirror in computervision_codes_b200/ binds them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; nothing here allocates;
+ *   - all functions return 0 on success and a negative TCN_ERR_* code otherwise, never throw, and
+ *     leave a message for tcn_last_error() (thread local);
+ *   - `stream` is a cudaStream_t; calls only enqueue work (no host synchronisation);
+ *   - activations are TIME-MAJOR fp32: row = frame, columns = channels, row stride `ld*`;
+ *     frames of a batch of sequences are packed along the row axis, each sequence starting at a
+ *     multiple of 128 rows ("padded rows"); `meta` is an array of `nblk` int4 records, one per
+ *     128-row block: {lo, hi, in_delta, seq} = valid row range of the owning sequence, the offset
+ *     to add to a padded row to index caller-owned unpadded per-frame arrays, sequence index.
+ */
+#ifndef TCN_B200_H_
+#define TCN_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCN_OK 0
+#define TCN_ERR_INVALID_ARG (-1)
+#define TCN_ERR_UNSUPPORTED (-2)
+#define TCN_ERR_CUDA (-3)
+
+#define TCN_VERSION 100
+
+typedef struct CUstream_st* tcn_stream_t;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int tcn_version(void);
+const char* tcn_last_error(void);
+/* compute capability of the current device and the architecture the kernels were built for (100) */
+int tcn_device_info(int* cc_major, int* cc_minor, int* num_sms, int* built_for_sm);
+
+/* ---- weights ---------------------------------------------------------------------------------- */
+/* Re-orders a torch Conv1d / Linear weight (n_out, c_in, ntaps) into the fragment-ordered, hi/lo
+ * split buffer the tensor-core kernels read.  transpose=1 builds the operand of the input-gradient
+ * pass (contraction over n_out).  Call once per optimizer step per weight. */
+long long tcn_prep_weight_floats(int n_out, int c_in, int ntaps, int transpose);
+int tcn_prep_weight(const float* w, int n_out, int c_in, int ntaps, int transpose, float* wf, tcn_stream_t stream);
+
+/* ---- generic tap GEMM ---------------------------------------------------------------------------
+ * y[r, n] = epi( sum_tap sum_c x[r + shift[tap], c] * W[n, c, tap] + bias[n] ), taps that leave the
+ * sequence contribute zero.  epi = relu -> (* [relu_mask > 0]) -> dropout(p, seed, stream id) ->
+ * (+ residual).  Replaces nn.Conv1d (k = 1 or 3, any dilation, zero padding / causal front padding)
+ * and nn.Linear wherever the reference applies them per frame:
+ *   network.py:113,129 (stage projection), :114-115,189-190 (layer convs), :74,98-106 (FPN lateral),
+ *   :21-24,63-67 (heads); Temporal_mstct/MSTCT/Temporal_Encoder.py:12,15,57-59,139 ; TS_Mixer.py:10,39-48. */
+typedef struct {
+  const float* x; int ldx; int x_unpadded;      /* x_unpadded: rows of x are addressed with meta.in_delta */
+  const float* colscale; int colscale_ld;       /* optional per-(sequence, input column) scale of x */
+  const float* wf;                              /* from tcn_prep_weight */
+  const float* bias;                            /* [n_out] or NULL */
+  float* y; int ldy;
+  const float* residual; int ldr;               /* NULL or (rows, n_out) added after dropout */
+  const float* relu_mask; int ldm;              /* NULL or (rows, n_out): output zeroed where mask <= 0 */
+  const int* meta; int nblk;
+  int c_in; int n_out; int ntaps; int shift[3];
+  int relu;
+  float drop_p; unsigned drop_seed; unsigned drop_stream;
+} tcn_tapgemm_args;
+int tcn_tapgemm(const tcn_tapgemm_args* args, tcn_stream_t stream);
+
+/* dw[n, c, tap] += sum_r g[r, n] * x[r + shift[tap], c] ;  db[n] += sum_r g[r, n]   (fp32 atomics).
+ * The weight / bias gradients of the same layers. */
+typedef struct {
+  const float* g; int ldg; int g_cols;          /* g_cols: readable columns (multiple of 4, pads are zero) */
+  const float* x; int ldx; int x_unpadded;
+  const float* colscale; int colscale_ld;
+  const int* meta; int nblk;
+  int n_out; int c_in; int ntaps; int shift[3];
+  float* dw; float* db;                         /* db may be NULL */
+} tcn_wgrad_args;
+int tcn_wgrad(const tcn_wgrad_args* args, tcn_stream_t stream);
+
+/* ---- losses ------------------------------------------------------------------------------------
+ * Sigmoid-BCE over concatenated heads: nn.BCEWithLogitsLoss(pos_weight) as composed by
+ * MT4MTLKD/Temporal_tenco/run.py:190-212, TERL/0_5fold_TCN_black/run.py:307-343,
+ * MT4MTLKD/Spatial_cnn/run.py:159-162 and Temporal_mstct/run.py:185-196.
+ * loss[h] += sum over rows and over the columns of head h of row_scale(r) * col_unit[c] * bce;
+ * dl = d(sum_h head_weight_h * loss[h]) / d logits * grad_scale, with col_scale = head_weight * col_unit.
+ * With meta: row_scale(r) = row_scale / T_seq (per-video mean, then mean over videos);
+ * without: row_scale(r) = row_scale. */
+typedef struct {
+  const float* logits; int ldl;
+  const unsigned char* labels; int ldlab; int lab_unpadded;
+  const int* meta; int nrows; int ncols; int zero_cols;
+  const float* pos_w; const float* col_scale; const float* col_unit; const int* col_head;
+  float row_scale;
+  float* loss;                                  /* [8] accumulators */
+  float* dl; int lddl; float grad_scale;
+} tcn_bce_args;
+int tcn_bce_rows(const tcn_bce_args* args, tcn_stream_t stream);
+
+/* DistillKL.forward (MT4MTLKD/Spatial_cnn/run.py:284-295; Spatial_transformer/run.py:290-300):
+ * *loss += loss_scale * T^2/N * KL(softmax(t/T) || softmax(ys/T)),  t = sigmoid(yt) if teacher_sigmoid
+ * (run.py:180-182);  gys = grad_scale * T * (softmax(ys/T) - softmax(t/T)) / N. */
+int tcn_kd_kl_rows(const float* ys, int lds, const float* yt, int ldt, int teacher_sigmoid, int nrows, int K, float T,
+                   float* loss, float loss_scale, float* gys, int ldg, float grad_scale, tcn_stream_t stream);
+
+/* nn.MSELoss feature-KD (Spatial_cnn/run.py:187-191,328): *loss += loss_scale * mean((a-b)^2). */
+int tcn_mse(const float* a, const float* b, long long n, float* loss, float loss_scale, float* ga, float grad_scale,
+            tcn_stream_t stream);
+
+/* Softmax cross-entropy (7-way phase head; no reference counterpart). */
+int tcn_ce_rows(const float* x, int ldx, const int* target, const int* meta, int tgt_unpadded, int nrows, int K,
+                float row_scale, float* loss, float* gx, int ldg, float grad_scale, tcn_stream_t stream);
+
+/* ---- dropout / optimizer -----------------------------------------------------------------------
+ * Counter-based dropout keyed by (seed, stream id, row, column): nn.Dropout() of the residual layers
+ * (network.py:175,191) and Dropout2d over input channels (network.py:117,125-127). */
+int tcn_dropout_apply(const float* x, int ldx, float* y, int ldy, int nrows, int ncols, float p, unsigned seed,
+                      unsigned stream_id, tcn_stream_t stream);
+int tcn_dropout_mask(unsigned char* keep, int nrows, int ncols, float p, unsigned seed, unsigned stream_id,
+                     tcn_stream_t stream);
+/* torch.optim.SGD(lr, weight_decay), no momentum (Temporal_tenco/run.py:345-346), over a flat buffer:
+ * p -= lr * (grad_scale * g + weight_decay * p). */
+int tcn_sgd_step(float* params, const float* grads, long long n, float lr, float weight_decay, float grad_scale,
+                 tcn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCN_B200_H_ */

@@ -1,0 +1,302 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the golden fixtures.  GPU only.
+
+Bars (BASELINE.json north_star): per-frame logits within 1e-3 max-abs at fp32 accumulation, loss
+within 1e-4 relative, argmax identical.  The 3xTF32 kernels sit far inside: activations are held
+to 2e-5 here so that a regression shows up long before the contractual bar.
+"""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _no_tf32_in_any_torch_reference():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a)).float()
+
+
+def _maxabs(a, b):
+    return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
+
+
+def test_tapgemm_and_wgrad_against_fp64():
+    from computervision_codes_b200 import ops
+    from computervision_codes_b200.layout import SeqLayout
+
+    torch.manual_seed(0)
+    for (lengths, c_in, n_out, shifts) in [([70], 24, 16, (0,)), ([300, 17], 64, 131, (0,)),
+                                           ([129, 128, 5], 40, 64, (-3, 0, 3)), ([200], 16, 16, (-256, -128, 0)),
+                                           ([50, 260], 2048, 64, (0,)), ([140], 100, 72, (-1, 0, 1))]:
+        lay = SeqLayout(lengths, DEV)
+        ntaps = len(shifts)
+        xs = [torch.randn(T, c_in, dtype=torch.float64) for T in lengths]
+        w = torch.randn(n_out, c_in, ntaps, dtype=torch.float64) / (c_in * ntaps) ** 0.5
+        b = torch.randn(n_out, dtype=torch.float64)
+        gs = [torch.randn(T, n_out, dtype=torch.float64) for T in lengths]
+        x_rows = torch.zeros(lay.rows, c_in)
+        g_rows = torch.zeros(lay.rows, (n_out + 3) // 4 * 4)
+        for s, T in enumerate(lengths):
+            x_rows[lay.starts[s]:lay.starts[s] + T] = xs[s].float()
+            g_rows[lay.starts[s]:lay.starts[s] + T, :n_out] = gs[s].float()
+        x_rows, g_rows = x_rows.to(DEV), g_rows.to(DEV)
+        wf = ops.prep_weight(w.float().to(DEV))
+        y = ops.tapgemm(x_rows, wf, lay, c_in, n_out, shifts, bias=b.float().to(DEV))
+        dw = torch.zeros(n_out, c_in, ntaps, device=DEV)
+        db = torch.zeros(n_out, device=DEV)
+        ops.wgrad(g_rows, x_rows, lay, n_out, c_in, shifts, dw, db)
+        wft = ops.prep_weight(w.float().to(DEV), transpose=True)
+        gx = ops.tapgemm(g_rows, wft, lay, g_rows.shape[1], c_in, tuple(-s for s in shifts), ldy=c_in)
+        dw_ref = torch.zeros_like(w)
+        db_ref = torch.zeros_like(b)
+        for s, T in enumerate(lengths):
+            xb = xs[s].t().unsqueeze(0)
+            ref = O.conv_taps(xb, w, b, shifts)[0].t()
+            got = y[lay.starts[s]:lay.starts[s] + T, :n_out]
+            scale = float(ref.abs().max())
+            assert _maxabs(got, ref) <= 3e-6 * max(scale, 1.0) + 2e-6 * c_in ** 0.5, (lengths, c_in, n_out, shifts)
+            gb_ = gs[s].t().unsqueeze(0)
+            for k, sh in enumerate(shifts):
+                dw_ref[:, :, k] += torch.einsum("bot,bct->oc", gb_, O.shift_time(xb, sh))
+            db_ref += gs[s].sum(0)
+            gx_ref = sum(torch.einsum("oc,bot->bct", w[:, :, k], O.shift_time(gb_, -sh))
+                         for k, sh in enumerate(shifts))[0].t()
+            assert _maxabs(gx[lay.starts[s]:lay.starts[s] + T], gx_ref) <= 1e-5 * max(float(gx_ref.abs().max()), 1.0)
+        assert _maxabs(dw, dw_ref) <= 2e-5 * max(float(dw_ref.abs().max()), 1.0)
+        assert _maxabs(db, db_ref) <= 2e-5 * max(float(db_ref.abs().max()), 1.0)
+        # pad rows / pad columns of the output stay zero
+        if y.shape[1] > n_out:
+            assert float(y[:, n_out:].abs().max()) == 0.0
+
+
+def test_layers_against_golden(golden_dir):
+    from computervision_codes_b200.tcn import DilatedResidualCausalLayer, DilatedResidualLayer
+
+    z = _load(golden_dir, "tcn_layers.npz")
+    for i in range(int(z["num_cases"])):
+        tag = f"c{i}."
+        causal = str(z[tag + "kind"]) == "causal"
+        d = int(z[tag + "dilation"])
+        cls = DilatedResidualCausalLayer if causal else DilatedResidualLayer
+        m = cls(d, 16, 16).to(DEV).eval()
+        m.load_state_dict({k[len(tag) + 3:]: _t(z[k]) for k in z.files if k.startswith(tag + "sd.")})
+        x = _t(z[tag + "x"]).to(DEV).requires_grad_(True)
+        y = m(x)
+        assert y.shape == x.shape
+        assert _maxabs(y, _t(z[tag + "y"])) <= 2e-5, (tag, _maxabs(y, _t(z[tag + "y"])))
+        y.backward(_t(z[tag + "gy"]).to(DEV))
+        assert _maxabs(x.grad, _t(z[tag + "gx"])) <= 2e-5
+        for k, v in m.named_parameters():
+            ref = _t(z[tag + "grad." + k])
+            assert _maxabs(v.grad, ref) <= 2e-5 * max(1.0, float(ref.abs().max())), (tag, k)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("C,T,B,d", [(64, 1800, 1, 512), (64, 999, 2, 1), (64, 10, 3, 1024), (32, 300, 2, 16),
+                                     (512, 200, 1, 4)])
+def test_layer_against_oracle_fp64(causal, C, T, B, d):
+    from computervision_codes_b200.tcn import DilatedResidualCausalLayer, DilatedResidualLayer
+
+    torch.manual_seed(C + T + d)
+    cls = DilatedResidualCausalLayer if causal else DilatedResidualLayer
+    m = cls(d, C, C).to(DEV).eval()
+    x = torch.randn(B, C, T)
+    gy = torch.randn(B, C, T)
+    xg = x.to(DEV).requires_grad_(True)
+    y = m(xg)
+    y.backward(gy.to(DEV))
+    ws = [m.conv_dilated.weight, m.conv_dilated.bias, m.conv_1x1.weight, m.conv_1x1.bias]
+    wd = [w.detach().double().cpu() for w in ws]
+    yr = O.dilated_residual_layer(x.double(), *wd, d, causal=causal)
+    refs = O.layer_backward_closed_form(x.double(), gy.double(), *wd, d, causal=causal)
+    assert _maxabs(y, yr) <= 2e-5
+    assert _maxabs(xg.grad, refs[0]) <= 2e-5
+    for w, r in zip(ws, refs[1:]):
+        assert _maxabs(w.grad, r.reshape(w.shape)) <= 3e-5 * max(1.0, float(r.abs().max())), (C, T, d)
+
+
+def test_layer_train_mode_dropout_matches_oracle_with_same_mask():
+    from computervision_codes_b200 import ops
+    from computervision_codes_b200.layout import SeqLayout
+
+    torch.manual_seed(5)
+    B, C, T, d, p = 2, 64, 300, 4, 0.5
+    lay = SeqLayout.uniform(B, T, DEV)
+    x = torch.randn(B, C, T)
+    gy = torch.randn(B, C, T)
+    w1, b1 = torch.randn(C, C, 3) / (3 * C) ** 0.5, torch.randn(C) * 0.1
+    w2, b2 = torch.randn(C, C, 1) / C ** 0.5, torch.randn(C) * 0.1
+    prm = [t.to(DEV).requires_grad_(True) for t in (w1, b1, w2, b2)]
+    xr = lay.pad_bct(x.to(DEV)).requires_grad_(True)
+    seed, sid = 1234, 7
+    y = ops.dilated_residual(xr, *prm, lay, d, False, p, seed, sid)
+    y.backward(lay.pad_bct(gy.to(DEV)))
+    keep_rows = ops.dropout_keep_mask(lay.rows, C, p, seed, sid, DEV)
+    keep = lay.as_bct(keep_rows.float(), C).double().cpu()
+    frac = float(keep.mean())
+    assert 0.47 < frac < 0.53
+    wd = [t.double() for t in (w1, b1, w2, b2)]
+    yr = O.dilated_residual_layer(x.double(), *wd, d, keep=keep, p=p)
+    refs = O.layer_backward_closed_form(x.double(), gy.double(), *wd, d, keep=keep, p=p)
+    assert _maxabs(lay.as_bct(y, C), yr) <= 3e-5
+    assert _maxabs(lay.as_bct(xr.grad, C), refs[0]) <= 3e-5
+    for w, r in zip(prm, refs[1:]):
+        assert _maxabs(w.grad, r.reshape(w.shape)) <= 3e-5 * max(1.0, float(r.abs().max()))
+    # a different stream id gives a different mask
+    other = ops.dropout_keep_mask(lay.rows, C, p, seed, sid + 1, DEV)
+    assert float((other != keep_rows).float().mean()) > 0.4
+
+
+def test_stage_against_golden(golden_dir):
+    from computervision_codes_b200.tcn import BaseCausalTCN, Refinement
+
+    z = _load(golden_dir, "tcn_stage.npz")
+    args = types.SimpleNamespace(output=False, hier=False)
+    for tag, causal in (("acausal", False), ("causal", True)):
+        pg = BaseCausalTCN(6, 32, 40, 7, causal=causal).to(DEV).eval()
+        rf = Refinement(args, 6, 32, 7, 7, None, causal=causal).to(DEV).eval()
+        pg.load_state_dict({k[len(tag) + 7:]: _t(z[k]) for k in z.files if k.startswith(tag + ".sd.PG.")})
+        rf.load_state_dict({k[len(tag) + 9:]: _t(z[k]) for k in z.files if k.startswith(tag + ".sd.Rs.0.")})
+        x = _t(z[tag + ".x"]).to(DEV)
+        f0, l0 = pg(x.permute(0, 2, 1))
+        f1, l1 = rf(f0)
+        for got, name in ((f0, "f0"), (l0, "l0"), (f1, "f1"), (l1, "l1")):
+            ref = _t(z[f"{tag}.{name}"])
+            assert got.shape == ref.shape
+            assert _maxabs(got, ref) <= 5e-5, (tag, name, _maxabs(got, ref))
+        assert torch.equal(l1.argmax(1).cpu(), _t(z[tag + ".l1"]).argmax(1))  # phase predictions identical
+
+
+def test_videonas_against_golden(golden_dir):
+    from computervision_codes_b200.tcn import VideoNas
+
+    z = _load(golden_dir, "tcn_videonas.npz")
+    nl_pg, nl_r, n_r, C, D, K, T, B = [int(v) for v in z["cfg"]]
+    args = types.SimpleNamespace(fpn=True, output=False, feature=False, trans=False, mask=False, hier=False)
+    m = VideoNas(args, nl_pg, nl_r, n_r, C, D, K).to(DEV).eval()
+    m.load_state_dict({k[3:]: _t(z[k]) for k in z.files if k.startswith("sd.")})
+    x = _t(z["x"]).to(DEV)
+    outs = m(x, False)
+    for name, lst in zip(("ivt", "i", "v", "t", "f"), (outs[0], outs[1], outs[2], outs[3], outs[4])):
+        assert len(lst) == 4
+        for lvl, t in enumerate(lst):
+            ref = _t(z[f"out_{name}.{lvl}"])
+            assert t.shape == ref.shape
+            assert _maxabs(t, ref) <= 1e-4, (name, lvl, _maxabs(t, ref))
+            if name != "f":
+                assert torch.equal(t.argmax(1).cpu(), ref.argmax(1))
+    # the reference's own loss glue (torch BCEWithLogitsLoss on our outputs), then backward
+    labels = [_t(z["label_" + n]).to(DEV) for n in "ivtq"]
+    bce = torch.nn.BCEWithLogitsLoss()
+    terms = [sum(bce(pd[0].transpose(0, 1), y) for pd in lst)
+             for lst, y in zip((outs[1], outs[2], outs[3], outs[0]), labels)]
+    loss = 0.1 * (terms[0] + terms[1] + terms[2]) + terms[3]
+    assert abs(float(loss) - float(z["loss"])) <= 1e-4 * abs(float(z["loss"]))
+    loss.backward()
+    nograd = set(str(s) for s in z["nograd"])
+    for k, v in m.named_parameters():
+        if "grad." + k in z.files:
+            ref = _t(z["grad." + k])
+            assert v.grad is not None, k
+            assert _maxabs(v.grad, ref) <= 2e-5 * max(1.0, float(ref.abs().max())) + 1e-6, (k, _maxabs(v.grad, ref))
+        else:
+            assert k in nograd and v.grad is None, k  # stays None so SGD weight decay skips it, as in the reference
+
+    # fused loss path == the reference composition (tenco and TERL variants)
+    from computervision_codes_b200 import losses
+    from computervision_codes_b200.layout import SeqLayout
+
+    lay = SeqLayout.uniform(B, T, DEV)
+    m.zero_grad(set_to_none=True)
+    f_rows, logit_rows = m.forward_packed(x.contiguous(), lay)
+    lab = losses.pack_labels(*[l.long() for l in labels])
+    total, li, lv, lt, livt = losses.tenco_loss(logit_rows, lab, lay)
+    assert abs(float(total) - float(z["loss"])) <= 1e-4 * abs(float(z["loss"]))
+    np.testing.assert_allclose([float(li), float(lv), float(lt), float(livt)], z["loss_terms"], rtol=1e-4)
+    total.backward()
+    for k, v in m.named_parameters():
+        if "grad." + k in z.files:
+            ref = _t(z["grad." + k])
+            assert _maxabs(v.grad, ref) <= 2e-5 * max(1.0, float(ref.abs().max())) + 1e-6, (k, _maxabs(v.grad, ref))
+    with torch.no_grad():
+        _, li, lv, lt, livt = losses.tenco_loss(logit_rows, lab, lay, terl_pos_weight=True)
+    np.testing.assert_allclose([float(li), float(lv), float(lt), float(livt)], z["terl_loss_terms"], rtol=1e-4)
+
+
+def test_kd_losses_against_golden(golden_dir):
+    from computervision_codes_b200 import losses
+
+    z = _load(golden_dir, "kd_loss.npz")
+    kl = losses.DistillKL(4.0)
+    for i in range(int(z["num_kl"])):
+        ys = _t(z[f"kl{i}.ys"]).to(DEV).requires_grad_(True)
+        ytl = _t(z[f"kl{i}.yt_logits"]).to(DEV)
+        ref = float(z[f"kl{i}.loss"])
+        for fused in (False, True):
+            ys.grad = None
+            loss = kl(ys, ytl if fused else torch.sigmoid(ytl), teacher_is_logits=fused)
+            assert abs(float(loss) - ref) <= 1e-4 * abs(ref) + 1e-8
+            loss.backward()
+            assert _maxabs(ys.grad, _t(z[f"kl{i}.gys"])) <= 1e-6
+    logits = [_t(z[f"comp.logits{k}"]).to(DEV).requires_grad_(True) for k in range(4)]
+    labels = [_t(z[f"comp.labels{k}"]).to(DEV) for k in range(4)]
+    teach = [_t(z[f"comp.teach{k}"]).to(DEV) for k in range(3)]
+    feats = [_t(z[f"comp.feat{k}"]).to(DEV).requires_grad_(True) for k in range(3)]
+    tfeats = [_t(z[f"comp.tfeat{k}"]).to(DEV) for k in range(3)]
+    crit = losses.MultiTeacherKDLoss(temp=4.0, rates=(1.0, 1.0, 1.0))
+    loss, hard, soft, kd = crit(logits, labels, teach, feats, tfeats)
+    np.testing.assert_allclose([float(loss), float(hard), float(soft), float(kd)], z["comp.loss"], rtol=1e-4)
+    loss.backward()
+    for k in range(4):
+        assert _maxabs(logits[k].grad, _t(z[f"comp.glogits{k}"])) <= 1e-6
+    for k in range(3):
+        assert _maxabs(feats[k].grad, _t(z[f"comp.gfeat{k}"])) <= 1e-6
+    # phase head (parity unpinned: textbook definition)
+    torch.manual_seed(3)
+    x = torch.randn(1800, 7, device=DEV, requires_grad=True)
+    y = torch.randint(0, 7, (1800,), device=DEV)
+    got = losses.phase_cross_entropy(x, y)
+    ref = O.phase_ce(x.detach().double().cpu(), y.cpu())
+    assert abs(float(got) - float(ref)) <= 1e-5 * float(ref)
+    got.backward()
+    xr = x.detach().double().cpu().requires_grad_(True)
+    O.phase_ce(xr, y.cpu()).backward()
+    assert _maxabs(x.grad, xr.grad) <= 1e-7
+
+
+def test_videonas_cfg_baseline_shape_vs_oracle():
+    """BASELINE-shaped instantiation (C=64, D=2048, one 1,800-frame video): logits <= 1e-3, argmax identical."""
+    from computervision_codes_b200.tcn import VideoNas
+
+    args = types.SimpleNamespace(fpn=True, output=False, feature=False, trans=False, mask=False, hier=False)
+    torch.manual_seed(0)
+    m = VideoNas(args, 11, 10, 3, 64, 2048, 100).eval()
+    x = torch.randn(1, 1800, 2048)
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref = O.videonas_forward(x, sd)
+    m = m.to(DEV)
+    with torch.no_grad():
+        outs = m(x.to(DEV), False)
+    for a_list, r_list in zip(outs[:4], ref[:4]):
+        for a, r in zip(a_list, r_list):
+            assert _maxabs(a, r) <= 1e-3
+            assert torch.equal(a.argmax(1).cpu(), r.argmax(1))
+            assert torch.equal((a > 0).cpu(), r > 0) or float(((a > 0).cpu() != (r > 0)).float().mean()) < 1e-5

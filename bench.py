@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- temporal-head train frames/s (BASELINE.json metric) on N B200s of one node.
+
+Workload (BASELINE.json configs[1]): one 5-fold training epoch schedule over 45 synthetic
+CholecT45-shaped videos (seeded ragged lengths 900..3600 frames, 2048-d fp32 features, 100/6/10/15
+multi-label heads), VideoNas(fpn, 11/10/3 layers, 64 channels), data-parallel by video.  One "step"
+= every rank runs forward + loss + backward over its next batch of `--videos-per-step` videos, then
+one all-reduce of the flat gradient buffer and one SGD update.
+
+  python bench.py [--gpus N --steps K --warmup W]          this repo's CUDA path
+  python bench.py --impl reference ...                     CPU arm: the oracle port on the host cores
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CROSSVAL = {  # cholect45-crossval test folds, MT4MTLKD/Temporal_tenco/dataloader.py:131-137
+    1: [79, 2, 51, 6, 25, 14, 66, 23, 50], 2: [80, 32, 5, 15, 40, 47, 26, 48, 70],
+    3: [31, 57, 36, 18, 52, 68, 10, 8, 73], 4: [42, 29, 60, 27, 65, 75, 22, 49, 12],
+    5: [78, 43, 62, 35, 74, 1, 56, 4, 13],
+}
+D_FEAT, C_MAPS, HEADS = 2048, 64, (100, 6, 10, 15)
+LAYERS = (11, 10, 3)
+
+
+def video_table():
+    vids = sorted(v for f in CROSSVAL.values() for v in f)
+    rng = np.random.RandomState(45)
+    lengths = rng.randint(900, 3600, size=len(vids))
+    return vids, {v: int(t) for v, t in zip(vids, lengths)}
+
+
+def fold_schedule():
+    """155 training passes: for each fold the 31 videos that are neither its test fold nor its
+    5-video validation subset (first five of the next fold), in fold order."""
+    vids, lengths = video_table()
+    passes = []
+    for k in range(1, 6):
+        test = set(CROSSVAL[k])
+        val = set(CROSSVAL[k % 5 + 1][:5])
+        passes += [v for v in vids if v not in test and v not in val]
+    return passes, lengths
+
+
+def make_video(v, T, pinned):
+    g = torch.Generator().manual_seed(1000 + v)
+    x = torch.randn(T, D_FEAT, generator=g)
+    lab = (torch.rand(T, 132, generator=g) < 0.05).to(torch.uint8)
+    lab[:, 131] = 0
+    if pinned:
+        x, lab = x.pin_memory(), lab.pin_memory()
+    return x, lab
+
+
+def build_model(device):
+    from computervision_codes_b200.tcn import VideoNas
+
+    args = types.SimpleNamespace(fpn=True, output=False, feature=False, trans=False, mask=False, hier=False)
+    torch.manual_seed(0)
+    return VideoNas(args, *LAYERS, C_MAPS, D_FEAT, HEADS[0]).to(device).train()
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_arm(steps, warmup, budget_s=25.0):
+    """The oracle's torch-CPU port (oracle/torch_port.py) of the same train step, on the host cores:
+    forward + tenco loss + backward, train mode, one video per step, thread count swept."""
+    from oracle import torch_port as P
+
+    passes, lengths = fold_schedule()
+    model = build_model("cpu")
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    vids = passes[: max(1, min(3, steps))]
+    data = []
+    for v in vids:
+        x, lab = make_video(v, lengths[v], pinned=False)
+        y = lab[:, :131].float()
+        data.append((x.unsqueeze(0), (y[:, 100:106], y[:, 106:116], y[:, 116:131], y[:, 0:100]), lengths[v]))
+
+    def one(x, labels):
+        for p in params.values():
+            p.grad = None
+        loss = P.train_step_loss(x, params, labels, train=True)
+        loss.backward()
+        return float(loss)
+
+    ncpu = os.cpu_count() or 1
+    cands = sorted({n for n in (1, 2, 4, 8, 16, 32, 64, ncpu) if n <= ncpu})
+    best = None
+    t_start = time.time()
+    for n in cands:
+        torch.set_num_threads(n)
+        one(*data[0][:2])  # warm-up
+        t0 = time.time()
+        frames = 0
+        for x, labels, T in data:
+            one(x, labels)
+            frames += T
+        dt = time.time() - t0
+        fps = frames / dt
+        if best is None or fps > best[0]:
+            best = (fps, n, dt / len(data))
+        if time.time() - t_start > budget_s:
+            break
+    return {"value": best[0], "unit": "frames/s", "cores": best[1], "kind": "port",
+            "sample": f"{len(data)} videos ({sum(d[2] for d in data)} frames) of the same schedule, fwd+loss+bwd, "
+                      f"train mode, torch {torch.__version__} CPU (oneDNN), best of threads {cands}, host has {ncpu} cpus",
+            "ms_per_video": best[2] * 1e3}
+
+
+# --------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--videos-per-step", type=int, default=1, help="videos per rank per step (ragged batch)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "cfg2: 5-fold epoch schedule over 45 synthetic CholecT45-shaped videos "
+                          "(ragged 900..3600 frames, seed 45), VideoNas(fpn, 11/10/3, C=64, D=2048, heads 100/6/10/15), "
+                          "tenco BCE loss, SGD(lr 1e-2, wd 1e-5)",
+              "videos_per_rank_per_step": a.videos_per_step, "parallelism": f"dp{world}-by-video",
+              "l2": "inputs cycle through the 0.8 GB feature set (>> 126 MB L2); no explicit flush"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_arm(a.steps, a.warmup, budget_s=60.0)
+        line = {"impl": "reference", "metric": "temporal-head train frames/s", "value": cb["value"], "unit": "frames/s",
+                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": cb["ms_per_video"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (use --impl reference for the CPU arm)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+        pg = torch.distributed.group.WORLD
+
+    from computervision_codes_b200 import _lib
+    from computervision_codes_b200.trainer import TemporalTrainer
+
+    _lib.load()
+    model = build_model(dev)
+    trainer = TemporalTrainer(model, lr=1e-2, weight_decay=1e-5, process_group=pg, world_size=world)
+
+    passes, lengths = fold_schedule()
+    mine = passes[rank::world]
+    V = a.videos_per_step
+    nsteps_total = a.warmup + a.steps
+    # batches this rank will run (cycled over its shard of the schedule)
+    batches = [[mine[(s * V + j) % len(mine)] for j in range(V)] for s in range(nsteps_total)]
+    needed = sorted({v for b in batches for v in b})
+    host = {v: make_video(v, lengths[v], pinned=True) for v in needed}
+    resident = {v: (x.to(dev), lab.to(dev)) for v, (x, lab) in host.items()}
+
+    def batch_dev(b):
+        if len(b) == 1:
+            return resident[b[0]][0], resident[b[0]][1], [lengths[b[0]]]
+        return (torch.cat([resident[v][0] for v in b]), torch.cat([resident[v][1] for v in b]), [lengths[v] for v in b])
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(run_step, nb):
+        for s in range(a.warmup):
+            run_step(nb[s])
+        barrier()
+        clocks = ClockSampler(local_rank)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(a.warmup, nsteps_total):
+            run_step(nb[s])
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        ck = clocks.stop()
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item()), ck
+
+    # ---- arm 1: inputs resident in HBM
+    pre = [batch_dev(b) for b in batches] if V == 1 else None
+
+    def step_resident(b):
+        x, lab, lens = pre[batches.index(b)] if pre is not None else batch_dev(b)
+        trainer.step(x, lab, lens)
+
+    ms_total, clocks = timed(step_resident, batches)
+    frames_rank = sum(lengths[v] for b in batches[a.warmup:] for v in b)
+    fr = torch.tensor([frames_rank], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(fr)
+    frames_all = float(fr.item())
+    value = frames_all / (ms_total * 1e-3)
+
+    # ---- arm 2: end to end through the public API with HOST (pinned) inputs, H2D + D2H inside
+    loss_host = torch.empty(5, dtype=torch.float32).pin_memory()
+    h2d = [0]
+
+    def step_e2e(b):
+        xs = [host[v][0].to(dev, non_blocking=True) for v in b]
+        ls = [host[v][1].to(dev, non_blocking=True) for v in b]
+        h2d[0] = sum(t.numel() * t.element_size() for t in xs + ls)
+        x = xs[0] if len(b) == 1 else torch.cat(xs)
+        lab = ls[0] if len(b) == 1 else torch.cat(ls)
+        out = trainer.step(x, lab, [lengths[v] for v in b])
+        loss_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ms_e2e, _ = timed(step_e2e, batches)
+    e2e_value = frames_all / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (residual-layer kernels), timed live with CUDA events
+    roof = measure_layer_roofline(model, resident, lengths, batches[a.warmup], dev)
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    cb = None if a.no_cpu_baseline or world > 1 else cpu_arm(a.steps, a.warmup)
+    launches = count_launches(trainer, batch_dev(batches[a.warmup])) * a.steps
+    line = {"metric": "temporal-head train frames/s", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)",
+            "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": 20,
+                    "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": launches, "roofline": roof}
+    if cb is not None:
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def count_launches(trainer, batch):
+    """Kernels of this library launched by one step (counted through the ctypes call log)."""
+    from computervision_codes_b200 import _lib
+
+    lib = _lib.load()
+    counted = [0]
+    names = [n for n in _lib.SIGNATURES if n not in ("tcn_version", "tcn_last_error", "tcn_device_info",
+                                                      "tcn_prep_weight_floats")]
+    originals = {}
+    for n in names:
+        fn = getattr(lib, n)
+        originals[n] = fn
+
+        def wrap(*args, _fn=fn):
+            counted[0] += 1
+            return _fn(*args)
+        setattr(lib, n, wrap)
+    try:
+        trainer.step(*batch)
+        torch.cuda.synchronize()
+    finally:
+        for n, fn in originals.items():
+            setattr(lib, n, fn)
+    return counted[0]
+
+
+def measure_layer_roofline(model, resident, lengths, batch, dev):
+    """Average duration of the residual-layer forward launch(es), CUDA events on the launch stream."""
+    from computervision_codes_b200 import ops
+    from computervision_codes_b200.layout import SeqLayout
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, src = 6650.0, "fallback"
+    if os.path.exists(peaks_path):
+        peak, src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
+    lens = [lengths[v] for v in batch]
+    lay = SeqLayout.get(lens, dev)
+    frames = sum(lens)
+    x = torch.randn(lay.rows, C_MAPS, device=dev)
+    layer = model.PG.layers[3]
+    with torch.no_grad():
+        for _ in range(3):
+            layer._run_packed(x, lay)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 20
+        e0.record()
+        for _ in range(n):
+            layer._run_packed(x, lay)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    alg_bytes = 8 * C_MAPS * frames  # fused layer fwd = 8*C bytes per frame
+    achieved = alg_bytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "residual layer forward (tapgemm x2 + weight prep, unfused v1)",
+            "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "frames_per_launch": frames, "ms_per_launch": ms}
+
+
+if __name__ == "__main__":
+    main()

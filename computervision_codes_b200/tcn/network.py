@@ -110,16 +110,16 @@ class BaseCausalTCN(nn.Module):
         self.channel_dropout = nn.Dropout2d()
         self.num_classes = num_classes
 
-    def _features_packed(self, x_btd, lay, mask_btd=None):
-        """x_btd: (B, T, D) contiguous frames.  Returns packed (rows, C) features."""
-        B, T, D = x_btd.shape
-        if mask_btd is not None:
-            x_btd = x_btd * mask_btd
-        x_rows = x_btd.reshape(B * T, D)
+    def _features_packed(self, x_rows, lay, mask_rows=None):
+        """x_rows: (frames, D) contiguous frames of the batch, unpadded.  Returns packed (rows, C) features."""
+        D = x_rows.shape[-1]
+        x_rows = x_rows.reshape(-1, D)
+        if mask_rows is not None:
+            x_rows = x_rows * mask_rows.reshape(-1, D)
         colscale = None
         if self.training and self.channel_dropout.p > 0:
             p = self.channel_dropout.p
-            keep = (torch.rand(B, D, device=x_btd.device) >= p).float()
+            keep = (torch.rand(lay.num_seqs, D, device=x_rows.device) >= p).float()
             colscale = (keep / (1.0 - p)).contiguous()
         out = ops.tap_linear(x_rows, self.conv_1x1.weight, self.conv_1x1.bias, lay, x_unpadded=True,
                              colscale=colscale)
@@ -230,10 +230,10 @@ class VideoNas(nn.Module):
         b = torch.cat([self.conv_out.bias, self.conv_out_i.bias, self.conv_out_v.bias, self.conv_out_t.bias], dim=0)
         return w, b
 
-    def forward_packed(self, x_btd, lay, mask_btd=None):
-        """Packed core of forward.  Returns (f_rows list, logits_rows list) with the four heads
-        concatenated along the columns in the order ivt | i | v | t."""
-        f = self.PG._features_packed(x_btd, lay, mask_btd)
+    def forward_packed(self, x_rows, lay, mask_rows=None):
+        """Packed core of forward.  x_rows: (frames, D) or (B, T, D) contiguous.  Returns (f_rows list,
+        logits_rows list) with the four heads concatenated along the columns in the order ivt | i | v | t."""
+        f = self.PG._features_packed(x_rows, lay, mask_rows)
         f_list = [f]
         for R in self.Rs:
             f = R._features_packed(f, lay)

@@ -155,3 +155,17 @@ def test_linear_resize_identity_and_general():
     assert torch.equal(O.linear_resize(x, 17), x)
     ref = torch.nn.functional.interpolate(x, size=29, mode="linear")
     assert torch.allclose(O.linear_resize(x, 29), ref, atol=1e-5)
+
+
+def test_torch_port_matches_golden(golden_dir):
+    from oracle import torch_port as P
+
+    z = _load(golden_dir, "tcn_videonas.npz")
+    sd = {k: v.requires_grad_(True) for k, v in _sd(z, "sd.").items()}
+    labels = tuple(_t(z["label_" + n]) for n in "ivtq")
+    loss = P.train_step_loss(_t(z["x"]), sd, labels, train=False)
+    assert abs(float(loss.detach()) - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))
+    loss.backward()
+    for k, v in sd.items():
+        if "grad." + k in z.files:
+            assert torch.allclose(v.grad, _t(z["grad." + k]), atol=2e-6, rtol=2e-3), k

@@ -299,4 +299,5 @@ def test_videonas_cfg_baseline_shape_vs_oracle():
         for a, r in zip(a_list, r_list):
             assert _maxabs(a, r) <= 1e-3
             assert torch.equal(a.argmax(1).cpu(), r.argmax(1))
-            assert torch.equal((a > 0).cpu(), r > 0) or float(((a > 0).cpu() != (r > 0)).float().mean()) < 1e-5
+            flips = (a > 0).cpu() != (r > 0)   # sigmoid > 0.5 decisions: only ties (|logit| ~ 0) may differ
+            assert float(r[flips].abs().max()) < 1e-4 if bool(flips.any()) else True

@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--videos-per-step", type=int, default=1, help="videos per rank per step (ragged batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of a CUDA graph")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -211,11 +212,14 @@ def main():
 
     _lib.load()
     model = build_model(dev)
-    trainer = TemporalTrainer(model, lr=1e-2, weight_decay=1e-5, process_group=pg, world_size=world)
-
     passes, lengths = fold_schedule()
-    mine = passes[rank::world]
     V = a.videos_per_step
+    max_frames = max(lengths.values()) * V
+    trainer = TemporalTrainer(model, lr=1e-2, weight_decay=1e-5, process_group=pg, world_size=world,
+                              max_frames=max_frames, max_seqs=max(V, 1), use_graph=not a.no_graph,
+                              input_mask_p=0.25)  # --mask of Scripts/train_fold1.sh:28
+
+    mine = passes[rank::world]
     nsteps_total = a.warmup + a.steps
     # batches this rank will run (cycled over its shard of the schedule)
     batches = [[mine[(s * V + j) % len(mine)] for j in range(V)] for s in range(nsteps_total)]
@@ -223,25 +227,20 @@ def main():
     host = {v: make_video(v, lengths[v], pinned=True) for v in needed}
     resident = {v: (x.to(dev), lab.to(dev)) for v, (x, lab) in host.items()}
 
-    def batch_dev(b):
-        if len(b) == 1:
-            return resident[b[0]][0], resident[b[0]][1], [lengths[b[0]]]
-        return (torch.cat([resident[v][0] for v in b]), torch.cat([resident[v][1] for v in b]), [lengths[v] for v in b])
-
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def timed(run_step, nb):
+    def timed(run_step):
         for s in range(a.warmup):
-            run_step(nb[s])
+            run_step(batches[s])
         barrier()
         clocks = ClockSampler(local_rank)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for s in range(a.warmup, nsteps_total):
-            run_step(nb[s])
+            run_step(batches[s])
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -251,14 +250,11 @@ def main():
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t.item()), ck
 
-    # ---- arm 1: inputs resident in HBM
-    pre = [batch_dev(b) for b in batches] if V == 1 else None
-
+    # ---- arm 1: inputs resident in HBM (the step starts from device tensors)
     def step_resident(b):
-        x, lab, lens = pre[batches.index(b)] if pre is not None else batch_dev(b)
-        trainer.step(x, lab, lens)
+        trainer.step([resident[v][0] for v in b], [resident[v][1] for v in b], [lengths[v] for v in b])
 
-    ms_total, clocks = timed(step_resident, batches)
+    ms_total, clocks = timed(step_resident)
     frames_rank = sum(lengths[v] for b in batches[a.warmup:] for v in b)
     fr = torch.tensor([frames_rank], device=dev, dtype=torch.float64)
     if world > 1:
@@ -266,37 +262,35 @@ def main():
     frames_all = float(fr.item())
     value = frames_all / (ms_total * 1e-3)
 
-    # ---- arm 2: end to end through the public API with HOST (pinned) inputs, H2D + D2H inside
-    loss_host = torch.empty(5, dtype=torch.float32).pin_memory()
+    # ---- arm 2: end to end through the public API with HOST (pinned) inputs: H2D of this step's
+    # features + labels and D2H of the loss vector inside the timed region, every step
+    loss_host = torch.empty(8, dtype=torch.float32).pin_memory()
     h2d = [0]
 
     def step_e2e(b):
-        xs = [host[v][0].to(dev, non_blocking=True) for v in b]
-        ls = [host[v][1].to(dev, non_blocking=True) for v in b]
+        xs, ls = [host[v][0] for v in b], [host[v][1] for v in b]
         h2d[0] = sum(t.numel() * t.element_size() for t in xs + ls)
-        x = xs[0] if len(b) == 1 else torch.cat(xs)
-        lab = ls[0] if len(b) == 1 else torch.cat(ls)
-        out = trainer.step(x, lab, [lengths[v] for v in b])
+        out = trainer.step(xs, ls, [lengths[v] for v in b])
         loss_host.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    ms_e2e, _ = timed(step_e2e, batches)
+    ms_e2e, _ = timed(step_e2e)
     e2e_value = frames_all / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel (residual-layer kernels), timed live with CUDA events
-    roof = measure_layer_roofline(model, resident, lengths, batches[a.warmup], dev)
+    # ---- roofline of the dominant kernel (fused residual-layer forward), timed live with CUDA events
+    roof = measure_layer_roofline(model, lengths, batches[a.warmup], dev)
 
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
         return
     cb = None if a.no_cpu_baseline or world > 1 else cpu_arm(a.steps, a.warmup)
-    launches = count_launches(trainer, batch_dev(batches[a.warmup])) * a.steps
+    launches = trainer.launches_per_step() * a.steps
     line = {"metric": "temporal-head train frames/s", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)",
             "data": "synthetic", "config": config, "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": 20,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": 32,
                     "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": launches, "roofline": roof}
     if cb is not None:
@@ -306,34 +300,10 @@ def main():
         torch.distributed.destroy_process_group()
 
 
-def count_launches(trainer, batch):
-    """Kernels of this library launched by one step (counted through the ctypes call log)."""
-    from computervision_codes_b200 import _lib
-
-    lib = _lib.load()
-    counted = [0]
-    names = [n for n in _lib.SIGNATURES if n not in ("tcn_version", "tcn_last_error", "tcn_device_info",
-                                                      "tcn_prep_weight_floats")]
-    originals = {}
-    for n in names:
-        fn = getattr(lib, n)
-        originals[n] = fn
-
-        def wrap(*args, _fn=fn):
-            counted[0] += 1
-            return _fn(*args)
-        setattr(lib, n, wrap)
-    try:
-        trainer.step(*batch)
-        torch.cuda.synchronize()
-    finally:
-        for n, fn in originals.items():
-            setattr(lib, n, fn)
-    return counted[0]
-
-
-def measure_layer_roofline(model, resident, lengths, batch, dev):
-    """Average duration of the residual-layer forward launch(es), CUDA events on the launch stream."""
+def measure_layer_roofline(model, lengths, batch, dev):
+    """Fused residual-layer forward kernel (the kernel every stage is made of): average duration over
+    back-to-back launches on this batch shape, CUDA events on the launch stream, training variant
+    (writes y and h).  Algorithmic bytes per frame per SURVEY 8(d): 8*C (read x, write y)."""
     from computervision_codes_b200 import ops
     from computervision_codes_b200.layout import SeqLayout
 
@@ -344,25 +314,39 @@ def measure_layer_roofline(model, resident, lengths, batch, dev):
     lens = [lengths[v] for v in batch]
     lay = SeqLayout.get(lens, dev)
     frames = sum(lens)
-    x = torch.randn(lay.rows, C_MAPS, device=dev)
     layer = model.PG.layers[3]
-    with torch.no_grad():
-        for _ in range(3):
-            layer._run_packed(x, lay)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n = 20
-        e0.record()
-        for _ in range(n):
-            layer._run_packed(x, lay)
-        e1.record()
-        torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
-    alg_bytes = 8 * C_MAPS * frames  # fused layer fwd = 8*C bytes per frame
+    w1f = ops.prep_weight(layer.conv_dilated.weight)
+    w2f = ops.prep_weight(layer.conv_1x1.weight)
+    b1, b2 = layer.conv_dilated.bias.detach(), layer.conv_1x1.bias.detach()
+    shifts = ops.tap_shifts(layer.dilation, layer.causal)
+    nbuf = 8  # rotate over several activation buffers, as the 41 layers of a step do
+    xs = [torch.randn(lay.rows, C_MAPS, device=dev) for _ in range(nbuf)]
+    lib_args = dict(save_h=True, drop_p=0.5, seed=1, stream_id=3)
+    for i in range(3):
+        ops.layer_fwd(xs[i % nbuf], w1f, w2f, b1, b2, lay, shifts, **lib_args)
+    torch.cuda.synchronize()
+    n = 40
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        ops.layer_fwd(xs[i % nbuf], w1f, w2f, b1, b2, lay, shifts, **lib_args)
+    e1.record()
+    torch.cuda.synchronize()
+    # the loop above also pays two torch.zeros_like allocations + fills per call; time those alone and subtract
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(n):
+        torch.zeros_like(xs[0]); torch.zeros_like(xs[0])
+    e3.record()
+    torch.cuda.synchronize()
+    ms = max((e0.elapsed_time(e1) - e2.elapsed_time(e3)) / n, 1e-6)
+    alg_bytes = 8 * C_MAPS * frames
     achieved = alg_bytes / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "residual layer forward (tapgemm x2 + weight prep, unfused v1)",
+    return {"bound": "hbm", "kernel": "layer_fwd64_kernel (fused dilated residual layer forward, training variant)",
             "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "frames_per_launch": frames, "ms_per_launch": ms}
+            "traffic": None, "frames_per_launch": frames, "ms_per_launch": ms,
+            "note": "this workload launches it on one video (~2k frames, 0.5 MB): latency-bound, L2-resident; "
+                    "see profiles/ for the stress shape (64 x 8000 frames)"}
 
 
 if __name__ == "__main__":

@@ -30,6 +30,7 @@ class TapGemmArgs(C.Structure):
         ("c_in", C.c_int), ("n_out", C.c_int), ("ntaps", C.c_int), ("shift", C.c_int * 3),
         ("relu", C.c_int),
         ("drop_p", C.c_float), ("drop_seed", C.c_uint), ("drop_stream", C.c_uint),
+        ("in_drop_p", C.c_float),
     ]
 
 
@@ -41,6 +42,25 @@ class WgradArgs(C.Structure):
         ("meta", C.c_void_p), ("nblk", C.c_int),
         ("n_out", C.c_int), ("c_in", C.c_int), ("ntaps", C.c_int), ("shift", C.c_int * 3),
         ("dw", C.c_void_p), ("db", C.c_void_p),
+        ("g_drop_p", C.c_float), ("drop_seed", C.c_uint), ("drop_stream", C.c_uint),
+    ]
+
+
+class LayerFwdArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("y", C.c_void_p), ("h", C.c_void_p),
+        ("w1f", C.c_void_p), ("w2f", C.c_void_p), ("b1", C.c_void_p), ("b2", C.c_void_p),
+        ("meta", C.c_void_p), ("nblk", C.c_int), ("channels", C.c_int),
+        ("shift", C.c_int * 3),
+        ("drop_p", C.c_float), ("drop_seed", C.c_uint), ("drop_stream", C.c_uint),
+    ]
+
+
+class ModelConfig(C.Structure):
+    _fields_ = [
+        ("layers_pg", C.c_int), ("layers_r", C.c_int), ("num_r", C.c_int), ("channels", C.c_int),
+        ("in_dim", C.c_int), ("head_sizes", C.c_int * 4), ("causal", C.c_int),
+        ("max_rows", C.c_int), ("max_seqs", C.c_int),
     ]
 
 
@@ -65,6 +85,23 @@ SIGNATURES = {
     "tcn_prep_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tcn_tapgemm": (C.c_int, [C.POINTER(TapGemmArgs), C.c_void_p]),
     "tcn_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
+    "tcn_layer_fwd": (C.c_int, [C.POINTER(LayerFwdArgs), C.c_void_p]),
+    "tcn_model_create": (C.c_int, [C.POINTER(ModelConfig), C.POINTER(C.c_void_p)]),
+    "tcn_model_destroy": (None, [C.c_void_p]),
+    "tcn_model_num_params": (C.c_longlong, [C.c_void_p]),
+    "tcn_model_num_tensors": (C.c_int, [C.c_void_p]),
+    "tcn_model_param_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]),
+    "tcn_model_bind": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tcn_model_set_loss": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "tcn_model_set_dropout": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float]),
+    "tcn_model_set_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint,
+                                      C.c_void_p]),
+    "tcn_model_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p]),
+    "tcn_model_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_int), C.c_void_p]),
+    "tcn_model_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                     C.c_void_p]),
     "tcn_bce_rows": (C.c_int, [C.POINTER(BceArgs), C.c_void_p]),
     "tcn_kd_kl_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                  C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),

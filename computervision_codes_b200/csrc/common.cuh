@@ -21,6 +21,12 @@ int num_sms();
     }                                          \
   } while (0)
 
+#define TCN_CHECK(expr)            \
+  do {                             \
+    const int rc__ = (expr);       \
+    if (rc__ != TCN_OK) return rc__; \
+  } while (0)
+
 // Per-128-row block metadata of the packed, time-major activation layout.
 //   lo, hi : valid row range [lo, hi) of the sequence that owns this block (padded-row coordinates,
 //            lo is a multiple of 128)
@@ -31,6 +37,23 @@ struct __align__(16) BlkMeta {
   int lo, hi, in_delta, seq;
 };
 constexpr int kBlkRows = 128;
+
+// Batch descriptor living in device memory so that a captured CUDA graph can be replayed on batches
+// of a different shape: kernels launched with a non-null `dyn` read nblk / num_seqs from here.
+struct __align__(16) BatchDesc {
+  int nblk, rows, num_seqs, frames;
+  unsigned seed;  // dropout seed of this step
+  int pad[3];
+};
+
+// One (weight tensor, orientation) pair of the batched weight preparation.
+struct PrepJob {
+  long first;    // exclusive prefix of float4 outputs
+  long src_off;  // float offset of the torch-layout weight in the flat parameter buffer
+  int n_out, c_in, ntaps, transpose, NT8, kpt;
+};
+int launch_prep_batched(const PrepJob* jobs_dev, int njobs, const float* params, float* wf_base, long total_f4,
+                        cudaStream_t stream);
 
 // ----------------------------------------------------------------------------------------------
 // device helpers
@@ -60,19 +83,37 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 // Fragment layout (g = lane >> 2, t = lane & 3):
 //   a0:(g, t) a1:(g+8, t) a2:(g, t+4) a3:(g+8, t+4);  b0:(k=t, n=g) b1:(k=t+4, n=g)
 //   d0:(g, 2t) d1:(g, 2t+1) d2:(g+8, 2t) d3:(g+8, 2t+1)
+// Not volatile: independent accumulator chains must be free to interleave.
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// 3-term split product: acc += a * b with ~fp32 accuracy (small cross terms first).
-__device__ __forceinline__ void mma_3xtf32(float (&d)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4],
-                                           uint32_t b0hi, uint32_t b1hi, uint32_t b0lo, uint32_t b1lo) {
-  mma_tf32(d, alo, b0hi, b1hi);
-  mma_tf32(d, ahi, b0lo, b1lo);
-  mma_tf32(d, ahi, b0hi, b1hi);
+// acc[MT][NT] += A * B with the 3-term split (small cross terms first), issued as three sweeps over
+// the MT*NT independent accumulators so that consecutive MMAs never depend on each other.
+template <int MT, int NT>
+__device__ __forceinline__ void mma_block_3xtf32(float (&acc)[MT][NT][4], const uint32_t (&ahi)[MT][4],
+                                                 const uint32_t (&alo)[MT][4], const uint32_t (&bhi)[NT][2],
+                                                 const uint32_t (&blo)[NT][2], int ntc = NT) {
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+    if (nt < ntc) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][nt], alo[mt], bhi[nt][0], bhi[nt][1]);
+    }
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+    if (nt < ntc) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][nt], ahi[mt], blo[nt][0], blo[nt][1]);
+    }
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+    if (nt < ntc) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][nt], ahi[mt], bhi[nt][0], bhi[nt][1]);
+    }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -108,5 +149,116 @@ __host__ __device__ __forceinline__ uint32_t drop_thresh(float p) {
   if (v > 4294967295.0) v = 4294967295.0;
   return (uint32_t)v;
 }
+// scale (1/(1-p)) if kept, 0 if dropped
+__device__ __forceinline__ float drop_factor(uint32_t seed, uint32_t stream, uint32_t thresh, float scale, int row,
+                                             int col) {
+  return (drop_hash(seed, stream, (uint32_t)row, (uint32_t)col) >= thresh) ? scale : 0.f;
+}
+
+// ----------------------------------------------------------------------------------------------
+// internal launchers shared by the C ABI wrappers and the whole-model executor (model.cu)
+struct TapGemmDev {
+  const float* X;
+  int ldx;
+  int x_unpadded;
+  const float* colscale;
+  int colscale_ld;
+  const float4* Wf;
+  const float* bias;
+  float* Y;
+  int ldy;
+  const float* R;
+  int ldr;
+  const float* M;
+  int ldm;
+  const BlkMeta* meta;
+  int nblk;
+  const BatchDesc* dyn;  // nullable: overrides nblk at run time
+  int kpt;               // padded K per tap (multiple of 8)
+  int c_in;
+  int n_out;
+  int NT8;
+  int ntaps;
+  int shift[3];
+  int relu;
+  // dropout on the output (forward) ...
+  uint32_t drop_thresh;
+  float drop_scale;
+  uint32_t drop_seed, drop_stream;
+  // ... or on the A operand as it is loaded (backward: gv = keep * gy / (1 - p))
+  uint32_t in_drop_thresh;
+  float in_drop_scale;
+  uint32_t in_drop_seed, in_drop_stream;
+};
+int launch_tapgemm(TapGemmDev& p, int grid_cap_blocks, cudaStream_t stream);
+
+struct WgradDev {
+  const float* G;
+  int ldg;
+  int g_cols;  // readable columns of G (>= n_out, multiple of 4, pad columns must be zero)
+  const float* X;
+  int ldx;
+  int x_unpadded;
+  const float* colscale;
+  int colscale_ld;
+  const BlkMeta* meta;
+  int nblk;
+  const BatchDesc* dyn;
+  int n_out, c_in, ntaps;
+  int shift[3];
+  float* dW;
+  float* db;
+  int n_tiles, c_tiles, row_splits;
+  uint32_t g_drop_thresh;  // dropout applied to G as it is loaded
+  float g_drop_scale;
+  uint32_t g_drop_seed, g_drop_stream;
+  uint32_t x_drop_thresh;  // keep-mask applied to X as it is loaded (input masking of the projection)
+  float x_drop_scale;
+  uint32_t x_drop_seed, x_drop_stream;
+};
+int launch_wgrad(WgradDev& p, int cap_nblk, cudaStream_t stream);
+
+struct BceDev {
+  const float* logits;
+  int ldl;
+  const uint8_t* labels;
+  int ldlab;
+  int lab_unpadded;
+  const BlkMeta* meta;  // nullptr: plain (nrows x K) problem
+  int nrows;            // padded rows (meta) or plain rows
+  const BatchDesc* dyn; // nullable: rows / num_seqs read at run time (row_scale_const = 1/num_seqs)
+  int ncols;
+  int zero_cols;
+  const float* pos_w;
+  const float* col_scale;
+  const float* col_unit;
+  const int* col_head;
+  float row_scale_const;
+  float* loss;
+  float* dL;
+  int lddl;
+  float grad_scale;
+};
+int launch_bce(const BceDev& p, int cap_rows, cudaStream_t stream);
+int launch_chan_scale(float* out, int ld, int max_seqs, const BatchDesc* dyn, float p, uint32_t seed,
+                      uint32_t stream_id, cudaStream_t stream);
+
+struct LayerFwdDev {
+  const float* X;   // (rows, 64)
+  float* Y;         // (rows, 64)
+  float* H;         // (rows, 64) relu(u), saved for backward; nullable (inference)
+  const float4* W1f;  // fragment-ordered, KS = 24, NT8 = 8
+  const float4* W2f;  // KS = 8, NT8 = 8
+  const float* b1;
+  const float* b2;
+  const BlkMeta* meta;
+  int nblk;
+  const BatchDesc* dyn;
+  int shift[3];
+  uint32_t drop_thresh;
+  float drop_scale;
+  uint32_t drop_seed, drop_stream;
+};
+int launch_layer_fwd64(const LayerFwdDev& p, int cap_nblk, cudaStream_t stream);
 
 }  // namespace tcn

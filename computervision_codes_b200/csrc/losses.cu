@@ -14,43 +14,25 @@ namespace tcn {
 
 constexpr int kMaxHeads = 8;
 
-struct BceDev {
-  const float* logits;
-  int ldl;
-  const uint8_t* labels;
-  int ldlab;
-  int lab_unpadded;
-  const BlkMeta* meta;  // nullptr: plain (nrows x K) problem, row_scale_const applies
-  int nrows;            // padded rows (meta) or plain rows
-  int ncols;
-  int zero_cols;  // dL columns [ncols, zero_cols) are written as zeros
-  const float* pos_w;      // [ncols] or nullptr
-  const float* col_scale;  // [ncols]  head_weight / K_head
-  const int* col_head;     // [ncols]  head index < kMaxHeads
-  float row_scale_const;   // plain mode: 1 / nrows ; meta mode: 1 / num_seqs (times 1/T_seq per row)
-  float* loss;             // [kMaxHeads] accumulated with atomicAdd: sum over rows/cols of row_scale*col_scale/head_w-free
-  float* dL;               // nullable
-  int lddl;
-  float grad_scale;
-};
-
 // loss[h] accumulates  sum_{r, c in head h} row_scale(r) * col_unit(c) * bce(r, c),  col_unit = 1 / K_head
 // (so that loss[h] is the reference's mean-BCE of head h, averaged over the sequences of the batch);
 // dL carries the full chain factor col_scale(c) (= head_weight / K_head) * row_scale(r) * grad_scale.
-__global__ void __launch_bounds__(256) bce_rows_kernel(const BceDev p, const float* __restrict__ col_unit) {
+__global__ void __launch_bounds__(256) bce_rows_kernel(const BceDev p) {
   __shared__ float red[8][kMaxHeads];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float part[kMaxHeads];
 #pragma unroll
   for (int h = 0; h < kMaxHeads; ++h) part[h] = 0.f;
 
-  for (int row = blockIdx.x * 8 + warp; row < p.nrows; row += gridDim.x * 8) {
-    float rs = p.row_scale_const;
+  const int nrows = p.dyn ? p.dyn->rows : p.nrows;
+  const float rsc = p.dyn ? 1.f / (float)p.dyn->num_seqs : p.row_scale_const;
+  for (int row = blockIdx.x * 8 + warp; row < nrows; row += gridDim.x * 8) {
+    float rs = rsc;
     int lrow = row;
     if (p.meta != nullptr) {
       const BlkMeta m = p.meta[row / kBlkRows];
       if (row >= m.hi) continue;
-      rs = p.row_scale_const / (float)(m.hi - m.lo);
+      rs = rsc / (float)(m.hi - m.lo);
       if (p.lab_unpadded) lrow = row + m.in_delta;
     }
     const float* x = p.logits + (size_t)row * p.ldl;
@@ -65,7 +47,7 @@ __global__ void __launch_bounds__(256) bce_rows_kernel(const BceDev p, const flo
         const float sp = log1pf(expf(-fabsf(xv))) + fmaxf(-xv, 0.f);
         const float l = (1.f - yv) * xv + lw * sp;
         const int h = __ldg(p.col_head + c);
-        const float lu = rs * __ldg(col_unit + c) * l;
+        const float lu = rs * __ldg(p.col_unit + c) * l;
 #pragma unroll
         for (int k = 0; k < kMaxHeads; ++k) part[k] += (k == h) ? lu : 0.f;
         if (p.dL != nullptr) {
@@ -232,6 +214,37 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, l
   }
 }
 
+int launch_bce(const BceDev& p, int cap_rows, cudaStream_t stream) {
+  const long rows = cap_rows > 0 ? cap_rows : p.nrows;
+  long b = (rows + 7) / 8;
+  const long cap = (long)num_sms() * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  bce_rows_kernel<<<(int)b, 256, 0, stream>>>(p);
+  return check_launch("bce_rows_kernel");
+}
+
+// keep / (1 - p) per (sequence, input channel): Dropout2d over whole input channels
+// (MT4MTLKD/Temporal_tenco/network.py:117,125-127)
+__global__ void chan_scale_kernel(float* __restrict__ out, int ld, int max_seqs, const BatchDesc* dyn, uint32_t thresh,
+                                  float scale, uint32_t seed0, uint32_t stream_id) {
+  const int nseq = dyn ? dyn->num_seqs : max_seqs;
+  const uint32_t seed = seed0 ^ (dyn ? dyn->seed : 0u);
+  const long total = (long)nseq * ld;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int s = (int)(i / ld), d = (int)(i - (long)s * ld);
+    out[i] = drop_factor(seed, stream_id, thresh, scale, s, d);
+  }
+}
+int launch_chan_scale(float* out, int ld, int max_seqs, const BatchDesc* dyn, float p, uint32_t seed,
+                      uint32_t stream_id, cudaStream_t stream) {
+  long b = ((long)max_seqs * ld + 255) / 256;
+  if (b > 1024) b = 1024;
+  chan_scale_kernel<<<(int)b, 256, 0, stream>>>(out, ld, max_seqs, dyn, drop_thresh(p), 1.f / (1.f - p), seed,
+                                               stream_id);
+  return check_launch("chan_scale_kernel");
+}
+
 }  // namespace tcn
 
 using namespace tcn;
@@ -254,8 +267,8 @@ extern "C" int tcn_bce_rows(const tcn_bce_args* a, tcn_stream_t stream) {
   p.meta = reinterpret_cast<const BlkMeta*>(a->meta); p.nrows = a->nrows; p.ncols = a->ncols;
   p.zero_cols = a->zero_cols; p.pos_w = a->pos_w; p.col_scale = a->col_scale; p.col_head = a->col_head;
   p.row_scale_const = a->row_scale; p.loss = a->loss; p.dL = a->dl; p.lddl = a->lddl; p.grad_scale = a->grad_scale;
-  bce_rows_kernel<<<grid_for(a->nrows, 8, num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(p, a->col_unit);
-  return check_launch("bce_rows_kernel");
+  p.col_unit = a->col_unit; p.dyn = nullptr;
+  return launch_bce(p, 0, (cudaStream_t)stream);
 }
 
 extern "C" int tcn_kd_kl_rows(const float* ys, int lds, const float* yt, int ldt, int teacher_sigmoid, int nrows,

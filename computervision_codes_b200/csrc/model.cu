@@ -1,0 +1,597 @@
+// Whole-model executor: VideoNas(fpn) forward + multi-head BCE loss + backward as one sequence of
+// kernel launches on one stream, no host synchronisation, CUDA-graph capturable.
+//
+// Mirrors VideoNas.forward (MT4MTLKD/Temporal_tenco/network.py:36-68): BaseCausalTCN (:120-135) ->
+// num_r x Refinement (:149-162, use_output = hier = False as in every reference script) -> FPN
+// (:98-106, latlayer1 three times, interpolate == identity) -> conv_out / _i / _v / _t on the four
+// levels (:63-67), and the loss of train_loop (Temporal_tenco/run.py:190-212; TERL variant
+// TERL/0_5fold_TCN_black/run.py:307-343).  Backward follows the closed forms of SURVEY.md section 8a.
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace tcn {
+
+struct TensorSlot {
+  long off, size;
+};
+
+static inline int rup(int a, int b) { return (a + b - 1) / b * b; }
+static inline long rupl(long a, long b) { return (a + b - 1) / b * b; }
+
+}  // namespace tcn
+
+using namespace tcn;
+
+struct tcn_model {
+  tcn_model_config cfg;
+  int L = 0;       // residual layers in total
+  int C = 0, D = 0, NH = 0, LDH = 0, NLVL = 4;
+  std::vector<int> stage_first;  // first global layer index of each stage (+ sentinel)
+  std::vector<int> dilation;     // per global layer
+  // flat parameter layout
+  std::vector<TensorSlot> slots;
+  long off_proj_w = 0, off_proj_b = 0, off_lat_w = 0, off_lat_b = 0, off_head_w = 0, off_head_b = 0;
+  std::vector<long> off_w1, off_b1, off_w2, off_b2;
+  long n_params = 0;
+  float* params = nullptr;
+  float* grads = nullptr;
+  // device workspace
+  char* ws = nullptr;
+  size_t ws_bytes = 0;
+  // prepared weights (float offsets into wf)
+  float* wf = nullptr;
+  long wf_floats = 0;
+  long wf_proj = 0, wf_lat = 0, wf_latT = 0, wf_head = 0, wf_headT = 0;
+  std::vector<long> wf_w1, wf_w2, wf_w1T, wf_w2T;
+  PrepJob* jobs_dev = nullptr;
+  int njobs = 0;
+  long prep_total_f4 = 0;
+  // activations
+  std::vector<float*> act, H;
+  float* P[3] = {nullptr, nullptr, nullptr};
+  float* logits[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* dL[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* Gp[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* gbuf[2] = {nullptr, nullptr};
+  float* gu = nullptr;
+  float* colscale = nullptr;
+  BatchDesc* desc = nullptr;
+  BlkMeta* meta = nullptr;
+  static constexpr int kSlots = 4;  // ring of pinned staging slots: desc followed by the block table
+  char* desc_host = nullptr;
+  cudaEvent_t slot_done[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  int slot = 0;
+  size_t slot_bytes = 0;
+  int max_blk = 0;
+  // loss tables
+  float *col_unit = nullptr, *col_scale = nullptr, *pos_w = nullptr, *loss8 = nullptr;
+  int* col_head = nullptr;
+  bool has_pos_w = false;
+  float head_w[4] = {1.f, 0.1f, 0.1f, 0.1f};
+  float input_mask_p = 0.f, chan_drop_p = 0.5f, layer_drop_p = 0.5f;
+  bool fwd_training = false;
+
+  const float* p_(long off) const { return params + off; }
+  float* g_(long off) const { return grads + off; }
+  const float4* wf_(long off) const { return reinterpret_cast<const float4*>(wf + off); }
+};
+
+namespace {
+
+constexpr uint32_t kStreamChan = 0x7fff0001u;  // dropout stream ids that cannot collide with layer indices
+constexpr uint32_t kStreamMask = 0x7fff0002u;
+
+long prep_floats(int n_out, int c_in, int ntaps, int transpose) {
+  return (long)tcn_prep_weight_floats(n_out, c_in, ntaps, transpose);
+}
+
+void add_job(std::vector<PrepJob>& jobs, long& first_f4, long src_off, int n_out, int c_in, int ntaps, int transpose) {
+  PrepJob j;
+  const int kdim = transpose ? n_out : c_in, ncols = transpose ? c_in : n_out;
+  j.first = first_f4;
+  j.src_off = src_off;
+  j.n_out = n_out; j.c_in = c_in; j.ntaps = ntaps; j.transpose = transpose;
+  j.kpt = rup(kdim, 8);
+  j.NT8 = (ncols + 7) / 8;
+  first_f4 += (long)ntaps * j.kpt / 8 * j.NT8 * 32;
+  jobs.push_back(j);
+}
+
+void layer_shifts(const tcn_model* m, int l, int* s) {
+  const int d = m->dilation[l];
+  if (m->cfg.causal) { s[0] = -2 * d; s[1] = -d; s[2] = 0; } else { s[0] = -d; s[1] = 0; s[2] = d; }
+}
+
+TapGemmDev base_tapgemm(const tcn_model* m) {
+  TapGemmDev p;
+  memset(&p, 0, sizeof(p));
+  p.meta = m->meta; p.nblk = m->max_blk; p.dyn = m->desc;
+  p.ntaps = 1; p.drop_scale = 1.f; p.in_drop_scale = 1.f;
+  return p;
+}
+
+WgradDev base_wgrad(const tcn_model* m) {
+  WgradDev p;
+  memset(&p, 0, sizeof(p));
+  p.meta = m->meta; p.nblk = m->max_blk; p.dyn = m->desc;
+  p.ntaps = 1; p.g_drop_scale = 1.f; p.x_drop_scale = 1.f;
+  return p;
+}
+
+int gemm(const tcn_model* m, TapGemmDev& p, int c_in, int n_out, cudaStream_t st) {
+  p.c_in = c_in; p.kpt = rup(c_in, 8); p.n_out = n_out; p.NT8 = (n_out + 7) / 8;
+  return launch_tapgemm(p, 0, st);
+}
+
+}  // namespace
+
+// ================================================================================================ create
+extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
+  TCN_REQUIRE(cfg && out, "tcn_model_create: null pointer");
+  TCN_REQUIRE(cfg->layers_pg > 0 && cfg->layers_r >= 0 && cfg->num_r == 3,
+              "tcn_model_create: the FPN path needs exactly 3 refinement stages (network.py:98-106)");
+  TCN_REQUIRE(cfg->channels > 0 && cfg->channels % 4 == 0 && cfg->in_dim > 0 && cfg->in_dim % 4 == 0,
+              "tcn_model_create: channels and in_dim must be multiples of 4");
+  TCN_REQUIRE(cfg->max_rows > 0 && cfg->max_rows % kBlkRows == 0 && cfg->max_seqs > 0,
+              "tcn_model_create: max_rows must be a positive multiple of 128");
+  TCN_REQUIRE(cfg->layers_pg <= 20 && cfg->layers_r <= 20, "tcn_model_create: dilation 2^i overflows");
+  tcn_model* m = new (std::nothrow) tcn_model();
+  TCN_REQUIRE(m != nullptr, "tcn_model_create: out of host memory");
+  m->cfg = *cfg;
+  m->C = cfg->channels; m->D = cfg->in_dim;
+  m->NH = cfg->head_sizes[0] + cfg->head_sizes[1] + cfg->head_sizes[2] + cfg->head_sizes[3];
+  m->LDH = rup(m->NH, 4);
+  const int C = m->C, D = m->D, NH = m->NH;
+  // ---- stages / layers
+  m->stage_first.push_back(0);
+  for (int i = 0; i < cfg->layers_pg; ++i) m->dilation.push_back(1 << i);
+  m->stage_first.push_back((int)m->dilation.size());
+  for (int s = 0; s < cfg->num_r; ++s) {
+    for (int i = 0; i < cfg->layers_r; ++i) m->dilation.push_back(1 << i);
+    m->stage_first.push_back((int)m->dilation.size());
+  }
+  m->L = (int)m->dilation.size();
+  // ---- flat parameter layout (every tensor starts on a 16-byte boundary except inside the head block)
+  long off = 0;
+  auto slot = [&](long size, bool align) {
+    if (align) off = rupl(off, 4);
+    const long o = off;
+    m->slots.push_back({o, size});
+    off += size;
+    return o;
+  };
+  m->off_proj_w = slot((long)C * D, true);
+  m->off_proj_b = slot(C, true);
+  for (int l = 0; l < m->L; ++l) {
+    m->off_w1.push_back(slot((long)C * C * 3, true));
+    m->off_b1.push_back(slot(C, true));
+    m->off_w2.push_back(slot((long)C * C, true));
+    m->off_b2.push_back(slot(C, true));
+  }
+  m->off_lat_w = slot((long)C * C, true);
+  m->off_lat_b = slot(C, true);
+  m->off_head_w = slot((long)cfg->head_sizes[0] * C, true);
+  for (int h = 1; h < 4; ++h) slot((long)cfg->head_sizes[h] * C, false);
+  m->off_head_b = slot(cfg->head_sizes[0], true);
+  for (int h = 1; h < 4; ++h) slot(cfg->head_sizes[h], false);
+  m->n_params = rupl(off, 4);
+
+  // ---- prepared-weight buffer and the batched prep job table
+  std::vector<PrepJob> jobs;
+  long f4 = 0;
+  auto reg = [&](long src, int n_out, int c_in, int ntaps, int tr) {
+    const long at = f4 * 4;
+    add_job(jobs, f4, src, n_out, c_in, ntaps, tr);
+    return at;
+  };
+  m->wf_proj = reg(m->off_proj_w, C, D, 1, 0);
+  for (int l = 0; l < m->L; ++l) {
+    m->wf_w1.push_back(reg(m->off_w1[l], C, C, 3, 0));
+    m->wf_w2.push_back(reg(m->off_w2[l], C, C, 1, 0));
+    m->wf_w1T.push_back(reg(m->off_w1[l], C, C, 3, 1));
+    m->wf_w2T.push_back(reg(m->off_w2[l], C, C, 1, 1));
+  }
+  m->wf_lat = reg(m->off_lat_w, C, C, 1, 0);
+  m->wf_latT = reg(m->off_lat_w, C, C, 1, 1);
+  m->wf_head = reg(m->off_head_w, NH, C, 1, 0);
+  m->wf_headT = reg(m->off_head_w, NH, C, 1, 1);
+  m->njobs = (int)jobs.size();
+  m->prep_total_f4 = f4;
+  m->wf_floats = f4 * 4;
+
+  // ---- workspace carve-up
+  const long rows = cfg->max_rows;
+  m->max_blk = cfg->max_rows / kBlkRows;
+  size_t bytes = 0;
+  auto carve = [&](size_t n) {
+    const size_t at = bytes;
+    bytes += (n + 255) / 256 * 256;
+    return at;
+  };
+  const size_t o_wf = carve((size_t)m->wf_floats * 4);
+  const size_t o_jobs = carve(jobs.size() * sizeof(PrepJob));
+  std::vector<size_t> o_act(m->L + 1), o_H(m->L);
+  for (int i = 0; i <= m->L; ++i) o_act[i] = carve((size_t)rows * C * 4);
+  for (int i = 0; i < m->L; ++i) o_H[i] = carve((size_t)rows * C * 4);
+  size_t o_P[3], o_log[4], o_dL[4], o_Gp[4], o_gb[2];
+  for (int i = 0; i < 3; ++i) o_P[i] = carve((size_t)rows * C * 4);
+  for (int i = 0; i < 4; ++i) o_log[i] = carve((size_t)rows * m->LDH * 4);
+  for (int i = 0; i < 4; ++i) o_dL[i] = carve((size_t)rows * m->LDH * 4);
+  for (int i = 0; i < 4; ++i) o_Gp[i] = carve((size_t)rows * C * 4);
+  for (int i = 0; i < 2; ++i) o_gb[i] = carve((size_t)rows * C * 4);
+  const size_t o_gu = carve((size_t)rows * C * 4);
+  const size_t o_cs = carve((size_t)cfg->max_seqs * D * 4);
+  const size_t o_desc = carve(sizeof(BatchDesc) + (size_t)m->max_blk * sizeof(BlkMeta));
+  const size_t o_cu = carve((size_t)m->LDH * 4), o_cscale = carve((size_t)m->LDH * 4), o_pw = carve((size_t)m->LDH * 4);
+  const size_t o_ch = carve((size_t)m->LDH * 4), o_loss = carve(64);
+  m->ws_bytes = bytes;
+  cudaError_t e = cudaMalloc(&m->ws, bytes);
+  if (e == cudaSuccess) e = cudaMemset(m->ws, 0, bytes);
+  m->slot_bytes = sizeof(BatchDesc) + (size_t)m->max_blk * sizeof(BlkMeta);
+  if (e == cudaSuccess) e = cudaMallocHost(&m->desc_host, m->slot_bytes * tcn_model::kSlots);
+  for (int i = 0; i < tcn_model::kSlots && e == cudaSuccess; ++i)
+    e = cudaEventCreateWithFlags(&m->slot_done[i], cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    set_error("tcn_model_create: allocating %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    cudaGetLastError();
+    if (m->ws) cudaFree(m->ws);
+    delete m;
+    return TCN_ERR_CUDA;
+  }
+  m->wf = reinterpret_cast<float*>(m->ws + o_wf);
+  m->jobs_dev = reinterpret_cast<PrepJob*>(m->ws + o_jobs);
+  for (int i = 0; i <= m->L; ++i) m->act.push_back(reinterpret_cast<float*>(m->ws + o_act[i]));
+  for (int i = 0; i < m->L; ++i) m->H.push_back(reinterpret_cast<float*>(m->ws + o_H[i]));
+  for (int i = 0; i < 3; ++i) m->P[i] = reinterpret_cast<float*>(m->ws + o_P[i]);
+  for (int i = 0; i < 4; ++i) {
+    m->logits[i] = reinterpret_cast<float*>(m->ws + o_log[i]);
+    m->dL[i] = reinterpret_cast<float*>(m->ws + o_dL[i]);
+    m->Gp[i] = reinterpret_cast<float*>(m->ws + o_Gp[i]);
+  }
+  for (int i = 0; i < 2; ++i) m->gbuf[i] = reinterpret_cast<float*>(m->ws + o_gb[i]);
+  m->gu = reinterpret_cast<float*>(m->ws + o_gu);
+  m->colscale = reinterpret_cast<float*>(m->ws + o_cs);
+  m->desc = reinterpret_cast<BatchDesc*>(m->ws + o_desc);
+  m->meta = reinterpret_cast<BlkMeta*>(m->ws + o_desc + sizeof(BatchDesc));
+  m->col_unit = reinterpret_cast<float*>(m->ws + o_cu);
+  m->col_scale = reinterpret_cast<float*>(m->ws + o_cscale);
+  m->pos_w = reinterpret_cast<float*>(m->ws + o_pw);
+  m->col_head = reinterpret_cast<int*>(m->ws + o_ch);
+  m->loss8 = reinterpret_cast<float*>(m->ws + o_loss);
+  e = cudaMemcpy(m->jobs_dev, jobs.data(), jobs.size() * sizeof(PrepJob), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error("tcn_model_create: job table upload failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    tcn_model_destroy(m);
+    return TCN_ERR_CUDA;
+  }
+  *out = m;
+  const float w[4] = {1.f, 0.1f, 0.1f, 0.1f};
+  return tcn_model_set_loss(m, w, nullptr);
+}
+
+extern "C" void tcn_model_destroy(tcn_model* m) {
+  if (!m) return;
+  if (m->ws) cudaFree(m->ws);
+  if (m->desc_host) cudaFreeHost(m->desc_host);
+  for (int i = 0; i < tcn_model::kSlots; ++i)
+    if (m->slot_done[i]) cudaEventDestroy(m->slot_done[i]);
+  delete m;
+}
+
+extern "C" long long tcn_model_num_params(const tcn_model* m) { return m ? m->n_params : 0; }
+extern "C" int tcn_model_num_tensors(const tcn_model* m) { return m ? (int)m->slots.size() : 0; }
+
+extern "C" int tcn_model_param_layout(const tcn_model* m, long long* offsets, long long* sizes, int n) {
+  TCN_REQUIRE(m && offsets && sizes && n == (int)m->slots.size(), "tcn_model_param_layout: bad arguments");
+  for (int i = 0; i < n; ++i) {
+    offsets[i] = m->slots[i].off;
+    sizes[i] = m->slots[i].size;
+  }
+  return TCN_OK;
+}
+
+extern "C" int tcn_model_bind(tcn_model* m, float* params, float* grads) {
+  TCN_REQUIRE(m && params, "tcn_model_bind: null pointer");
+  TCN_REQUIRE((reinterpret_cast<uintptr_t>(params) & 15) == 0 && (reinterpret_cast<uintptr_t>(grads) & 15) == 0,
+              "tcn_model_bind: buffers must be 16-byte aligned");
+  m->params = params;
+  m->grads = grads;
+  return TCN_OK;
+}
+
+extern "C" int tcn_model_set_loss(tcn_model* m, const float* head_weights, const float* pos_w_host) {
+  TCN_REQUIRE(m && head_weights, "tcn_model_set_loss: null pointer");
+  std::vector<float> unit(m->LDH, 0.f), scale(m->LDH, 0.f), pw(m->LDH, 1.f);
+  std::vector<int> head(m->LDH, 0);
+  int c = 0;
+  for (int h = 0; h < 4; ++h) {
+    m->head_w[h] = head_weights[h];
+    for (int k = 0; k < m->cfg.head_sizes[h]; ++k, ++c) {
+      unit[c] = 1.f / (float)m->cfg.head_sizes[h];
+      scale[c] = head_weights[h] / (float)m->cfg.head_sizes[h];
+      head[c] = h;
+      if (pos_w_host) pw[c] = pos_w_host[c];
+    }
+  }
+  m->has_pos_w = pos_w_host != nullptr;
+  cudaError_t e = cudaMemcpy(m->col_unit, unit.data(), unit.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(m->col_scale, scale.data(), scale.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(m->pos_w, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(m->col_head, head.data(), head.size() * 4, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error("tcn_model_set_loss: upload failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return TCN_ERR_CUDA;
+  }
+  return TCN_OK;
+}
+
+extern "C" int tcn_model_set_dropout(tcn_model* m, float input_mask_p, float chan_drop_p, float layer_drop_p) {
+  TCN_REQUIRE(m, "tcn_model_set_dropout: null pointer");
+  TCN_REQUIRE(input_mask_p >= 0.f && input_mask_p < 1.f && chan_drop_p >= 0.f && chan_drop_p < 1.f &&
+                  layer_drop_p >= 0.f && layer_drop_p < 1.f,
+              "tcn_model_set_dropout: probabilities must be in [0, 1)");
+  m->input_mask_p = input_mask_p;
+  m->chan_drop_p = chan_drop_p;
+  m->layer_drop_p = layer_drop_p;
+  return TCN_OK;
+}
+
+extern "C" int tcn_model_set_batch(tcn_model* m, const int* meta_host, int nblk, int rows, int num_seqs, int frames,
+                                   unsigned seed, tcn_stream_t stream) {
+  TCN_REQUIRE(m && meta_host, "tcn_model_set_batch: null pointer");
+  TCN_REQUIRE(nblk > 0 && nblk <= m->max_blk && rows == nblk * kBlkRows,
+              "tcn_model_set_batch: %d blocks exceed the capacity of %d (max_rows)", nblk, m->max_blk);
+  TCN_REQUIRE(num_seqs > 0 && num_seqs <= m->cfg.max_seqs, "tcn_model_set_batch: too many sequences");
+  // pinned staging slots are reused round-robin: wait until this slot's previous upload has been consumed
+  const int sl = m->slot;
+  m->slot = (m->slot + 1) % tcn_model::kSlots;
+  cudaEventSynchronize(m->slot_done[sl]);
+  BatchDesc* d = reinterpret_cast<BatchDesc*>(m->desc_host + (size_t)sl * m->slot_bytes);
+  d->nblk = nblk; d->rows = rows; d->num_seqs = num_seqs; d->frames = frames; d->seed = seed;
+  memcpy(reinterpret_cast<char*>(d) + sizeof(BatchDesc), meta_host, (size_t)nblk * sizeof(BlkMeta));
+  cudaError_t e = cudaMemcpyAsync(m->desc, d, sizeof(BatchDesc) + (size_t)nblk * sizeof(BlkMeta),
+                                  cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaEventRecord(m->slot_done[sl], (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    set_error("tcn_model_set_batch: upload failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return TCN_ERR_CUDA;
+  }
+  return TCN_OK;
+}
+
+// ================================================================================================ forward
+static int model_forward(tcn_model* m, const float* x, int training, cudaStream_t st) {
+  const int C = m->C, D = m->D, L = m->L;
+  m->fwd_training = training != 0;
+  const float pl = training ? m->layer_drop_p : 0.f;
+  // 0. weights -> fragment order (one launch)
+  TCN_CHECK(launch_prep_batched(m->jobs_dev, m->njobs, m->params, m->wf, m->prep_total_f4, st));
+  // 1. stage-input projection (network.py:113,122-129), input mask + channel dropout folded into the load
+  const bool chan = training && m->chan_drop_p > 0.f;
+  if (chan) TCN_CHECK(launch_chan_scale(m->colscale, D, m->cfg.max_seqs, m->desc, m->chan_drop_p, 0u, kStreamChan, st));
+  {
+    TapGemmDev p = base_tapgemm(m);
+    p.X = x; p.ldx = D; p.x_unpadded = 1;
+    if (chan) { p.colscale = m->colscale; p.colscale_ld = D; }
+    if (training && m->input_mask_p > 0.f) {
+      p.in_drop_thresh = drop_thresh(m->input_mask_p); p.in_drop_scale = 1.f; p.in_drop_stream = kStreamMask;
+    }
+    p.Wf = m->wf_(m->wf_proj); p.bias = m->p_(m->off_proj_b);
+    p.Y = m->act[0]; p.ldy = C;
+    TCN_CHECK(gemm(m, p, D, C, st));
+  }
+  // 2. residual layers
+  for (int l = 0; l < L; ++l) {
+    int s[3];
+    layer_shifts(m, l, s);
+    if (C == 64) {
+      LayerFwdDev p;
+      p.X = m->act[l]; p.Y = m->act[l + 1]; p.H = training ? m->H[l] : nullptr;
+      p.W1f = m->wf_(m->wf_w1[l]); p.W2f = m->wf_(m->wf_w2[l]);
+      p.b1 = m->p_(m->off_b1[l]); p.b2 = m->p_(m->off_b2[l]);
+      p.meta = m->meta; p.nblk = m->max_blk; p.dyn = m->desc;
+      for (int i = 0; i < 3; ++i) p.shift[i] = s[i];
+      p.drop_thresh = pl > 0.f ? drop_thresh(pl) : 0u;
+      p.drop_scale = pl > 0.f ? 1.f / (1.f - pl) : 1.f;
+      p.drop_seed = 0u; p.drop_stream = (uint32_t)l;
+      TCN_CHECK(launch_layer_fwd64(p, m->max_blk, st));
+    } else {
+      TapGemmDev p = base_tapgemm(m);
+      p.X = m->act[l]; p.ldx = C; p.Wf = m->wf_(m->wf_w1[l]); p.bias = m->p_(m->off_b1[l]);
+      p.Y = m->H[l]; p.ldy = C; p.ntaps = 3; p.relu = 1;
+      for (int i = 0; i < 3; ++i) p.shift[i] = s[i];
+      TCN_CHECK(gemm(m, p, C, C, st));
+      TapGemmDev q = base_tapgemm(m);
+      q.X = m->H[l]; q.ldx = C; q.Wf = m->wf_(m->wf_w2[l]); q.bias = m->p_(m->off_b2[l]);
+      q.Y = m->act[l + 1]; q.ldy = C; q.R = m->act[l]; q.ldr = C;
+      if (pl > 0.f) { q.drop_thresh = drop_thresh(pl); q.drop_scale = 1.f / (1.f - pl); q.drop_stream = (uint32_t)l; }
+      TCN_CHECK(gemm(m, q, C, C, st));
+    }
+  }
+  // 3. FPN (network.py:98-106): p4 = f3, p3 = p4 + lat(f2), p2 = p3 + lat(f1), p1 = p2 + lat(f0)
+  const float* f[4];
+  for (int s = 0; s < 4; ++s) f[s] = m->act[m->stage_first[s + 1]];
+  const float* top = f[3];
+  for (int lv = 2; lv >= 0; --lv) {
+    TapGemmDev p = base_tapgemm(m);
+    p.X = f[lv]; p.ldx = C; p.Wf = m->wf_(m->wf_lat); p.bias = m->p_(m->off_lat_b);
+    p.Y = m->P[lv]; p.ldy = C; p.R = top; p.ldr = C;
+    TCN_CHECK(gemm(m, p, C, C, st));
+    top = m->P[lv];
+  }
+  // 4. heads on the four levels (network.py:63-67), all 131 classes in one GEMM per level
+  for (int lv = 0; lv < 4; ++lv) {
+    TapGemmDev p = base_tapgemm(m);
+    p.X = lv < 3 ? m->P[lv] : f[3]; p.ldx = C; p.Wf = m->wf_(m->wf_head); p.bias = m->p_(m->off_head_b);
+    p.Y = m->logits[lv]; p.ldy = m->LDH;
+    TCN_CHECK(gemm(m, p, C, m->NH, st));
+  }
+  return TCN_OK;
+}
+
+// ================================================================================================ backward
+// gl[lv]: gradient w.r.t. the logits of level lv (rows, LDH; pad columns zero) or nullptr;
+// gf[lv]: extra gradient w.r.t. feature level lv (rows, C) or nullptr.
+static int model_backward(tcn_model* m, const float* x, const float* const* gl, const float* const* gf,
+                          cudaStream_t st) {
+  const int C = m->C, D = m->D, L = m->L, NH = m->NH, LDH = m->LDH;
+  TCN_REQUIRE(m->grads != nullptr, "tcn_model backward: no gradient buffer bound");
+  const float pl = m->fwd_training ? m->layer_drop_p : 0.f;
+  if (cudaMemsetAsync(m->grads, 0, (size_t)m->n_params * 4, st) != cudaSuccess) {
+    set_error("tcn_model backward: memset failed");
+    cudaGetLastError();
+    return TCN_ERR_CUDA;
+  }
+  const float* f[4];
+  for (int s = 0; s < 4; ++s) f[s] = m->act[m->stage_first[s + 1]];
+  const float* plv[4] = {m->P[0], m->P[1], m->P[2], f[3]};
+  // heads: weight grads, then the gradient of each FPN level, accumulated top-down (p_l feeds p_{l-1})
+  const float* prev = nullptr;
+  for (int lv = 0; lv < 4; ++lv) {
+    if (gf && gf[lv]) {
+      set_error("tcn_model backward: gradients w.r.t. the feature maps are not supported yet");
+      return TCN_ERR_UNSUPPORTED;
+    }
+    if (gl && gl[lv]) {
+      WgradDev w = base_wgrad(m);
+      w.G = gl[lv]; w.ldg = LDH; w.g_cols = LDH; w.X = plv[lv]; w.ldx = C;
+      w.n_out = NH; w.c_in = C; w.dW = m->g_(m->off_head_w); w.db = m->g_(m->off_head_b);
+      TCN_CHECK(launch_wgrad(w, m->max_blk, st));
+      TapGemmDev p = base_tapgemm(m);
+      p.X = gl[lv]; p.ldx = LDH; p.Wf = m->wf_(m->wf_headT); p.Y = m->Gp[lv]; p.ldy = C;
+      p.R = prev; p.ldr = C;
+      TCN_CHECK(gemm(m, p, LDH, C, st));
+    } else {
+      set_error("tcn_model backward: every level needs a logits gradient");
+      return TCN_ERR_UNSUPPORTED;
+    }
+    prev = m->Gp[lv];
+  }
+  // lateral weight grads: p_l = p_{l+1} + lat(f_l) for l = 0..2
+  for (int lv = 0; lv < 3; ++lv) {
+    WgradDev w = base_wgrad(m);
+    w.G = m->Gp[lv]; w.ldg = C; w.g_cols = C; w.X = f[lv]; w.ldx = C;
+    w.n_out = C; w.c_in = C; w.dW = m->g_(m->off_lat_w); w.db = m->g_(m->off_lat_b);
+    TCN_CHECK(launch_wgrad(w, m->max_blk, st));
+  }
+  // stages, last to first
+  const float* g = m->Gp[3];
+  int pp = 0;
+  for (int s = 3; s >= 0; --s) {
+    for (int l = m->stage_first[s + 1] - 1; l >= m->stage_first[s]; --l) {
+      int sh[3];
+      layer_shifts(m, l, sh);
+      // gu = (gv W2) * [h > 0],   gv = keep * gy / (1 - p) applied as gy is loaded
+      {
+        TapGemmDev p = base_tapgemm(m);
+        p.X = g; p.ldx = C; p.Wf = m->wf_(m->wf_w2T[l]); p.Y = m->gu; p.ldy = C; p.M = m->H[l]; p.ldm = C;
+        if (pl > 0.f) { p.in_drop_thresh = drop_thresh(pl); p.in_drop_scale = 1.f / (1.f - pl); p.in_drop_stream = (uint32_t)l; }
+        TCN_CHECK(gemm(m, p, C, C, st));
+      }
+      {
+        WgradDev w = base_wgrad(m);
+        w.G = g; w.ldg = C; w.g_cols = C; w.X = m->H[l]; w.ldx = C; w.n_out = C; w.c_in = C;
+        w.dW = m->g_(m->off_w2[l]); w.db = m->g_(m->off_b2[l]);
+        if (pl > 0.f) { w.g_drop_thresh = drop_thresh(pl); w.g_drop_scale = 1.f / (1.f - pl); w.g_drop_stream = (uint32_t)l; }
+        TCN_CHECK(launch_wgrad(w, m->max_blk, st));
+      }
+      {
+        WgradDev w = base_wgrad(m);
+        w.G = m->gu; w.ldg = C; w.g_cols = C; w.X = m->act[l]; w.ldx = C; w.n_out = C; w.c_in = C; w.ntaps = 3;
+        for (int i = 0; i < 3; ++i) w.shift[i] = sh[i];
+        w.dW = m->g_(m->off_w1[l]); w.db = m->g_(m->off_b1[l]);
+        TCN_CHECK(launch_wgrad(w, m->max_blk, st));
+      }
+      {  // gx = gy + sum_k W1_k^T gu[t - s_k]
+        TapGemmDev p = base_tapgemm(m);
+        p.X = m->gu; p.ldx = C; p.Wf = m->wf_(m->wf_w1T[l]); p.Y = m->gbuf[pp]; p.ldy = C; p.R = g; p.ldr = C;
+        p.ntaps = 3;
+        for (int i = 0; i < 3; ++i) p.shift[i] = -sh[i];
+        TCN_CHECK(gemm(m, p, C, C, st));
+        g = m->gbuf[pp];
+        pp ^= 1;
+      }
+    }
+    if (s > 0) {  // f_{s-1} also feeds the lateral of level s-1
+      TapGemmDev p = base_tapgemm(m);
+      p.X = m->Gp[s - 1]; p.ldx = C; p.Wf = m->wf_(m->wf_latT); p.Y = m->gbuf[pp]; p.ldy = C; p.R = g; p.ldr = C;
+      TCN_CHECK(gemm(m, p, C, C, st));
+      g = m->gbuf[pp];
+      pp ^= 1;
+    }
+  }
+  // projection weight grads (x is a leaf: no input gradient); same mask / channel scale as the forward
+  {
+    WgradDev w = base_wgrad(m);
+    w.G = g; w.ldg = C; w.g_cols = C; w.X = x; w.ldx = D; w.x_unpadded = 1; w.n_out = C; w.c_in = D;
+    w.dW = m->g_(m->off_proj_w); w.db = m->g_(m->off_proj_b);
+    if (m->fwd_training && m->chan_drop_p > 0.f) { w.colscale = m->colscale; w.colscale_ld = D; }
+    if (m->fwd_training && m->input_mask_p > 0.f) {
+      w.x_drop_thresh = drop_thresh(m->input_mask_p); w.x_drop_scale = 1.f; w.x_drop_stream = kStreamMask;
+    }
+    TCN_CHECK(launch_wgrad(w, m->max_blk, st));
+  }
+  return TCN_OK;
+}
+
+extern "C" int tcn_model_forward(tcn_model* m, const float* x, int training, const float** feats,
+                                 const float** logits, int* ld_logits, tcn_stream_t stream) {
+  TCN_REQUIRE(m && x && m->params, "tcn_model_forward: null pointer / parameters not bound");
+  TCN_CHECK(model_forward(m, x, training, (cudaStream_t)stream));
+  if (feats) {
+    for (int lv = 0; lv < 3; ++lv) feats[lv] = m->P[lv];
+    feats[3] = m->act[m->stage_first[4]];
+  }
+  if (logits)
+    for (int lv = 0; lv < 4; ++lv) logits[lv] = m->logits[lv];
+  if (ld_logits) *ld_logits = m->LDH;
+  return TCN_OK;
+}
+
+extern "C" int tcn_model_backward(tcn_model* m, const float* x, const float* const* glogits,
+                                  const float* const* gfeats, tcn_stream_t stream) {
+  TCN_REQUIRE(m && x && m->params, "tcn_model_backward: null pointer / parameters not bound");
+  return model_backward(m, x, glogits, gfeats, (cudaStream_t)stream);
+}
+
+__global__ void finish_loss_kernel(float* loss8, float* out, float w0, float w1, float w2, float w3) {
+  if (threadIdx.x == 0) {
+    const float a = loss8[0], b = loss8[1], c = loss8[2], d = loss8[3];
+    out[0] = a; out[1] = b; out[2] = c; out[3] = d;
+    out[4] = w0 * a + w1 * b + w2 * c + w3 * d;
+    out[5] = out[6] = out[7] = 0.f;
+  }
+}
+
+extern "C" int tcn_model_train_step(tcn_model* m, const float* x, const unsigned char* labels, int ldlab,
+                                    int training, float* loss_out, tcn_stream_t stream) {
+  TCN_REQUIRE(m && x && labels && loss_out && m->params, "tcn_model_train_step: null pointer / parameters not bound");
+  TCN_REQUIRE(ldlab >= m->NH, "tcn_model_train_step: labels need %d columns", m->NH);
+  cudaStream_t st = (cudaStream_t)stream;
+  TCN_CHECK(model_forward(m, x, training, st));
+  if (cudaMemsetAsync(m->loss8, 0, 32, st) != cudaSuccess) {
+    set_error("tcn_model_train_step: memset failed");
+    cudaGetLastError();
+    return TCN_ERR_CUDA;
+  }
+  for (int lv = 0; lv < 4; ++lv) {
+    BceDev b;
+    memset(&b, 0, sizeof(b));
+    b.logits = m->logits[lv]; b.ldl = m->LDH; b.labels = labels; b.ldlab = ldlab; b.lab_unpadded = 1;
+    b.meta = m->meta; b.nrows = m->cfg.max_rows; b.dyn = m->desc; b.ncols = m->NH; b.zero_cols = m->LDH;
+    b.pos_w = m->has_pos_w ? m->pos_w : nullptr; b.col_scale = m->col_scale; b.col_unit = m->col_unit;
+    b.col_head = m->col_head; b.row_scale_const = 1.f; b.loss = m->loss8; b.dL = m->dL[lv]; b.lddl = m->LDH;
+    b.grad_scale = 1.f;
+    TCN_CHECK(launch_bce(b, m->cfg.max_rows, st));
+  }
+  finish_loss_kernel<<<1, 32, 0, st>>>(m->loss8, loss_out, m->head_w[0], m->head_w[1], m->head_w[2], m->head_w[3]);
+  TCN_CHECK(check_launch("finish_loss_kernel"));
+  const float* gl[4] = {m->dL[0], m->dL[1], m->dL[2], m->dL[3]};
+  return model_backward(m, x, gl, nullptr, st);
+}

@@ -31,7 +31,8 @@ def prep_weight(w: torch.Tensor, transpose: bool = False) -> torch.Tensor:
 
 
 def tapgemm(x, wf, lay: SeqLayout, c_in, n_out, shifts=(0,), bias=None, out=None, ldy=None, residual=None,
-            relu_mask=None, relu=False, drop_p=0.0, seed=0, stream_id=0, x_unpadded=False, colscale=None):
+            relu_mask=None, relu=False, drop_p=0.0, seed=0, stream_id=0, x_unpadded=False, colscale=None,
+            in_drop_p=0.0):
     lib = _lib.load()
     assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
     if ldy is None:
@@ -51,11 +52,13 @@ def tapgemm(x, wf, lay: SeqLayout, c_in, n_out, shifts=(0,), bias=None, out=None
         a.shift[i] = int(s)
     a.relu = int(relu)
     a.drop_p, a.drop_seed, a.drop_stream = float(drop_p), int(seed) & 0xFFFFFFFF, int(stream_id) & 0xFFFFFFFF
+    a.in_drop_p = float(in_drop_p)
     _lib.check(lib.tcn_tapgemm(C.byref(a), _lib.stream_ptr()), "tcn_tapgemm")
     return out
 
 
-def wgrad(g, x, lay: SeqLayout, n_out, c_in, shifts, dw, db=None, x_unpadded=False, colscale=None):
+def wgrad(g, x, lay: SeqLayout, n_out, c_in, shifts, dw, db=None, x_unpadded=False, colscale=None, g_drop_p=0.0,
+          seed=0, stream_id=0):
     """dw (n_out, c_in, ntaps) += ..., db (n_out,) += ...  (accumulating, fp32 atomics)."""
     lib = _lib.load()
     assert g.is_contiguous() and x.is_contiguous() and dw.is_contiguous()
@@ -68,7 +71,25 @@ def wgrad(g, x, lay: SeqLayout, n_out, c_in, shifts, dw, db=None, x_unpadded=Fal
     for i, s in enumerate(shifts):
         a.shift[i] = int(s)
     a.dw, a.db = _lib.ptr(dw), _lib.ptr(db)
+    a.g_drop_p, a.drop_seed, a.drop_stream = float(g_drop_p), int(seed) & 0xFFFFFFFF, int(stream_id) & 0xFFFFFFFF
     _lib.check(lib.tcn_wgrad(C.byref(a), _lib.stream_ptr()), "tcn_wgrad")
+
+
+def layer_fwd(x, w1f, w2f, b1, b2, lay: SeqLayout, shifts, save_h=True, drop_p=0.0, seed=0, stream_id=0):
+    """Fused residual layer forward (64 channels): returns (y, h)."""
+    lib = _lib.load()
+    assert x.is_contiguous() and x.shape[1] == 64
+    y = torch.zeros_like(x)
+    h = torch.zeros_like(x) if save_h else None
+    a = _lib.LayerFwdArgs()
+    a.x, a.y, a.h = _lib.ptr(x), _lib.ptr(y), _lib.ptr(h)
+    a.w1f, a.w2f, a.b1, a.b2 = _lib.ptr(w1f), _lib.ptr(w2f), _lib.ptr(b1), _lib.ptr(b2)
+    a.meta, a.nblk, a.channels = _lib.ptr(lay.meta), lay.nblk, x.shape[1]
+    for i, s in enumerate(shifts):
+        a.shift[i] = int(s)
+    a.drop_p, a.drop_seed, a.drop_stream = float(drop_p), int(seed) & 0xFFFFFFFF, int(stream_id) & 0xFFFFFFFF
+    _lib.check(lib.tcn_layer_fwd(C.byref(a), _lib.stream_ptr()), "tcn_layer_fwd")
+    return y, h
 
 
 def dropout_apply(x, p, seed, stream_id):
@@ -159,9 +180,13 @@ class DilatedResidualFn(torch.autograd.Function):
         x = _f32c(x)
         Cc = w1.shape[0]
         shifts = tap_shifts(dilation, causal)
-        h = tapgemm(x, prep_weight(w1), lay, Cc, Cc, shifts, bias=_f32c(b1.detach()), relu=True)
-        y = tapgemm(h, prep_weight(w2), lay, Cc, Cc, (0,), bias=_f32c(b2.detach()), residual=x, drop_p=p, seed=seed,
-                    stream_id=stream_id)
+        if Cc == 64:  # one fused launch
+            y, h = layer_fwd(x, prep_weight(w1), prep_weight(w2), _f32c(b1.detach()), _f32c(b2.detach()), lay, shifts,
+                             True, p, seed, stream_id)
+        else:
+            h = tapgemm(x, prep_weight(w1), lay, Cc, Cc, shifts, bias=_f32c(b1.detach()), relu=True)
+            y = tapgemm(h, prep_weight(w2), lay, Cc, Cc, (0,), bias=_f32c(b2.detach()), residual=x, drop_p=p,
+                        seed=seed, stream_id=stream_id)
         ctx.save_for_backward(x, h, w1, w2)
         ctx.lay, ctx.shifts, ctx.p, ctx.seed, ctx.stream_id = lay, shifts, p, seed, stream_id
         return y
@@ -172,11 +197,12 @@ class DilatedResidualFn(torch.autograd.Function):
         lay, shifts, p = ctx.lay, ctx.shifts, ctx.p
         gy = _f32c(gy)
         Cc = w1.shape[0]
-        gv = dropout_apply(gy, p, ctx.seed, ctx.stream_id) if p > 0 else gy
+        # gv = keep * gy / (1 - p) is never materialised: the mask is regenerated as gy is loaded
         gw2 = torch.zeros(Cc, Cc, 1, device=gy.device, dtype=torch.float32)
         gb2 = torch.zeros(Cc, device=gy.device, dtype=torch.float32)
-        wgrad(gv, h, lay, Cc, Cc, (0,), gw2, gb2)
-        gu = tapgemm(gv, prep_weight(w2, transpose=True), lay, Cc, Cc, (0,), relu_mask=h)
+        wgrad(gy, h, lay, Cc, Cc, (0,), gw2, gb2, g_drop_p=p, seed=ctx.seed, stream_id=ctx.stream_id)
+        gu = tapgemm(gy, prep_weight(w2, transpose=True), lay, Cc, Cc, (0,), relu_mask=h, in_drop_p=p, seed=ctx.seed,
+                     stream_id=ctx.stream_id)
         gw1 = torch.zeros(Cc, Cc, 3, device=gy.device, dtype=torch.float32)
         gb1 = torch.zeros(Cc, device=gy.device, dtype=torch.float32)
         wgrad(gu, x, lay, Cc, Cc, shifts, gw1, gb1)

@@ -23,7 +23,10 @@ def _is_trainable(name: str) -> bool:
     return not any(tok in name for tok in _NO_GRAD_FPN)
 
 
-class TemporalTrainer:
+class TemporalTrainerEager:
+    """Reference composition through the per-op autograd Functions (one Python call per kernel):
+    slow, kept as the cross-check of the native executor."""
+
     def __init__(self, model, lr=1e-2, weight_decay=1e-5, loss_type="all", terl_pos_weight=False,
                  process_group=None, world_size=1):
         self.model = model
@@ -76,3 +79,92 @@ def lpt_assign(lengths, world):
         shards[r].append(i)
         loads[r] += lengths[i]
     return shards
+
+
+class TemporalTrainer:
+    """Native path: csrc/model.cu executor, optionally replayed from one CUDA graph per trainer
+    (batch shape, block table and dropout seed are device-side data, so one graph serves every batch).
+
+    step(x_rows, labels_u8, lengths): x_rows (frames, D) fp32 and labels_u8 (frames, >=131) uint8 may be
+    device tensors or pinned host tensors (then the H2D copy is part of the step, on the same stream).
+    """
+
+    def __init__(self, model, lr=1e-2, weight_decay=1e-5, loss_type="all", terl_pos_weight=False,
+                 process_group=None, world_size=1, max_frames=4096, max_seqs=8, use_graph=True,
+                 input_mask_p=0.0, seed=0):
+        from .executor import ModelExecutor
+        from .losses import TARGET_WEIGHT, TOOL_WEIGHT, VERB_WEIGHT, _LOSS_TYPE_WEIGHTS
+
+        self.model = model
+        self.lr, self.weight_decay = lr, weight_decay
+        self.pg, self.world = process_group, world_size
+        max_rows = max_frames + 128 * max_seqs
+        self.ex = ModelExecutor(model, max_rows, max_seqs)
+        pw = None
+        if terl_pos_weight:
+            pw = [1.0] * model.head_sizes[0] + list(TOOL_WEIGHT) + list(VERB_WEIGHT) + list(TARGET_WEIGHT)
+        self.ex.set_loss(_LOSS_TYPE_WEIGHTS[loss_type], pw)
+        self.ex.set_dropout(input_mask_p, model.PG.channel_dropout.p, model.PG.layers[0].dropout.p)
+        dev = self.ex.device
+        D = self.ex.cfg.in_dim
+        self.max_frames = max_frames
+        self.x_static = torch.zeros(max_frames, D, device=dev, dtype=torch.float32)
+        self.lab_static = torch.zeros(max_frames, self.ex.ld_logits, device=dev, dtype=torch.uint8)
+        self.flat_p, self.flat_g = self.ex.flat_p, self.ex.flat_g
+        self.num_params = self.flat_p.numel()
+        self.use_graph = use_graph
+        self.graph = None
+        self.rng = torch.Generator().manual_seed(seed)
+        self.training = True
+
+    def _body(self):
+        out = self.ex.train_step(self.x_static, self.lab_static, training=self.training)
+        scale = 1.0
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_g, group=self.pg)
+            scale = 1.0 / self.world
+        ops.sgd_step(self.flat_p, self.flat_g, self.lr, self.weight_decay, grad_scale=scale)
+        return out
+
+    def launches_per_step(self):
+        """Kernels of this library enqueued by one step (static count of the executor's schedule)."""
+        L = self.ex.cfg.layers_pg + self.ex.cfg.layers_r * self.ex.cfg.num_r
+        fwd_layer = 1 if self.ex.cfg.channels == 64 else 2
+        # prep + chan-scale + proj + layers + 3 lateral + 4 heads + 4 bce + finish
+        fwd = 1 + 1 + 1 + L * fwd_layer + 3 + 4 + 4 + 1
+        # 4 x (head wgrad + dgrad) + 3 lateral wgrad + L x (dgrad1, wgrad2, wgrad1, dgrad2) + 3 lateral dgrad + proj wgrad
+        bwd = 8 + 3 + 4 * L + 3 + 1
+        return fwd + bwd + 1  # + sgd
+
+    def step(self, x_rows, labels_u8, lengths):
+        """x_rows / labels_u8: one tensor, or a list with one tensor per video (device or pinned host)."""
+        lay = SeqLayout.get(lengths, self.ex.device)
+        n = lay.frames
+        assert n <= self.max_frames
+        seed = int(torch.randint(0, 2 ** 31 - 1, (1,), generator=self.rng).item())
+        xs = x_rows if isinstance(x_rows, (list, tuple)) else [x_rows]
+        ls = labels_u8 if isinstance(labels_u8, (list, tuple)) else [labels_u8]
+        off = 0
+        for x in xs:
+            self.x_static[off:off + x.shape[0]].copy_(x, non_blocking=True)
+            off += x.shape[0]
+        assert off == n
+        off = 0
+        for lab in ls:
+            self.lab_static[off:off + lab.shape[0], :lab.shape[1]].copy_(lab, non_blocking=True)
+            off += lab.shape[0]
+        self.ex.set_batch(lay, seed)
+        if not self.use_graph:
+            return self._body()
+        if self.graph is None:
+            # warm-up outside capture (lazy module loading, cudaFuncSetAttribute), then capture once
+            snap_p = self.flat_p.clone()
+            self._body()
+            self.flat_p.copy_(snap_p)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._out = self._body()
+            self.flat_p.copy_(snap_p)
+        self.graph.replay()
+        return self._out

@@ -66,7 +66,8 @@ typedef struct {
   const int* meta; int nblk;
   int c_in; int n_out; int ntaps; int shift[3];
   int relu;
-  float drop_p; unsigned drop_seed; unsigned drop_stream;
+  float drop_p; unsigned drop_seed; unsigned drop_stream;   /* dropout on the output */
+  float in_drop_p;                              /* dropout (same key) on x as it is loaded: backward of a dropout */
 } tcn_tapgemm_args;
 int tcn_tapgemm(const tcn_tapgemm_args* args, tcn_stream_t stream);
 
@@ -79,8 +80,71 @@ typedef struct {
   const int* meta; int nblk;
   int n_out; int c_in; int ntaps; int shift[3];
   float* dw; float* db;                         /* db may be NULL */
+  float g_drop_p; unsigned drop_seed; unsigned drop_stream;   /* dropout on g as it is loaded */
 } tcn_wgrad_args;
 int tcn_wgrad(const tcn_wgrad_args* args, tcn_stream_t stream);
+
+/* ---- fused residual layer, forward ---------------------------------------------------------------
+ * y = x + Dropout_p(W2 relu(W1 (*)_d x + b1) + b2), one launch: DilatedResidualLayer.forward
+ * (network.py:193-198; shift = {-d, 0, +d}) and DilatedResidualCausalLayer.forward (network.py:178-183;
+ * shift = {-2d, -d, 0}).  x, y, h are (rows, 64) time-major; h = relu(u) is written when non-NULL
+ * (saved for the backward pass, which runs on tcn_tapgemm / tcn_wgrad).  channels must be 64
+ * (TCN_ERR_UNSUPPORTED otherwise: other widths run as two tcn_tapgemm calls). */
+typedef struct {
+  const float* x; float* y; float* h;
+  const float* w1f; const float* w2f;           /* tcn_prep_weight of (64,64,3) and (64,64,1) */
+  const float* b1; const float* b2;
+  const int* meta; int nblk; int channels;
+  int shift[3];
+  float drop_p; unsigned drop_seed; unsigned drop_stream;
+} tcn_layer_fwd_args;
+int tcn_layer_fwd(const tcn_layer_fwd_args* args, tcn_stream_t stream);
+
+/* ---- whole-model executor -------------------------------------------------------------------------
+ * VideoNas(fpn) of network.py:14-68 (BaseCausalTCN -> num_r x Refinement -> FPN -> 4 heads x 4 levels)
+ * plus the train_loop loss of Temporal_tenco/run.py:190-212 (TERL run.py:307-343 with pos_weight),
+ * forward + backward in one call, every launch on `stream`, graph-capturable: batch shape, block
+ * table and dropout seed are read from device memory written by tcn_model_set_batch.
+ * Parameters / gradients are two caller-owned flat fp32 buffers; tcn_model_param_layout gives the
+ * float offset of each tensor in canonical order:
+ *   PG.conv_1x1.{weight,bias}; for stage in PG, Rs.0.. : for layer: conv_dilated.{weight,bias},
+ *   conv_1x1.{weight,bias}; fpn.latlayer1.{weight,bias}; conv_out, conv_out_i, conv_out_v,
+ *   conv_out_t weights (contiguous), then their biases (contiguous). */
+typedef struct {
+  int layers_pg, layers_r, num_r, channels, in_dim;
+  int head_sizes[4];                            /* ivt, i, v, t */
+  int causal;
+  int max_rows;                                 /* capacity in padded rows (multiple of 128) */
+  int max_seqs;
+} tcn_model_config;
+typedef struct tcn_model tcn_model;
+int tcn_model_create(const tcn_model_config* cfg, tcn_model** out);
+void tcn_model_destroy(tcn_model* m);
+long long tcn_model_num_params(const tcn_model* m);
+int tcn_model_num_tensors(const tcn_model* m);
+int tcn_model_param_layout(const tcn_model* m, long long* offsets, long long* sizes, int n);
+int tcn_model_bind(tcn_model* m, float* params, float* grads);
+/* head_weights[4] for (ivt, i, v, t); pos_w: HOST array of sum(head_sizes) floats or NULL */
+int tcn_model_set_loss(tcn_model* m, const float* head_weights, const float* pos_w_host);
+/* input_mask_p: probability of zeroing an input element (network.py:43-48 uses 0.25), 0 = off;
+ * chan_drop_p: Dropout2d over input channels (network.py:117), layer_drop_p: nn.Dropout of the layers */
+int tcn_model_set_dropout(tcn_model* m, float input_mask_p, float chan_drop_p, float layer_drop_p);
+/* meta_host: HOST int4[nblk]; copied (async) with the batch descriptor into device memory */
+int tcn_model_set_batch(tcn_model* m, const int* meta_host, int nblk, int rows, int num_seqs, int frames,
+                        unsigned seed, tcn_stream_t stream);
+/* x: (frames, in_dim) fp32 unpadded; labels: (frames, ldlab) uint8 unpadded, columns ivt|i|v|t.
+ * training != 0: dropout on, gradients accumulated into the bound grad buffer (zeroed first).
+ * loss_out (device, 8 floats): [0..3] = per-head mean BCE summed over levels (ivt, i, v, t), [4] = total. */
+int tcn_model_train_step(tcn_model* m, const float* x, const unsigned char* labels, int ldlab, int training,
+                         float* loss_out, tcn_stream_t stream);
+/* inference / feature extraction: fills pointers to the 4 FPN feature maps (rows, C) and the 4 logit
+ * maps (rows, ld_logits) owned by the model (valid until the next call) */
+int tcn_model_forward(tcn_model* m, const float* x, int training, const float** feats, const float** logits,
+                      int* ld_logits, tcn_stream_t stream);
+/* backward from externally supplied gradients w.r.t. the 4 logit maps (rows, ld_logits; may be NULL)
+ * and the 4 feature maps (rows, C; may be NULL), after tcn_model_forward(training=1) */
+int tcn_model_backward(tcn_model* m, const float* x, const float* const* glogits, const float* const* gfeats,
+                       tcn_stream_t stream);
 
 /* ---- losses ------------------------------------------------------------------------------------
  * Sigmoid-BCE over concatenated heads: nn.BCEWithLogitsLoss(pos_weight) as composed by

@@ -1,0 +1,155 @@
+"""Native whole-model executor (csrc/model.cu) against the oracle, eval and train mode.  GPU only."""
+import types
+
+import pytest
+import torch
+
+from oracle import tcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ARGS = types.SimpleNamespace(fpn=True, output=False, feature=False, trans=False, mask=False, hier=False)
+
+
+def _maxabs(a, b):
+    return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
+
+
+def _oracle_step(sd64, xs, labs, head_sizes, keeps=None):
+    """Mean over videos of the tenco loss; returns (loss terms, grads dict) in float64."""
+    params = {k: v.clone().requires_grad_(True) for k, v in sd64.items()}
+    total = 0.0
+    terms = [0.0, 0.0, 0.0, 0.0]
+    k0, k1, k2, k3 = head_sizes
+    for s, (x, lab) in enumerate(zip(xs, labs)):
+        kw = {}
+        if keeps is not None:
+            kw = dict(mask=keeps["mask"][s], chan_keep=keeps["chan"][s], layer_keeps=keeps["layers"][s], p=0.5)
+        outs = O.videonas_forward(x.double().unsqueeze(0), params, **kw)
+        y = lab.double()
+        labels = (y[:, k0:k0 + k1], y[:, k0 + k1:k0 + k1 + k2], y[:, k0 + k1 + k2:k0 + k1 + k2 + k3], y[:, :k0])
+        loss, li, lv, lt, livt = O.tenco_loss(outs[:4], labels)
+        total = total + loss / len(xs)
+        for i, t in enumerate((livt, li, lv, lt)):
+            terms[i] += float(t) / len(xs)
+    total.backward()
+    return float(total), terms, {k: v.grad for k, v in params.items()}
+
+
+@pytest.mark.parametrize("C,causal", [(64, False), (64, True), (32, False)])
+def test_executor_eval_matches_oracle_and_eager(C, causal):
+    from computervision_codes_b200.executor import ModelExecutor
+    from computervision_codes_b200.layout import SeqLayout
+    from computervision_codes_b200.tcn import VideoNas
+
+    torch.manual_seed(3)
+    D, heads = 48, (100, 6, 10, 15)
+    m = VideoNas(ARGS, 5, 4, 3, C, D, 100, causal=causal).to(DEV)
+    sd64 = {k: v.detach().double().cpu() for k, v in m.state_dict().items()}
+    lengths = [300, 170, 129]
+    g = torch.Generator().manual_seed(1)
+    xs = [torch.randn(T, D, generator=g) for T in lengths]
+    labs = [(torch.rand(T, 132, generator=g) < 0.1).to(torch.uint8) for T in lengths]
+    for lab in labs:
+        lab[:, 131] = 0
+    ref_total, ref_terms, ref_grads = _oracle_step(sd64, xs, labs, heads)
+
+    ex = ModelExecutor(m, max_rows=1024, max_seqs=4)
+    lay = SeqLayout.get(lengths, DEV)
+    ex.set_batch(lay, seed=5)
+    x_rows = torch.cat(xs).to(DEV)
+    lab_rows = torch.cat(labs).to(DEV)
+    loss = ex.train_step(x_rows, lab_rows, training=False).cpu()
+    assert abs(float(loss[4]) - ref_total) <= 1e-4 * abs(ref_total)
+    for i in range(4):
+        assert abs(float(loss[i]) - ref_terms[i]) <= 1e-4 * abs(ref_terms[i])
+    for name, p in m.named_parameters():
+        r = ref_grads[name]
+        if r is None:
+            continue
+        assert p.grad is not None, name
+        assert _maxabs(p.grad, r) <= 3e-5 * max(1.0, float(r.abs().max())) + 1e-6, (name, _maxabs(p.grad, r))
+    # inference outputs of the executor == oracle (logits <= 1e-3, argmax identical)
+    feats, logits = ex.forward(x_rows, training=False)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        for s, T in enumerate(lengths):
+            outs = O.videonas_forward(xs[s].double().unsqueeze(0), sd64, causal=causal)
+            r0 = lay.starts[s]
+            for lv in range(4):
+                got = logits[lv][r0:r0 + T, :100].cpu()
+                ref = outs[0][lv][0].t()
+                assert _maxabs(got, ref) <= 1e-3
+                assert torch.equal(got.argmax(1), ref.float().argmax(1))
+                assert _maxabs(feats[lv][r0:r0 + T].cpu(), outs[4][lv][0].t()) <= 1e-4
+
+
+def test_executor_train_mode_with_the_kernels_own_masks():
+    """Train mode: input mask (p=0.25, no rescale), Dropout2d over input channels, nn.Dropout in every layer.
+    The oracle is run with the very keep-masks the kernels derive from (seed, stream id)."""
+    from computervision_codes_b200 import ops
+    from computervision_codes_b200.executor import ModelExecutor
+    from computervision_codes_b200.layout import SeqLayout
+    from computervision_codes_b200.tcn import VideoNas
+
+    torch.manual_seed(4)
+    C, D, heads = 64, 40, (100, 6, 10, 15)
+    m = VideoNas(ARGS, 3, 2, 3, C, D, 100).to(DEV)
+    sd64 = {k: v.detach().double().cpu() for k, v in m.state_dict().items()}
+    lengths = [150, 200]
+    g = torch.Generator().manual_seed(2)
+    xs = [torch.randn(T, D, generator=g) for T in lengths]
+    labs = [(torch.rand(T, 132, generator=g) < 0.1).to(torch.uint8) for T in lengths]
+    ex = ModelExecutor(m, max_rows=1024, max_seqs=4)
+    ex.set_dropout(input_mask_p=0.25, chan_drop_p=0.5, layer_drop_p=0.5)
+    lay = SeqLayout.get(lengths, DEV)
+    seed = 777
+    ex.set_batch(lay, seed=seed)
+    loss = ex.train_step(torch.cat(xs).to(DEV), torch.cat(labs).to(DEV), training=True).cpu()
+
+    nl = 3 + 2 * 3
+    layer_masks = [ops.dropout_keep_mask(lay.rows, C, 0.5, seed, l, DEV).cpu().double() for l in range(nl)]
+    chan = ops.dropout_keep_mask(len(lengths), D, 0.5, seed, 0x7fff0001, DEV).cpu().double()
+    inmask = ops.dropout_keep_mask(lay.rows, D, 0.25, seed, 0x7fff0002, DEV).cpu().double()
+    keeps = {"mask": [], "chan": [], "layers": []}
+    prefixes = ["PG"] * 3 + ["Rs.0"] * 2 + ["Rs.1"] * 2 + ["Rs.2"] * 2
+    for s, T in enumerate(lengths):
+        r0 = lay.starts[s]
+        keeps["mask"].append(inmask[r0:r0 + T].t().unsqueeze(0))
+        keeps["chan"].append(chan[s:s + 1])
+        d = {}
+        for l, pre in enumerate(prefixes):
+            d.setdefault(pre, []).append(layer_masks[l][r0:r0 + T].t().unsqueeze(0))
+        keeps["layers"].append(d)
+    ref_total, ref_terms, ref_grads = _oracle_step(sd64, xs, labs, heads, keeps)
+    assert abs(float(loss[4]) - ref_total) <= 1e-4 * abs(ref_total)
+    for name, p in m.named_parameters():
+        r = ref_grads[name]
+        if r is None:
+            continue
+        assert _maxabs(p.grad, r) <= 3e-5 * max(1.0, float(r.abs().max())) + 1e-6, (name, _maxabs(p.grad, r))
+
+
+def test_trainer_graph_replay_equals_eager_steps():
+    """The CUDA-graph trainer (one graph, ragged batches of different shapes) follows the same SGD
+    trajectory as stepping the executor without a graph."""
+    from computervision_codes_b200.tcn import VideoNas
+    from computervision_codes_b200.trainer import TemporalTrainer
+
+    D = 32
+    g = torch.Generator().manual_seed(9)
+    batches = []
+    for lengths in ([200], [90, 140], [257]):
+        xs = torch.cat([torch.randn(T, D, generator=g) for T in lengths]).to(DEV)
+        lab = (torch.rand(sum(lengths), 132, generator=g) < 0.1).to(torch.uint8).to(DEV)
+        batches.append((xs, lab, lengths))
+    results = []
+    for use_graph in (False, True):
+        torch.manual_seed(11)
+        m = VideoNas(ARGS, 3, 2, 3, 64, D, 100).to(DEV).train()
+        tr = TemporalTrainer(m, lr=0.05, weight_decay=1e-5, max_frames=512, max_seqs=4, use_graph=use_graph, seed=3)
+        losses = [float(tr.step(*b)[4]) for b in batches for _ in range(2)]
+        results.append((losses, tr.flat_p.clone()))
+    la, lb = results[0][0], results[1][0]
+    assert all(abs(a - b) <= 2e-4 * abs(a) for a, b in zip(la, lb)), (la, lb)
+    assert _maxabs(results[0][1], results[1][1]) <= 1e-4

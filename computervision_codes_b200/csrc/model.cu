@@ -366,7 +366,7 @@ extern "C" int tcn_model_set_batch(tcn_model* m, const int* meta_host, int nblk,
 }
 
 // ================================================================================================ forward
-static int model_forward(tcn_model* m, const float* x, int training, cudaStream_t st) {
+static int model_forward(tcn_model* m, const float* x, int training, bool save_h, cudaStream_t st) {
   const int C = m->C, D = m->D, L = m->L;
   m->fwd_training = training != 0;
   const float pl = training ? m->layer_drop_p : 0.f;
@@ -392,7 +392,7 @@ static int model_forward(tcn_model* m, const float* x, int training, cudaStream_
     layer_shifts(m, l, s);
     if (C == 64) {
       LayerFwdDev p;
-      p.X = m->act[l]; p.Y = m->act[l + 1]; p.H = training ? m->H[l] : nullptr;
+      p.X = m->act[l]; p.Y = m->act[l + 1]; p.H = save_h ? m->H[l] : nullptr;
       p.W1f = m->wf_(m->wf_w1[l]); p.W2f = m->wf_(m->wf_w2[l]);
       p.b1 = m->p_(m->off_b1[l]); p.b2 = m->p_(m->off_b2[l]);
       p.meta = m->meta; p.nblk = m->max_blk; p.dyn = m->desc;
@@ -543,7 +543,7 @@ static int model_backward(tcn_model* m, const float* x, const float* const* gl, 
 extern "C" int tcn_model_forward(tcn_model* m, const float* x, int training, const float** feats,
                                  const float** logits, int* ld_logits, tcn_stream_t stream) {
   TCN_REQUIRE(m && x && m->params, "tcn_model_forward: null pointer / parameters not bound");
-  TCN_CHECK(model_forward(m, x, training, (cudaStream_t)stream));
+  TCN_CHECK(model_forward(m, x, training, training != 0, (cudaStream_t)stream));
   if (feats) {
     for (int lv = 0; lv < 3; ++lv) feats[lv] = m->P[lv];
     feats[3] = m->act[m->stage_first[4]];
@@ -574,7 +574,7 @@ extern "C" int tcn_model_train_step(tcn_model* m, const float* x, const unsigned
   TCN_REQUIRE(m && x && labels && loss_out && m->params, "tcn_model_train_step: null pointer / parameters not bound");
   TCN_REQUIRE(ldlab >= m->NH, "tcn_model_train_step: labels need %d columns", m->NH);
   cudaStream_t st = (cudaStream_t)stream;
-  TCN_CHECK(model_forward(m, x, training, st));
+  TCN_CHECK(model_forward(m, x, training, true, st));
   if (cudaMemsetAsync(m->loss8, 0, 32, st) != cudaSuccess) {
     set_error("tcn_model_train_step: memset failed");
     cudaGetLastError();

@@ -15,7 +15,7 @@ def _maxabs(a, b):
     return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
 
 
-def _oracle_step(sd64, xs, labs, head_sizes, keeps=None):
+def _oracle_step(sd64, xs, labs, head_sizes, keeps=None, causal=False):
     """Mean over videos of the tenco loss; returns (loss terms, grads dict) in float64."""
     params = {k: v.clone().requires_grad_(True) for k, v in sd64.items()}
     total = 0.0
@@ -25,7 +25,7 @@ def _oracle_step(sd64, xs, labs, head_sizes, keeps=None):
         kw = {}
         if keeps is not None:
             kw = dict(mask=keeps["mask"][s], chan_keep=keeps["chan"][s], layer_keeps=keeps["layers"][s], p=0.5)
-        outs = O.videonas_forward(x.double().unsqueeze(0), params, **kw)
+        outs = O.videonas_forward(x.double().unsqueeze(0), params, causal=causal, **kw)
         y = lab.double()
         labels = (y[:, k0:k0 + k1], y[:, k0 + k1:k0 + k1 + k2], y[:, k0 + k1 + k2:k0 + k1 + k2 + k3], y[:, :k0])
         loss, li, lv, lt, livt = O.tenco_loss(outs[:4], labels)
@@ -52,7 +52,7 @@ def test_executor_eval_matches_oracle_and_eager(C, causal):
     labs = [(torch.rand(T, 132, generator=g) < 0.1).to(torch.uint8) for T in lengths]
     for lab in labs:
         lab[:, 131] = 0
-    ref_total, ref_terms, ref_grads = _oracle_step(sd64, xs, labs, heads)
+    ref_total, ref_terms, ref_grads = _oracle_step(sd64, xs, labs, heads, causal=causal)
 
     ex = ModelExecutor(m, max_rows=1024, max_seqs=4)
     lay = SeqLayout.get(lengths, DEV)

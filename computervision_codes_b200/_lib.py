@@ -56,6 +56,18 @@ class LayerFwdArgs(C.Structure):
     ]
 
 
+class GemmTcArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("ldx", C.c_int), ("x_rows", C.c_longlong), ("x_unpadded", C.c_int),
+        ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("bias", C.c_void_p),
+        ("y", C.c_void_p), ("ldy", C.c_int),
+        ("meta", C.c_void_p), ("nblk", C.c_int),
+        ("k", C.c_int), ("n", C.c_int),
+        ("colscale", C.c_void_p), ("colscale_ld", C.c_int),
+        ("in_drop_p", C.c_float), ("in_drop_rescale", C.c_int), ("drop_seed", C.c_uint), ("drop_stream", C.c_uint),
+    ]
+
+
 class ModelConfig(C.Structure):
     _fields_ = [
         ("layers_pg", C.c_int), ("layers_r", C.c_int), ("num_r", C.c_int), ("channels", C.c_int),
@@ -86,6 +98,9 @@ SIGNATURES = {
     "tcn_tapgemm": (C.c_int, [C.POINTER(TapGemmArgs), C.c_void_p]),
     "tcn_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     "tcn_layer_fwd": (C.c_int, [C.POINTER(LayerFwdArgs), C.c_void_p]),
+    "tcn_gemm_tc_supported": (C.c_int, [C.c_int, C.c_int]),
+    "tcn_gemm_tc": (C.c_int, [C.POINTER(GemmTcArgs), C.c_void_p]),
+    "tcn_split_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "tcn_model_create": (C.c_int, [C.POINTER(ModelConfig), C.POINTER(C.c_void_p)]),
     "tcn_model_destroy": (None, [C.c_void_p]),
     "tcn_model_num_params": (C.c_longlong, [C.c_void_p]),
@@ -96,10 +111,10 @@ SIGNATURES = {
     "tcn_model_set_dropout": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float]),
     "tcn_model_set_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint,
                                       C.c_void_p]),
-    "tcn_model_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
-                                       C.c_void_p]),
-    "tcn_model_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
-                                    C.POINTER(C.c_int), C.c_void_p]),
+    "tcn_model_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p]),
+    "tcn_model_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_void_p]),
     "tcn_model_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                      C.c_void_p]),
     "tcn_bce_rows": (C.c_int, [C.POINTER(BceArgs), C.c_void_p]),

@@ -10,7 +10,7 @@
 #include <new>
 #include <vector>
 
-#include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace tcn {
 
@@ -58,6 +58,12 @@ struct tcn_model {
   float* gbuf[2] = {nullptr, nullptr};
   float* gu = nullptr;
   float* colscale = nullptr;
+  // tcgen05 projection: split weight halves + their TMA maps (fixed addresses), X map cached per pointer
+  bool proj_tc = false;
+  float *proj_whi = nullptr, *proj_wlo = nullptr;
+  CUtensorMap map_whi, map_wlo, map_x;
+  const float* map_x_ptr = nullptr;
+  long map_x_rows = 0;
   BatchDesc* desc = nullptr;
   BlkMeta* meta = nullptr;
   static constexpr int kSlots = 4;  // ring of pinned staging slots: desc followed by the block table
@@ -224,6 +230,8 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
   for (int i = 0; i < 2; ++i) o_gb[i] = carve((size_t)rows * C * 4);
   const size_t o_gu = carve((size_t)rows * C * 4);
   const size_t o_cs = carve((size_t)cfg->max_seqs * D * 4);
+  m->proj_tc = tcn_gemm_tc_supported(D, C) != 0;
+  const size_t o_whi = carve((size_t)C * D * 4), o_wlo = carve((size_t)C * D * 4);
   const size_t o_desc = carve(sizeof(BatchDesc) + (size_t)m->max_blk * sizeof(BlkMeta));
   const size_t o_cu = carve((size_t)m->LDH * 4), o_cscale = carve((size_t)m->LDH * 4), o_pw = carve((size_t)m->LDH * 4);
   const size_t o_ch = carve((size_t)m->LDH * 4), o_loss = carve(64);
@@ -254,6 +262,14 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
   for (int i = 0; i < 2; ++i) m->gbuf[i] = reinterpret_cast<float*>(m->ws + o_gb[i]);
   m->gu = reinterpret_cast<float*>(m->ws + o_gu);
   m->colscale = reinterpret_cast<float*>(m->ws + o_cs);
+  m->proj_whi = reinterpret_cast<float*>(m->ws + o_whi);
+  m->proj_wlo = reinterpret_cast<float*>(m->ws + o_wlo);
+  if (m->proj_tc) {
+    const int br = gemm_tc_box_rows_for_n(C);
+    if (make_tensor_map_2d(&m->map_whi, m->proj_whi, C, D, D, br) != TCN_OK ||
+        make_tensor_map_2d(&m->map_wlo, m->proj_wlo, C, D, D, br) != TCN_OK)
+      m->proj_tc = false;  // driver without tensor-map support: stay on the mma.sync path
+  }
   m->desc = reinterpret_cast<BatchDesc*>(m->ws + o_desc);
   m->meta = reinterpret_cast<BlkMeta*>(m->ws + o_desc + sizeof(BatchDesc));
   m->col_unit = reinterpret_cast<float*>(m->ws + o_cu);
@@ -366,7 +382,7 @@ extern "C" int tcn_model_set_batch(tcn_model* m, const int* meta_host, int nblk,
 }
 
 // ================================================================================================ forward
-static int model_forward(tcn_model* m, const float* x, int training, bool save_h, cudaStream_t st) {
+static int model_forward(tcn_model* m, const float* x, long x_rows, int training, bool save_h, cudaStream_t st) {
   const int C = m->C, D = m->D, L = m->L;
   m->fwd_training = training != 0;
   const float pl = training ? m->layer_drop_p : 0.f;
@@ -375,7 +391,21 @@ static int model_forward(tcn_model* m, const float* x, int training, bool save_h
   // 1. stage-input projection (network.py:113,122-129), input mask + channel dropout folded into the load
   const bool chan = training && m->chan_drop_p > 0.f;
   if (chan) TCN_CHECK(launch_chan_scale(m->colscale, D, m->cfg.max_seqs, m->desc, m->chan_drop_p, 0u, kStreamChan, st));
-  {
+  if (m->proj_tc) {  // tcgen05 + TMA (gemm_tc.cu)
+    TCN_CHECK(launch_split_weight(m->p_(m->off_proj_w), m->proj_whi, m->proj_wlo, (long)C * D, st));
+    if (m->map_x_ptr != x || m->map_x_rows != x_rows) {
+      TCN_CHECK(make_tensor_map_2d(&m->map_x, x, x_rows, D, D, 128));
+      m->map_x_ptr = x; m->map_x_rows = x_rows;
+    }
+    GemmTcDev p;
+    memset(&p, 0, sizeof(p));
+    p.Y = m->act[0]; p.ldy = C; p.bias = m->p_(m->off_proj_b);
+    p.meta = m->meta; p.nblk = m->max_blk; p.dyn = m->desc; p.x_unpadded = 1; p.K = D; p.N = C;
+    if (chan) { p.colscale = m->colscale; p.colscale_ld = D; }
+    p.in_drop_scale = 1.f;
+    if (training && m->input_mask_p > 0.f) { p.in_drop_thresh = drop_thresh(m->input_mask_p); p.in_drop_stream = kStreamMask; }
+    TCN_CHECK(launch_gemm_tc(m->map_x, m->map_whi, m->map_wlo, p, m->max_blk, st));
+  } else {
     TapGemmDev p = base_tapgemm(m);
     p.X = x; p.ldx = D; p.x_unpadded = 1;
     if (chan) { p.colscale = m->colscale; p.colscale_ld = D; }
@@ -540,10 +570,10 @@ static int model_backward(tcn_model* m, const float* x, const float* const* gl, 
   return TCN_OK;
 }
 
-extern "C" int tcn_model_forward(tcn_model* m, const float* x, int training, const float** feats,
+extern "C" int tcn_model_forward(tcn_model* m, const float* x, long long x_rows, int training, const float** feats,
                                  const float** logits, int* ld_logits, tcn_stream_t stream) {
-  TCN_REQUIRE(m && x && m->params, "tcn_model_forward: null pointer / parameters not bound");
-  TCN_CHECK(model_forward(m, x, training, training != 0, (cudaStream_t)stream));
+  TCN_REQUIRE(m && x && m->params && x_rows > 0, "tcn_model_forward: null pointer / parameters not bound");
+  TCN_CHECK(model_forward(m, x, x_rows, training, training != 0, (cudaStream_t)stream));
   if (feats) {
     for (int lv = 0; lv < 3; ++lv) feats[lv] = m->P[lv];
     feats[3] = m->act[m->stage_first[4]];
@@ -569,12 +599,12 @@ __global__ void finish_loss_kernel(float* loss8, float* out, float w0, float w1,
   }
 }
 
-extern "C" int tcn_model_train_step(tcn_model* m, const float* x, const unsigned char* labels, int ldlab,
+extern "C" int tcn_model_train_step(tcn_model* m, const float* x, long long x_rows, const unsigned char* labels, int ldlab,
                                     int training, float* loss_out, tcn_stream_t stream) {
   TCN_REQUIRE(m && x && labels && loss_out && m->params, "tcn_model_train_step: null pointer / parameters not bound");
   TCN_REQUIRE(ldlab >= m->NH, "tcn_model_train_step: labels need %d columns", m->NH);
   cudaStream_t st = (cudaStream_t)stream;
-  TCN_CHECK(model_forward(m, x, training, true, st));
+  TCN_CHECK(model_forward(m, x, x_rows, training, true, st));
   if (cudaMemsetAsync(m->loss8, 0, 32, st) != cudaSuccess) {
     set_error("tcn_model_train_step: memset failed");
     cudaGetLastError();

@@ -106,7 +106,7 @@ class ModelExecutor:
         """forward + loss + backward on the batch described by set_batch.  Returns the device tensor
         (loss_ivt, loss_i, loss_v, loss_t, total, 0, 0, 0); gradients are in flat_g / p.grad."""
         assert x_rows.is_contiguous() and labels_u8.is_contiguous() and labels_u8.dtype == torch.uint8
-        _lib.check(_lib.load().tcn_model_train_step(self.h, _lib.ptr(x_rows), _lib.ptr(labels_u8),
+        _lib.check(_lib.load().tcn_model_train_step(self.h, _lib.ptr(x_rows), x_rows.shape[0], _lib.ptr(labels_u8),
                                                     labels_u8.shape[1], int(training), _lib.ptr(self.loss),
                                                     _lib.stream_ptr()), "tcn_model_train_step")
         return self.loss
@@ -117,7 +117,7 @@ class ModelExecutor:
         lib = _lib.load()
         feats, logits = (C.c_void_p * 4)(), (C.c_void_p * 4)()
         ld = C.c_int()
-        _lib.check(lib.tcn_model_forward(self.h, _lib.ptr(x_rows), int(training), feats, logits, C.byref(ld),
+        _lib.check(lib.tcn_model_forward(self.h, _lib.ptr(x_rows), x_rows.shape[0], int(training), feats, logits, C.byref(ld),
                                          _lib.stream_ptr()), "tcn_model_forward")
         rows = self._lay.rows
         Cc = self.cfg.channels

@@ -92,6 +92,37 @@ def layer_fwd(x, w1f, w2f, b1, b2, lay: SeqLayout, shifts, save_h=True, drop_p=0
     return y, h
 
 
+def split_weight(w):
+    """(n, k) fp32 weight -> (w_hi, w_lo) with w_hi exactly representable in TF32 and w_hi + w_lo == w."""
+    lib = _lib.load()
+    w = _f32c(w.detach()).reshape(w.shape[0], -1)
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    _lib.check(lib.tcn_split_weight(_lib.ptr(w), _lib.ptr(hi), _lib.ptr(lo), w.numel(), _lib.stream_ptr()),
+               "tcn_split_weight")
+    return hi, lo
+
+
+def gemm_tc(x, w_hi, w_lo, lay: SeqLayout, bias=None, out=None, x_unpadded=False, colscale=None, in_drop_p=0.0,
+            in_drop_rescale=False, seed=0, stream_id=0):
+    """tcgen05/TMA GEMM y = x @ W^T + bias over the packed rows (k % 32 == 0, n % 64 == 0)."""
+    lib = _lib.load()
+    assert x.is_contiguous() and x.dim() == 2
+    n, k = w_hi.shape
+    if out is None:
+        out = torch.zeros(lay.rows, n, device=x.device, dtype=torch.float32)
+    a = _lib.GemmTcArgs()
+    a.x, a.ldx, a.x_rows, a.x_unpadded = _lib.ptr(x), x.shape[1], x.shape[0], int(x_unpadded)
+    a.w_hi, a.w_lo, a.bias = _lib.ptr(w_hi), _lib.ptr(w_lo), _lib.ptr(bias)
+    a.y, a.ldy = _lib.ptr(out), out.shape[1]
+    a.meta, a.nblk = _lib.ptr(lay.meta), lay.nblk
+    a.k, a.n = k, n
+    a.colscale, a.colscale_ld = _lib.ptr(colscale), (colscale.shape[1] if colscale is not None else 0)
+    a.in_drop_p, a.in_drop_rescale = float(in_drop_p), int(in_drop_rescale)
+    a.drop_seed, a.drop_stream = int(seed) & 0xFFFFFFFF, int(stream_id) & 0xFFFFFFFF
+    _lib.check(lib.tcn_gemm_tc(C.byref(a), _lib.stream_ptr()), "tcn_gemm_tc")
+    return out
+
+
 def dropout_apply(x, p, seed, stream_id):
     lib = _lib.load()
     y = torch.empty_like(x)

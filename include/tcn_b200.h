@@ -84,6 +84,26 @@ typedef struct {
 } tcn_wgrad_args;
 int tcn_wgrad(const tcn_wgrad_args* args, tcn_stream_t stream);
 
+/* ---- tcgen05 + TMA GEMM -----------------------------------------------------------------------------
+ * y[r, n] = sum_k x[r, k] * W[n, k] + bias[n] on the 5th-gen tensor cores (tcgen05.mma kind::tf32, 3-term
+ * split, TMEM accumulator, TMA-fed 4-stage ring): the stage-input projection Conv1d(dim -> C, 1) of
+ * BaseCausalTCN (network.py:113,129) with Dropout2d's channel scale (colscale, :125-127) and the 25 % input
+ * mask (in_drop_p with in_drop_rescale = 0, :43-50) folded into the operand load; also every Linear of
+ * the MS-TCT blocks.  Needs k % 32 == 0 and n % 64 == 0 (tcn_gemm_tc_supported), else TCN_ERR_UNSUPPORTED.
+ * w_hi / w_lo: (n, k) row-major halves of W from tcn_split_weight.  x_rows = rows addressable in x. */
+typedef struct {
+  const float* x; int ldx; long long x_rows; int x_unpadded;
+  const float* w_hi; const float* w_lo; const float* bias;
+  float* y; int ldy;
+  const int* meta; int nblk;
+  int k; int n;
+  const float* colscale; int colscale_ld;
+  float in_drop_p; int in_drop_rescale; unsigned drop_seed; unsigned drop_stream;
+} tcn_gemm_tc_args;
+int tcn_gemm_tc_supported(int k, int n);
+int tcn_gemm_tc(const tcn_gemm_tc_args* args, tcn_stream_t stream);
+int tcn_split_weight(const float* w, float* w_hi, float* w_lo, long long n, tcn_stream_t stream);
+
 /* ---- fused residual layer, forward ---------------------------------------------------------------
  * y = x + Dropout_p(W2 relu(W1 (*)_d x + b1) + b2), one launch: DilatedResidualLayer.forward
  * (network.py:193-198; shift = {-d, 0, +d}) and DilatedResidualCausalLayer.forward (network.py:178-183;
@@ -132,15 +152,15 @@ int tcn_model_set_dropout(tcn_model* m, float input_mask_p, float chan_drop_p, f
 /* meta_host: HOST int4[nblk]; copied (async) with the batch descriptor into device memory */
 int tcn_model_set_batch(tcn_model* m, const int* meta_host, int nblk, int rows, int num_seqs, int frames,
                         unsigned seed, tcn_stream_t stream);
-/* x: (frames, in_dim) fp32 unpadded; labels: (frames, ldlab) uint8 unpadded, columns ivt|i|v|t.
+/* x: (x_rows >= frames, in_dim) fp32 unpadded, x_rows = rows addressable behind x; labels: (frames, ldlab) uint8 unpadded, columns ivt|i|v|t.
  * training != 0: dropout on, gradients accumulated into the bound grad buffer (zeroed first).
  * loss_out (device, 8 floats): [0..3] = per-head mean BCE summed over levels (ivt, i, v, t), [4] = total. */
-int tcn_model_train_step(tcn_model* m, const float* x, const unsigned char* labels, int ldlab, int training,
-                         float* loss_out, tcn_stream_t stream);
+int tcn_model_train_step(tcn_model* m, const float* x, long long x_rows, const unsigned char* labels, int ldlab,
+                         int training, float* loss_out, tcn_stream_t stream);
 /* inference / feature extraction: fills pointers to the 4 FPN feature maps (rows, C) and the 4 logit
  * maps (rows, ld_logits) owned by the model (valid until the next call) */
-int tcn_model_forward(tcn_model* m, const float* x, int training, const float** feats, const float** logits,
-                      int* ld_logits, tcn_stream_t stream);
+int tcn_model_forward(tcn_model* m, const float* x, long long x_rows, int training, const float** feats,
+                      const float** logits, int* ld_logits, tcn_stream_t stream);
 /* backward from externally supplied gradients w.r.t. the 4 logit maps (rows, ld_logits; may be NULL)
  * and the 4 feature maps (rows, C; may be NULL), after tcn_model_forward(training=1) */
 int tcn_model_backward(tcn_model* m, const float* x, const float* const* glogits, const float* const* gfeats,

@@ -1,0 +1,67 @@
+"""tcgen05 + TMA GEMM (csrc/gemm_tc.cu) against an fp64 reference.  GPU only."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _maxabs(a, b):
+    return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
+
+
+@pytest.mark.parametrize("lengths,K,N,unpadded", [([1800], 2048, 64, True), ([300, 170, 129], 96, 64, True),
+                                                   ([256, 40], 768, 128, False), ([130], 32, 192, False),
+                                                   ([1000, 999], 512, 256, True)])
+def test_gemm_tc_matches_fp64(lengths, K, N, unpadded):
+    from computervision_codes_b200 import ops
+    from computervision_codes_b200.layout import SeqLayout
+
+    torch.manual_seed(K + N)
+    lay = SeqLayout.get(lengths, DEV)
+    xs = [torch.randn(T, K) for T in lengths]
+    w = torch.randn(N, K) / K ** 0.5
+    b = torch.randn(N)
+    if unpadded:
+        x = torch.cat(xs).to(DEV)
+    else:
+        x = torch.zeros(lay.rows, K)
+        for s, T in enumerate(lengths):
+            x[lay.starts[s]:lay.starts[s] + T] = xs[s]
+        x = x.to(DEV)
+    hi, lo = ops.split_weight(w.to(DEV))
+    assert torch.equal((hi + lo).cpu(), w)
+    y = ops.gemm_tc(x, hi, lo, lay, bias=b.to(DEV), x_unpadded=unpadded)
+    torch.cuda.synchronize()
+    for s, T in enumerate(lengths):
+        ref = xs[s].double() @ w.double().t() + b.double()
+        got = y[lay.starts[s]:lay.starts[s] + T]
+        err = _maxabs(got, ref)
+        assert err <= 4e-6 * max(1.0, float(ref.abs().max())) + 1e-6 * K ** 0.5, (lengths, K, N, err)
+    # rows between sequences are never written
+    for s, T in enumerate(lengths):
+        end = lay.starts[s + 1] if s + 1 < len(lengths) else lay.rows
+        assert float(y[lay.starts[s] + T:end].abs().max() if end > lay.starts[s] + T else 0.0) == 0.0
+
+
+def test_gemm_tc_channel_scale_and_input_mask():
+    from computervision_codes_b200 import ops
+    from computervision_codes_b200.layout import SeqLayout
+
+    torch.manual_seed(1)
+    lengths, K, N = [200, 150], 128, 64
+    lay = SeqLayout.get(lengths, DEV)
+    xs = [torch.randn(T, K) for T in lengths]
+    w = torch.randn(N, K) / K ** 0.5
+    hi, lo = ops.split_weight(w.to(DEV))
+    cs = (torch.rand(len(lengths), K) > 0.5).float() * 2.0
+    seed, sid = 99, 0x7fff0002
+    y = ops.gemm_tc(torch.cat(xs).to(DEV), hi, lo, lay, x_unpadded=True, colscale=cs.to(DEV), in_drop_p=0.25,
+                    in_drop_rescale=False, seed=seed, stream_id=sid)
+    keep = ops.dropout_keep_mask(lay.rows, K, 0.25, seed, sid, DEV).cpu().double()
+    assert 0.72 < float(keep.mean()) < 0.78
+    for s, T in enumerate(lengths):
+        r0 = lay.starts[s]
+        xm = xs[s].double() * cs[s].double() * keep[r0:r0 + T]
+        ref = xm @ w.double().t()
+        assert _maxabs(y[r0:r0 + T], ref) <= 1e-5

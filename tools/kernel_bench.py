@@ -103,13 +103,19 @@ def main():
                               "alg_GBps": round(byt * frames / ms / 1e6, 1),
                               "executed_TFLOPs_3xtf32": round(flops * frames * 3 / ms / 1e9, 1)}))
         # stage-input projection 2048 -> 64
-        if frames <= 100000:
-            D = 2048
+        if True:
+            D = 2048 if frames <= 100000 else 768
             x = torch.randn(frames, D, device=DEV)
             wp = ops.prep_weight(torch.randn(C, D, device=DEV) / D ** 0.5)
             out = torch.zeros(lay.rows, C, device=DEV)
             ms = timeit(lambda: ops.tapgemm(x, wp, lay, D, C, (0,), bias=b, out=out, x_unpadded=True))
             print(json.dumps({"kernel": "tapgemm projection 2048->64", "shape": name, "ms": round(ms, 4),
+                              "alg_GBps": round(4 * (D + C) * frames / ms / 1e6, 1),
+                              "frac_hbm": round(4 * (D + C) * frames / ms / 1e6 / PEAK, 4),
+                              "executed_TFLOPs_3xtf32": round(2 * D * C * frames * 3 / ms / 1e9, 1)}))
+            whi, wlo = ops.split_weight(torch.randn(C, D, device=DEV) / D ** 0.5)
+            ms = timeit(lambda: ops.gemm_tc(x, whi, wlo, lay, bias=b, out=out, x_unpadded=True))
+            print(json.dumps({"kernel": "gemm_tc (tcgen05+TMA) projection 2048->64", "shape": name, "ms": round(ms, 4),
                               "alg_GBps": round(4 * (D + C) * frames / ms / 1e6, 1),
                               "frac_hbm": round(4 * (D + C) * frames / ms / 1e6 / PEAK, 4),
                               "executed_TFLOPs_3xtf32": round(2 * D * C * frames * 3 / ms / 1e9, 1)}))

@@ -61,10 +61,14 @@ class GemmTcArgs(C.Structure):
         ("x", C.c_void_p), ("ldx", C.c_int), ("x_rows", C.c_longlong), ("x_unpadded", C.c_int),
         ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("bias", C.c_void_p),
         ("y", C.c_void_p), ("ldy", C.c_int),
+        ("residual", C.c_void_p), ("ldr", C.c_int),
+        ("relu_mask", C.c_void_p), ("ldm", C.c_int),
         ("meta", C.c_void_p), ("nblk", C.c_int),
-        ("k", C.c_int), ("n", C.c_int),
+        ("c_in", C.c_int), ("n_out", C.c_int), ("ntaps", C.c_int), ("shift", C.c_int * 3),
+        ("relu", C.c_int),
         ("colscale", C.c_void_p), ("colscale_ld", C.c_int),
-        ("in_drop_p", C.c_float), ("in_drop_rescale", C.c_int), ("drop_seed", C.c_uint), ("drop_stream", C.c_uint),
+        ("in_drop_p", C.c_float), ("in_drop_rescale", C.c_int),
+        ("drop_p", C.c_float), ("drop_seed", C.c_uint), ("drop_stream", C.c_uint),
     ]
 
 
@@ -100,7 +104,9 @@ SIGNATURES = {
     "tcn_layer_fwd": (C.c_int, [C.POINTER(LayerFwdArgs), C.c_void_p]),
     "tcn_gemm_tc_supported": (C.c_int, [C.c_int, C.c_int]),
     "tcn_gemm_tc": (C.c_int, [C.POINTER(GemmTcArgs), C.c_void_p]),
-    "tcn_split_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "tcn_split_weight_floats": (C.c_longlong, [C.c_int] * 4),
+    "tcn_split_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
     "tcn_model_create": (C.c_int, [C.POINTER(ModelConfig), C.POINTER(C.c_void_p)]),
     "tcn_model_destroy": (None, [C.c_void_p]),
     "tcn_model_num_params": (C.c_longlong, [C.c_void_p]),

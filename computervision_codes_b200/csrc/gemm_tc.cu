@@ -1,107 +1,29 @@
-// tcgen05 + TMA GEMM for per-frame dense contractions with a long K:
+// tcgen05 + TMA "tap GEMM": per-frame dense contractions on the 5th-generation tensor cores
 //
-//     Y[r, n] = sum_k X[r, k] * W[n, k] + bias[n]                (fp32 in, fp32 out)
+//     Y[r, n] = epi( sum_tap sum_c X[r + shift[tap], c] * W[n, c, tap] + bias[n] )      (fp32 in, fp32 out)
+//     epi = relu -> (* [M > 0]) -> dropout -> (+ R)
 //
-// the stage-input projection Conv1d(dim -> num_f_maps, 1) of BaseCausalTCN
-// (MT4MTLKD/Temporal_tenco/network.py:113,129; x arrives as (B, T, D) = K-major rows, :42) and every
-// nn.Linear / 1x1 Conv1d of the MS-TCT blocks (Temporal_mstct/MSTCT/Temporal_Encoder.py:12,15,57-59).
+//  - the stage-input projection Conv1d(dim -> num_f_maps, 1) of BaseCausalTCN
+//    (MT4MTLKD/Temporal_tenco/network.py:113,129; x arrives as (B, T, D) = K-major rows, :42), with
+//    Dropout2d's channel scale (:125-127) and the 25 % input mask (:43-50) folded into the operand load;
+//  - the k=3 dilated convolution and the 1x1 convolution of the residual layers and their input-gradient
+//    passes (network.py:178-198): each tap is the same TMA box fetched at a shifted row coordinate;
+//  - the FPN lateral (network.py:98-106), the four heads (:63-67) and their gradients;
+//  - nn.Linear / Conv1d(k=1,3) of the MS-TCT blocks (Temporal_mstct/MSTCT/Temporal_Encoder.py:12,15,57-59,139).
 //
-// Blackwell structure (one CTA = one 128-frame x BN tile, 6 warps):
-//   warp 0   : TMA producer  -- cp.async.bulk.tensor 2D loads of the X tile (128 x 32 fp32, 128B swizzle)
-//              and of the pre-split weight tiles W_hi / W_lo (BN x 32) into a 4-stage smem ring
-//   warps 2-5: operand split -- X -> (X_hi in place, X_lo) : hi = x & 0xffffe000 is exact in TF32, lo = x - hi;
-//              also folds Dropout2d's per-(sequence, channel) scale and the 25 % input mask into the load
+// Blackwell structure (one CTA = one 128-frame x 64 (or 128) column tile, 6 warps):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor 2D loads of the X tile (128 x 32 fp32, 128B swizzle) at
+//              row0 + shift[tap] and of the pre-split weight tiles W_hi / W_lo (BN x 32), 4-stage smem ring
+//   warps 2-5: operand split -- X -> (X_hi in place, X_lo): hi = x & 0xffffe000 is exact in TF32, lo = x - hi;
+//              rows whose tap leaves the sequence are zeroed here (Conv1d zero padding / causal F.pad)
 //   warp 1   : MMA issuer    -- one elected lane issues tcgen05.mma.kind::tf32 (M = 128, N = BN, K = 8), three
 //              products per k-slice (lo*hi + hi*lo + hi*hi) accumulating in TMEM (fp32); tcgen05.commit
 //              releases the smem stage back to the producer
-//   warps 2-5: epilogue      -- tcgen05.ld (32 lanes x 32 columns) -> + bias -> 128-bit stores of Y
+//   warps 2-5: epilogue      -- tcgen05.ld (32 lanes x 32 columns) -> epi -> 128-bit stores of Y
 // Accuracy: 3xTF32 == fp32 to ~1e-6 relative (see tests), the bar is 1e-3 on logits.
-// HBM traffic: X is read exactly once (the algorithmic 4*(D + C) bytes per frame); W tiles come from L2.
 #include "gemm_tc.cuh"
 
 namespace tcn {
-
-constexpr int TC_BM = 128;       // frames per tile
-constexpr int TC_BK = 32;        // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int TC_THREADS = 192;  // 6 warps
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
-
-// K-major, 128-byte-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address  [0,14)
-  d |= (uint64_t)0 << 16;                       // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset [32,46)
-  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
-  return d;
-}
-// kind::tf32, fp32 accumulate, A and B K-major
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 template <int BN>
 struct TcSmem {
@@ -158,22 +80,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   if (active) m = p.meta[blk];
   const int row0 = blk * kBlkRows;
   const bool has_rows = active && row0 < m.hi;
-  const int kblocks = p.K / TC_BK;
+  const int kblocks = p.ntaps * p.kbp;
 
   if (has_rows) {
     if (warp == 0) {
       // ===================== TMA producer =====================
       if (lane == 0) {
         const int xrow = row0 + (p.x_unpadded ? m.in_delta : 0);
+        int tap = 0, kc = 0;
         for (int kb = 0; kb < kblocks; ++kb) {
           const int s = kb % TC_STAGES;
           const uint32_t ph = (kb / TC_STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = tiles + s * S::kStage;
           mbar_arrive_expect_tx(&full_bar[s], S::kA + 2 * S::kB);
-          tma_load_2d(st, &map_x, &full_bar[s], kb * TC_BK, xrow);
+          const int sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
+          tma_load_2d(st, &map_x, &full_bar[s], kc * TC_BK, xrow + sh);  // rows < 0 or past the end: zero fill
           tma_load_2d(st + 2 * S::kA, &map_whi, &full_bar[s], kb * TC_BK, ntile * BN);
           tma_load_2d(st + 2 * S::kA + S::kB, &map_wlo, &full_bar[s], kb * TC_BK, ntile * BN);
+          if (++kc == p.kbp) { kc = 0; ++tap; }
         }
       }
     } else if (warp == 1) {
@@ -204,30 +129,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     } else {
       // ===================== operand split (warps 2..5) =====================
       const int ct = threadIdx.x - 64;  // 0..127
-      const uint32_t in_seed = p.in_drop_seed ^ (p.dyn ? p.dyn->seed : 0u);
+      const uint32_t dseed = p.dyn ? p.dyn->seed : 0u;
+      const uint32_t in_seed = p.in_drop_seed ^ dseed;
+      int tap = 0, kc = 0;
       for (int kb = 0; kb < kblocks; ++kb) {
         const int s = kb % TC_STAGES;
         const uint32_t ph = (kb / TC_STAGES) & 1;
+        const int sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
         mbar_wait(&full_bar[s], ph);
         float4* xa = reinterpret_cast<float4*>(tiles + s * S::kStage);
         float4* xl = reinterpret_cast<float4*>(tiles + s * S::kStage + S::kA);
 #pragma unroll
         for (int i = 0; i < (TC_BM * TC_BK / 4) / 128; ++i) {
           const int c = ct + i * 128;  // physical 16-byte chunk inside the tile
+          const int r = c >> 3;
+          const int src = row0 + r + sh;
           float4 v = xa[c];
-          if (p.colscale != nullptr || p.in_drop_thresh != 0u) {
-            const int r = c >> 3;
-            const int col = kb * TC_BK + (((c & 7) ^ (r & 7)) << 2);  // undo the 128B swizzle
-            if (p.colscale != nullptr) {
+          if (src < m.lo || src >= m.hi) {
+            v = make_float4(0.f, 0.f, 0.f, 0.f);  // the tap leaves its sequence
+          } else if (p.colscale != nullptr || p.in_drop_thresh != 0u) {
+            const int col = kc * TC_BK + (((c & 7) ^ (r & 7)) << 2);  // undo the 128B swizzle
+            if (p.colscale != nullptr && col < p.c_in) {
               const float4 sc = __ldg(reinterpret_cast<const float4*>(p.colscale + (size_t)m.seq * p.colscale_ld + col));
               v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
             }
             if (p.in_drop_thresh != 0u) {
-              const int row = row0 + r;
-              v.x *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, row, col);
-              v.y *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, row, col + 1);
-              v.z *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, row, col + 2);
-              v.w *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, row, col + 3);
+              v.x *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col);
+              v.y *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col + 1);
+              v.z *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col + 2);
+              v.w *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col + 3);
             }
           }
           float4 h, l;
@@ -240,6 +170,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         }
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(&ready_bar[s]);
+        if (++kc == p.kbp) { kc = 0; ++tap; }
       }
       // ===================== epilogue (same warps; TMEM lane quadrant = warp % 4) =====================
       mbar_wait(accum_bar, 0);
@@ -247,21 +178,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       const int q = warp & 3;
       const int row = row0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const uint32_t out_seed = p.drop_seed ^ dseed;
+      const bool vec_ok = ((p.ldy & 3) == 0) && (p.R == nullptr || (p.ldr & 3) == 0) && (p.M == nullptr || (p.ldm & 3) == 0);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
-        tmem_ld32(taddr + c0, v);
+        tmem_ld32(taddr + c0, v);  // warp-collective: every lane takes part, stores are predicated below
         if (row < m.hi) {
-          const int n0 = ntile * BN + c0;
-          float* yp = p.Y + (size_t)row * p.ldy + n0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (p.bias != nullptr) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            const int n = ntile * BN + c0 + j;
+            if (n < p.N) {
+              float o[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
+              const bool full4 = (n + 3 < p.N) && vec_ok;
+              if (full4) {
+                if (p.bias != nullptr) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                  o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
+                }
+                if (p.relu) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+                }
+                if (p.M != nullptr) {
+                  const float4 mk = *reinterpret_cast<const float4*>(p.M + (size_t)row * p.ldm + n);
+                  if (!(mk.x > 0.f)) o[0] = 0.f;
+                  if (!(mk.y > 0.f)) o[1] = 0.f;
+                  if (!(mk.z > 0.f)) o[2] = 0.f;
+                  if (!(mk.w > 0.f)) o[3] = 0.f;
+                }
+                if (p.drop_thresh != 0u) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    o[e] *= drop_factor(out_seed, p.drop_stream, p.drop_thresh, p.drop_scale, row, n + e);
+                }
+                if (p.R != nullptr) {
+                  const float4 rr = *reinterpret_cast<const float4*>(p.R + (size_t)row * p.ldr + n);
+                  o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+                }
+                *reinterpret_cast<float4*>(p.Y + (size_t)row * p.ldy + n) = make_float4(o[0], o[1], o[2], o[3]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (n + e < p.N) {
+                    float x = o[e];
+                    if (p.bias != nullptr) x += __ldg(p.bias + n + e);
+                    if (p.relu) x = fmaxf(x, 0.f);
+                    if (p.M != nullptr && !(p.M[(size_t)row * p.ldm + n + e] > 0.f)) x = 0.f;
+                    if (p.drop_thresh != 0u)
+                      x *= drop_factor(out_seed, p.drop_stream, p.drop_thresh, p.drop_scale, row, n + e);
+                    if (p.R != nullptr) x += p.R[(size_t)row * p.ldr + n + e];
+                    p.Y[(size_t)row * p.ldy + n + e] = x;
+                  }
+                }
+              }
             }
-            *reinterpret_cast<float4*>(yp + j) = o;
           }
         }
       }
@@ -316,48 +287,78 @@ int make_tensor_map_2d(CUtensorMap* map, const float* ptr, long rows, long cols,
   return TCN_OK;
 }
 
+__device__ __forceinline__ void split_one(const float* __restrict__ w, float* __restrict__ whi, float* __restrict__ wlo,
+                                          int n_out, int c_in, int ntaps, int transpose, int kcols, long i) {
+  const int r = (int)(i / kcols), k = (int)(i - (long)r * kcols);
+  const int kp = kcols / ntaps;  // padded K per tap
+  const int tap = k / kp, kk = k - tap * kp;
+  float v = 0.f;
+  if (!transpose) {
+    if (r < n_out && kk < c_in) v = w[((long)r * c_in + kk) * ntaps + tap];
+  } else {
+    if (r < c_in && kk < n_out) v = w[((long)kk * c_in + r) * ntaps + tap];
+  }
+  const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  whi[i] = h;
+  wlo[i] = v - h;
+}
+
 __global__ void split_weight_kernel(const float* __restrict__ w, float* __restrict__ whi, float* __restrict__ wlo,
-                                    long n) {
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const float v = w[i];
-    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-    whi[i] = h;
-    wlo[i] = v - h;
+                                    int n_out, int c_in, int ntaps, int transpose, int rows_pad, int kcols) {
+  const long total = (long)rows_pad * kcols;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x)
+    split_one(w, whi, wlo, n_out, c_in, ntaps, transpose, kcols, i);
+}
+
+__global__ void split_weight_batched_kernel(const SplitJob* __restrict__ jobs, int njobs,
+                                            const float* __restrict__ params, float* __restrict__ whi,
+                                            float* __restrict__ wlo, long total) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].first <= i) lo = mid; else hi = mid - 1;
+    }
+    const SplitJob jb = jobs[lo];
+    split_one(params + jb.src_off, whi + jb.dst_off, wlo + jb.dst_off, jb.n_out, jb.c_in, jb.ntaps, jb.transpose,
+              jb.kcols, i - jb.first);
   }
 }
 
-int launch_split_weight(const float* w, float* whi, float* wlo, long n, cudaStream_t stream) {
-  long b = (n + 255) / 256;
+int launch_split_weight(const float* w, float* whi, float* wlo, int n_out, int c_in, int ntaps, int transpose,
+                        cudaStream_t stream) {
+  const int rows_pad = (int)tc_weight_rows(n_out, c_in, transpose);
+  const int kcols = (int)tc_weight_cols(n_out, c_in, ntaps, transpose);
+  long b = ((long)rows_pad * kcols + 255) / 256;
   if (b > 1024) b = 1024;
-  split_weight_kernel<<<(int)b, 256, 0, stream>>>(w, whi, wlo, n);
+  split_weight_kernel<<<(int)b, 256, 0, stream>>>(w, whi, wlo, n_out, c_in, ntaps, transpose, rows_pad, kcols);
   return check_launch("split_weight_kernel");
 }
 
-int gemm_tc_box_rows_for_n(int n) { return (n % 128 == 0) ? 128 : 64; }
+int launch_split_batched(const SplitJob* jobs_dev, int njobs, const float* params, float* whi, float* wlo, long total,
+                         cudaStream_t stream) {
+  long b = (total + 255) / 256;
+  if (b > 2048) b = 2048;
+  split_weight_batched_kernel<<<(int)b, 256, 0, stream>>>(jobs_dev, njobs, params, whi, wlo, total);
+  return check_launch("split_weight_batched_kernel");
+}
 
 int launch_gemm_tc(const CUtensorMap& mx, const CUtensorMap& mwhi, const CUtensorMap& mwlo, const GemmTcDev& p,
                    int cap_nblk, cudaStream_t stream) {
   const int nb = cap_nblk > 0 ? cap_nblk : p.nblk;
-  const int bn = (p.N % 128 == 0) ? 128 : 64;
-  dim3 grid(nb, p.N / bn);
-  cudaError_t e;
-  if (bn == 128) {
-    static bool set128 = false;
-    if (!set128) {
-      e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128>::kBytes);
-      if (e != cudaSuccess) { set_error("gemm_tc<128>: smem attribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return TCN_ERR_CUDA; }
-      set128 = true;
+  dim3 grid(nb, (p.N + 63) / 64);
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e =
+        cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64>::kBytes);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc: smem attribute: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return TCN_ERR_CUDA;
     }
-    gemm_tc_kernel<128><<<grid, TC_THREADS, TcSmem<128>::kBytes, stream>>>(mx, mwhi, mwlo, p);
-  } else {
-    static bool set64 = false;
-    if (!set64) {
-      e = cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64>::kBytes);
-      if (e != cudaSuccess) { set_error("gemm_tc<64>: smem attribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return TCN_ERR_CUDA; }
-      set64 = true;
-    }
-    gemm_tc_kernel<64><<<grid, TC_THREADS, TcSmem<64>::kBytes, stream>>>(mx, mwhi, mwlo, p);
+    attr_set = true;
   }
+  gemm_tc_kernel<64><<<grid, TC_THREADS, TcSmem<64>::kBytes, stream>>>(mx, mwhi, mwlo, p);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -365,37 +366,54 @@ int launch_gemm_tc(const CUtensorMap& mx, const CUtensorMap& mwhi, const CUtenso
 
 using namespace tcn;
 
-extern "C" int tcn_gemm_tc_supported(int k, int n) { return (k > 0 && k % TC_BK == 0 && n > 0 && n % 64 == 0) ? 1 : 0; }
+extern "C" int tcn_gemm_tc_supported(int c_in, int n_out) {
+  // x rows must be 16-byte multiples for the TMA map; everything else is padded / masked
+  return (c_in > 0 && c_in % 4 == 0 && n_out > 0) ? 1 : 0;
+}
+
+extern "C" long long tcn_split_weight_floats(int n_out, int c_in, int ntaps, int transpose) {
+  return (long long)tc_weight_rows(n_out, c_in, transpose) * tc_weight_cols(n_out, c_in, ntaps, transpose);
+}
+
+extern "C" int tcn_split_weight(const float* w, int n_out, int c_in, int ntaps, int transpose, float* w_hi, float* w_lo,
+                                tcn_stream_t stream) {
+  TCN_REQUIRE(w && w_hi && w_lo && n_out > 0 && c_in > 0 && ntaps >= 1 && ntaps <= 3, "tcn_split_weight: bad arguments");
+  return launch_split_weight(w, w_hi, w_lo, n_out, c_in, ntaps, transpose, (cudaStream_t)stream);
+}
 
 extern "C" int tcn_gemm_tc(const tcn_gemm_tc_args* a, tcn_stream_t stream) {
   TCN_REQUIRE(a && a->x && a->w_hi && a->w_lo && a->y && a->meta, "tcn_gemm_tc: null pointer");
-  if (!tcn_gemm_tc_supported(a->k, a->n)) {
-    set_error("tcn_gemm_tc: needs k %% 32 == 0 and n %% 64 == 0 (got k=%d n=%d); use tcn_tapgemm", a->k, a->n);
+  if (!tcn_gemm_tc_supported(a->c_in, a->n_out)) {
+    set_error("tcn_gemm_tc: needs c_in %% 4 == 0 (got c_in=%d n_out=%d); use tcn_tapgemm", a->c_in, a->n_out);
     return TCN_ERR_UNSUPPORTED;
   }
-  TCN_REQUIRE(a->nblk > 0 && a->x_rows > 0 && a->ldx >= a->k && a->ldx % 4 == 0 && a->ldy >= a->n && a->ldy % 4 == 0,
+  TCN_REQUIRE(a->nblk > 0 && a->x_rows > 0 && a->ldx >= a->c_in && a->ldx % 4 == 0 && a->ldy >= a->n_out,
               "tcn_gemm_tc: bad shape");
-  TCN_REQUIRE((reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->y) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(a->w_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w_lo) & 15) == 0,
-              "tcn_gemm_tc: pointers must be 16-byte aligned");
-  TCN_REQUIRE(a->in_drop_p >= 0.f && a->in_drop_p < 1.f, "tcn_gemm_tc: in_drop_p must be in [0, 1)");
-  const int bn = (a->n % 128 == 0) ? 128 : 64;
+  TCN_REQUIRE(a->ntaps >= 1 && a->ntaps <= 3, "tcn_gemm_tc: ntaps must be 1..3");
+  TCN_REQUIRE((reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w_hi) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(a->w_lo) & 15) == 0,
+              "tcn_gemm_tc: x, w_hi, w_lo must be 16-byte aligned");
+  TCN_REQUIRE(a->in_drop_p >= 0.f && a->in_drop_p < 1.f && a->drop_p >= 0.f && a->drop_p < 1.f,
+              "tcn_gemm_tc: dropout probabilities must be in [0, 1)");
+  const long wrows = tc_weight_rows(a->n_out, a->c_in, 0);  // caller passes the (already oriented) logical shape
+  const long wcols = (long)a->ntaps * tc_kbp(a->c_in) * TC_BK;
   CUtensorMap mx, mh, ml;
-  TCN_CHECK(make_tensor_map_2d(&mx, a->x, a->x_rows, a->k, a->ldx, TC_BM));
-  TCN_CHECK(make_tensor_map_2d(&mh, a->w_hi, a->n, a->k, a->k, bn));
-  TCN_CHECK(make_tensor_map_2d(&ml, a->w_lo, a->n, a->k, a->k, bn));
+  TCN_CHECK(make_tensor_map_2d(&mx, a->x, a->x_rows, a->c_in, a->ldx, TC_BM));
+  TCN_CHECK(make_tensor_map_2d(&mh, a->w_hi, wrows, wcols, wcols, 64));
+  TCN_CHECK(make_tensor_map_2d(&ml, a->w_lo, wrows, wcols, wcols, 64));
   GemmTcDev p;
-  p.Y = a->y; p.ldy = a->ldy; p.bias = a->bias;
+  p.Y = a->y; p.ldy = a->ldy; p.N = a->n_out; p.bias = a->bias;
+  p.R = a->residual; p.ldr = a->ldr; p.M = a->relu_mask; p.ldm = a->ldm; p.relu = a->relu;
   p.meta = reinterpret_cast<const BlkMeta*>(a->meta); p.nblk = a->nblk; p.dyn = nullptr;
-  p.x_unpadded = a->x_unpadded; p.K = a->k; p.N = a->n;
+  p.x_unpadded = a->x_unpadded; p.ntaps = a->ntaps;
+  for (int i = 0; i < 3; ++i) p.shift[i] = a->shift[i];
+  p.kbp = tc_kbp(a->c_in); p.c_in = a->c_in;
   p.colscale = a->colscale; p.colscale_ld = a->colscale_ld;
   p.in_drop_thresh = a->in_drop_p > 0.f ? drop_thresh(a->in_drop_p) : 0u;
-  p.in_drop_scale = a->in_drop_rescale ? 1.f / (1.f - a->in_drop_p) : 1.f;
+  p.in_drop_scale = (a->in_drop_p > 0.f && a->in_drop_rescale) ? 1.f / (1.f - a->in_drop_p) : 1.f;
   p.in_drop_seed = a->drop_seed; p.in_drop_stream = a->drop_stream;
+  p.drop_thresh = a->drop_p > 0.f ? drop_thresh(a->drop_p) : 0u;
+  p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
+  p.drop_seed = a->drop_seed; p.drop_stream = a->drop_stream;
   return launch_gemm_tc(mx, mh, ml, p, 0, (cudaStream_t)stream);
-}
-
-extern "C" int tcn_split_weight(const float* w, float* w_hi, float* w_lo, long long n, tcn_stream_t stream) {
-  TCN_REQUIRE(w && w_hi && w_lo && n > 0, "tcn_split_weight: bad arguments");
-  return launch_split_weight(w, w_hi, w_lo, (long)n, (cudaStream_t)stream);
 }

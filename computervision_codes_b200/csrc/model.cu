@@ -231,7 +231,8 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
   const size_t o_gu = carve((size_t)rows * C * 4);
   const size_t o_cs = carve((size_t)cfg->max_seqs * D * 4);
   m->proj_tc = tcn_gemm_tc_supported(D, C) != 0;
-  const size_t o_whi = carve((size_t)C * D * 4), o_wlo = carve((size_t)C * D * 4);
+  const size_t proj_wf = (size_t)tcn_split_weight_floats(C, D, 1, 0);
+  const size_t o_whi = carve(proj_wf * 4), o_wlo = carve(proj_wf * 4);
   const size_t o_desc = carve(sizeof(BatchDesc) + (size_t)m->max_blk * sizeof(BlkMeta));
   const size_t o_cu = carve((size_t)m->LDH * 4), o_cscale = carve((size_t)m->LDH * 4), o_pw = carve((size_t)m->LDH * 4);
   const size_t o_ch = carve((size_t)m->LDH * 4), o_loss = carve(64);
@@ -265,9 +266,9 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
   m->proj_whi = reinterpret_cast<float*>(m->ws + o_whi);
   m->proj_wlo = reinterpret_cast<float*>(m->ws + o_wlo);
   if (m->proj_tc) {
-    const int br = gemm_tc_box_rows_for_n(C);
-    if (make_tensor_map_2d(&m->map_whi, m->proj_whi, C, D, D, br) != TCN_OK ||
-        make_tensor_map_2d(&m->map_wlo, m->proj_wlo, C, D, D, br) != TCN_OK)
+    const long wr = tc_weight_rows(C, D, 0), wc = tc_weight_cols(C, D, 1, 0);
+    if (make_tensor_map_2d(&m->map_whi, m->proj_whi, wr, wc, wc, 64) != TCN_OK ||
+        make_tensor_map_2d(&m->map_wlo, m->proj_wlo, wr, wc, wc, 64) != TCN_OK)
       m->proj_tc = false;  // driver without tensor-map support: stay on the mma.sync path
   }
   m->desc = reinterpret_cast<BatchDesc*>(m->ws + o_desc);
@@ -392,17 +393,18 @@ static int model_forward(tcn_model* m, const float* x, long x_rows, int training
   const bool chan = training && m->chan_drop_p > 0.f;
   if (chan) TCN_CHECK(launch_chan_scale(m->colscale, D, m->cfg.max_seqs, m->desc, m->chan_drop_p, 0u, kStreamChan, st));
   if (m->proj_tc) {  // tcgen05 + TMA (gemm_tc.cu)
-    TCN_CHECK(launch_split_weight(m->p_(m->off_proj_w), m->proj_whi, m->proj_wlo, (long)C * D, st));
+    TCN_CHECK(launch_split_weight(m->p_(m->off_proj_w), m->proj_whi, m->proj_wlo, C, D, 1, 0, st));
     if (m->map_x_ptr != x || m->map_x_rows != x_rows) {
       TCN_CHECK(make_tensor_map_2d(&m->map_x, x, x_rows, D, D, 128));
       m->map_x_ptr = x; m->map_x_rows = x_rows;
     }
     GemmTcDev p;
     memset(&p, 0, sizeof(p));
-    p.Y = m->act[0]; p.ldy = C; p.bias = m->p_(m->off_proj_b);
-    p.meta = m->meta; p.nblk = m->max_blk; p.dyn = m->desc; p.x_unpadded = 1; p.K = D; p.N = C;
+    p.Y = m->act[0]; p.ldy = C; p.N = C; p.bias = m->p_(m->off_proj_b);
+    p.meta = m->meta; p.nblk = m->max_blk; p.dyn = m->desc; p.x_unpadded = 1;
+    p.ntaps = 1; p.kbp = tc_kbp(D); p.c_in = D;
     if (chan) { p.colscale = m->colscale; p.colscale_ld = D; }
-    p.in_drop_scale = 1.f;
+    p.in_drop_scale = 1.f; p.drop_scale = 1.f;
     if (training && m->input_mask_p > 0.f) { p.in_drop_thresh = drop_thresh(m->input_mask_p); p.in_drop_stream = kStreamMask; }
     TCN_CHECK(launch_gemm_tc(m->map_x, m->map_whi, m->map_wlo, p, m->max_blk, st));
   } else {

@@ -92,33 +92,47 @@ def layer_fwd(x, w1f, w2f, b1, b2, lay: SeqLayout, shifts, save_h=True, drop_p=0
     return y, h
 
 
-def split_weight(w):
-    """(n, k) fp32 weight -> (w_hi, w_lo) with w_hi exactly representable in TF32 and w_hi + w_lo == w."""
+def split_weight(w, transpose: bool = False):
+    """torch weight (n_out, c_in[, ntaps]) -> (w_hi, w_lo) in the layout tcn_gemm_tc reads: rows = output column
+    (zero-padded to a multiple of 64), columns = tap * ceil(c_in/32)*32 + c; w_hi is exact in TF32, w_hi + w_lo == w.
+    transpose=True builds the operand of the input-gradient pass."""
     lib = _lib.load()
-    w = _f32c(w.detach()).reshape(w.shape[0], -1)
-    hi, lo = torch.empty_like(w), torch.empty_like(w)
-    _lib.check(lib.tcn_split_weight(_lib.ptr(w), _lib.ptr(hi), _lib.ptr(lo), w.numel(), _lib.stream_ptr()),
-               "tcn_split_weight")
+    w = _f32c(w.detach())
+    n_out, c_in = w.shape[0], w.shape[1]
+    ntaps = w.shape[2] if w.dim() == 3 else 1
+    n = lib.tcn_split_weight_floats(n_out, c_in, ntaps, int(transpose))
+    kcols = ntaps * ((((n_out if transpose else c_in) + 31) // 32) * 32)
+    hi = torch.empty(n // kcols, kcols, device=w.device, dtype=torch.float32)
+    lo = torch.empty_like(hi)
+    _lib.check(lib.tcn_split_weight(_lib.ptr(w), n_out, c_in, ntaps, int(transpose), _lib.ptr(hi), _lib.ptr(lo),
+                                    _lib.stream_ptr()), "tcn_split_weight")
     return hi, lo
 
 
-def gemm_tc(x, w_hi, w_lo, lay: SeqLayout, bias=None, out=None, x_unpadded=False, colscale=None, in_drop_p=0.0,
-            in_drop_rescale=False, seed=0, stream_id=0):
-    """tcgen05/TMA GEMM y = x @ W^T + bias over the packed rows (k % 32 == 0, n % 64 == 0)."""
+def gemm_tc(x, w_hi, w_lo, lay: SeqLayout, c_in, n_out, shifts=(0,), bias=None, out=None, ldy=None, residual=None,
+            relu_mask=None, relu=False, x_unpadded=False, colscale=None, in_drop_p=0.0, in_drop_rescale=False,
+            drop_p=0.0, seed=0, stream_id=0):
+    """tcgen05/TMA tap GEMM over the packed rows (same contract as tapgemm)."""
     lib = _lib.load()
     assert x.is_contiguous() and x.dim() == 2
-    n, k = w_hi.shape
+    if ldy is None:
+        ldy = round_up(n_out, 4)
     if out is None:
-        out = torch.zeros(lay.rows, n, device=x.device, dtype=torch.float32)
+        out = torch.zeros(lay.rows, ldy, device=x.device, dtype=torch.float32)
     a = _lib.GemmTcArgs()
     a.x, a.ldx, a.x_rows, a.x_unpadded = _lib.ptr(x), x.shape[1], x.shape[0], int(x_unpadded)
     a.w_hi, a.w_lo, a.bias = _lib.ptr(w_hi), _lib.ptr(w_lo), _lib.ptr(bias)
     a.y, a.ldy = _lib.ptr(out), out.shape[1]
+    a.residual, a.ldr = _lib.ptr(residual), (residual.shape[1] if residual is not None else 0)
+    a.relu_mask, a.ldm = _lib.ptr(relu_mask), (relu_mask.shape[1] if relu_mask is not None else 0)
     a.meta, a.nblk = _lib.ptr(lay.meta), lay.nblk
-    a.k, a.n = k, n
+    a.c_in, a.n_out, a.ntaps = c_in, n_out, len(shifts)
+    for i, sft in enumerate(shifts):
+        a.shift[i] = int(sft)
+    a.relu = int(relu)
     a.colscale, a.colscale_ld = _lib.ptr(colscale), (colscale.shape[1] if colscale is not None else 0)
     a.in_drop_p, a.in_drop_rescale = float(in_drop_p), int(in_drop_rescale)
-    a.drop_seed, a.drop_stream = int(seed) & 0xFFFFFFFF, int(stream_id) & 0xFFFFFFFF
+    a.drop_p, a.drop_seed, a.drop_stream = float(drop_p), int(seed) & 0xFFFFFFFF, int(stream_id) & 0xFFFFFFFF
     _lib.check(lib.tcn_gemm_tc(C.byref(a), _lib.stream_ptr()), "tcn_gemm_tc")
     return out
 

@@ -84,25 +84,38 @@ typedef struct {
 } tcn_wgrad_args;
 int tcn_wgrad(const tcn_wgrad_args* args, tcn_stream_t stream);
 
-/* ---- tcgen05 + TMA GEMM -----------------------------------------------------------------------------
- * y[r, n] = sum_k x[r, k] * W[n, k] + bias[n] on the 5th-gen tensor cores (tcgen05.mma kind::tf32, 3-term
- * split, TMEM accumulator, TMA-fed 4-stage ring): the stage-input projection Conv1d(dim -> C, 1) of
- * BaseCausalTCN (network.py:113,129) with Dropout2d's channel scale (colscale, :125-127) and the 25 % input
- * mask (in_drop_p with in_drop_rescale = 0, :43-50) folded into the operand load; also every Linear of
- * the MS-TCT blocks.  Needs k % 32 == 0 and n % 64 == 0 (tcn_gemm_tc_supported), else TCN_ERR_UNSUPPORTED.
- * w_hi / w_lo: (n, k) row-major halves of W from tcn_split_weight.  x_rows = rows addressable in x. */
+/* ---- tcgen05 + TMA tap GEMM ------------------------------------------------------------------------
+ * Same contract as tcn_tapgemm, executed on the 5th-gen tensor cores: tcgen05.mma kind::tf32 with a
+ * 3-term operand split (fp32-level accuracy), accumulator in TMEM, operands fed by TMA through a 4-stage
+ * shared-memory ring; a tap is the same TMA box fetched at a shifted row coordinate.
+ *   y[r, n] = epi( sum_tap sum_c x[r + shift[tap], c] * W[n, c, tap] + bias[n] ),
+ *   epi = relu -> (* [relu_mask > 0]) -> dropout(drop_p) -> (+ residual)
+ * Used for the stage-input projection Conv1d(dim -> C, 1) of BaseCausalTCN (network.py:113,129) with
+ * Dropout2d's channel scale (colscale, :125-127) and the 25 % input mask (in_drop_p, in_drop_rescale = 0,
+ * :43-50) folded into the operand load; for the convolutions of the residual layers and their
+ * input-gradient passes (network.py:178-198; in_drop_p with in_drop_rescale = 1 regenerates the
+ * dropout mask on the incoming gradient); for the FPN lateral, the heads, and the MS-TCT Linear layers.
+ * w_hi / w_lo come from tcn_split_weight (tcn_split_weight_floats each).  For an input-gradient pass
+ * split with transpose = 1 and call with (c_in, n_out) exchanged.  x_rows = rows addressable behind x
+ * (rows outside [0, x_rows) read as zero).  Needs c_in % 4 == 0 (tcn_gemm_tc_supported). */
 typedef struct {
   const float* x; int ldx; long long x_rows; int x_unpadded;
   const float* w_hi; const float* w_lo; const float* bias;
   float* y; int ldy;
+  const float* residual; int ldr;
+  const float* relu_mask; int ldm;
   const int* meta; int nblk;
-  int k; int n;
+  int c_in; int n_out; int ntaps; int shift[3];
+  int relu;
   const float* colscale; int colscale_ld;
-  float in_drop_p; int in_drop_rescale; unsigned drop_seed; unsigned drop_stream;
+  float in_drop_p; int in_drop_rescale;
+  float drop_p; unsigned drop_seed; unsigned drop_stream;
 } tcn_gemm_tc_args;
-int tcn_gemm_tc_supported(int k, int n);
+int tcn_gemm_tc_supported(int c_in, int n_out);
 int tcn_gemm_tc(const tcn_gemm_tc_args* args, tcn_stream_t stream);
-int tcn_split_weight(const float* w, float* w_hi, float* w_lo, long long n, tcn_stream_t stream);
+long long tcn_split_weight_floats(int n_out, int c_in, int ntaps, int transpose);
+int tcn_split_weight(const float* w, int n_out, int c_in, int ntaps, int transpose, float* w_hi, float* w_lo,
+                     tcn_stream_t stream);
 
 /* ---- fused residual layer, forward ---------------------------------------------------------------
  * y = x + Dropout_p(W2 relu(W1 (*)_d x + b1) + b2), one launch: DilatedResidualLayer.forward

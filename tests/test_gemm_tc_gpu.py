@@ -12,7 +12,8 @@ def _maxabs(a, b):
 
 @pytest.mark.parametrize("lengths,K,N,unpadded", [([1800], 2048, 64, True), ([300, 170, 129], 96, 64, True),
                                                    ([256, 40], 768, 128, False), ([130], 32, 192, False),
-                                                   ([1000, 999], 512, 256, True)])
+                                                   ([1000, 999], 512, 256, True), ([200, 77], 132, 64, False),
+                                                   ([140], 64, 131, False), ([90], 100, 7, True)])
 def test_gemm_tc_matches_fp64(lengths, K, N, unpadded):
     from computervision_codes_b200 import ops
     from computervision_codes_b200.layout import SeqLayout
@@ -30,18 +31,20 @@ def test_gemm_tc_matches_fp64(lengths, K, N, unpadded):
             x[lay.starts[s]:lay.starts[s] + T] = xs[s]
         x = x.to(DEV)
     hi, lo = ops.split_weight(w.to(DEV))
-    assert torch.equal((hi + lo).cpu(), w)
-    y = ops.gemm_tc(x, hi, lo, lay, bias=b.to(DEV), x_unpadded=unpadded)
+    assert torch.equal((hi + lo).cpu()[:N, :K], w)
+    y = ops.gemm_tc(x, hi, lo, lay, K, N, bias=b.to(DEV), x_unpadded=unpadded)
     torch.cuda.synchronize()
     for s, T in enumerate(lengths):
         ref = xs[s].double() @ w.double().t() + b.double()
-        got = y[lay.starts[s]:lay.starts[s] + T]
+        got = y[lay.starts[s]:lay.starts[s] + T, :N]
         err = _maxabs(got, ref)
         assert err <= 4e-6 * max(1.0, float(ref.abs().max())) + 1e-6 * K ** 0.5, (lengths, K, N, err)
     # rows between sequences are never written
     for s, T in enumerate(lengths):
         end = lay.starts[s + 1] if s + 1 < len(lengths) else lay.rows
         assert float(y[lay.starts[s] + T:end].abs().max() if end > lay.starts[s] + T else 0.0) == 0.0
+    if y.shape[1] > N:
+        assert float(y[:, N:].abs().max()) == 0.0
 
 
 def test_gemm_tc_channel_scale_and_input_mask():
@@ -56,7 +59,7 @@ def test_gemm_tc_channel_scale_and_input_mask():
     hi, lo = ops.split_weight(w.to(DEV))
     cs = (torch.rand(len(lengths), K) > 0.5).float() * 2.0
     seed, sid = 99, 0x7fff0002
-    y = ops.gemm_tc(torch.cat(xs).to(DEV), hi, lo, lay, x_unpadded=True, colscale=cs.to(DEV), in_drop_p=0.25,
+    y = ops.gemm_tc(torch.cat(xs).to(DEV), hi, lo, lay, K, N, x_unpadded=True, colscale=cs.to(DEV), in_drop_p=0.25,
                     in_drop_rescale=False, seed=seed, stream_id=sid)
     keep = ops.dropout_keep_mask(lay.rows, K, 0.25, seed, sid, DEV).cpu().double()
     assert 0.72 < float(keep.mean()) < 0.78
@@ -65,3 +68,47 @@ def test_gemm_tc_channel_scale_and_input_mask():
         xm = xs[s].double() * cs[s].double() * keep[r0:r0 + T]
         ref = xm @ w.double().t()
         assert _maxabs(y[r0:r0 + T], ref) <= 1e-5
+
+
+@pytest.mark.parametrize("shifts", [(-1, 0, 1), (-4, 0, 4), (-512, 0, 512), (-2, -1, 0), (-64, -32, 0), (0,)])
+def test_gemm_tc_taps_and_epilogue_match_mma_sync_path_and_fp64(shifts):
+    """Taps, sequence-boundary zeroing and the full epilogue: tcgen05 kernel == mma.sync kernel == fp64."""
+    from computervision_codes_b200 import ops
+    from computervision_codes_b200.layout import SeqLayout
+    from oracle import tcn_oracle as O
+
+    torch.manual_seed(5 + len(shifts) + abs(shifts[0]))
+    lengths, C = [300, 129, 1000], 64
+    lay = SeqLayout.get(lengths, DEV)
+    ntaps = len(shifts)
+    w = torch.randn(C, C, ntaps) / (C * ntaps) ** 0.5
+    b = torch.randn(C)
+    x = torch.zeros(lay.rows, C)
+    res = torch.zeros(lay.rows, C)
+    msk = torch.zeros(lay.rows, C)
+    xs = []
+    for s, T in enumerate(lengths):
+        xs.append(torch.randn(T, C))
+        x[lay.starts[s]:lay.starts[s] + T] = xs[-1]
+        res[lay.starts[s]:lay.starts[s] + T] = torch.randn(T, C)
+        msk[lay.starts[s]:lay.starts[s] + T] = torch.randn(T, C)
+    x, res, msk = x.to(DEV), res.to(DEV), msk.to(DEV)
+    hi, lo = ops.split_weight(w.to(DEV))
+    y = ops.gemm_tc(x, hi, lo, lay, C, C, shifts, bias=b.to(DEV), residual=res, relu_mask=msk, drop_p=0.5, seed=3,
+                    stream_id=9)
+    y2 = ops.tapgemm(x, ops.prep_weight(w.to(DEV)), lay, C, C, shifts, bias=b.to(DEV), residual=res, relu_mask=msk,
+                     drop_p=0.5, seed=3, stream_id=9)
+    assert _maxabs(y, y2) <= 2e-5
+    keep = ops.dropout_keep_mask(lay.rows, C, 0.5, 3, 9, DEV).cpu().double()
+    for s, T in enumerate(lengths):
+        r0 = lay.starts[s]
+        u = O.conv_taps(xs[s].double().t().unsqueeze(0), w.double(), b.double(), shifts)[0].t()
+        u = u * (msk[r0:r0 + T].cpu().double() > 0) * keep[r0:r0 + T] * 2.0 + res[r0:r0 + T].cpu().double()
+        assert _maxabs(y[r0:r0 + T], u) <= 2e-5
+    # relu + dropout applied to the loaded operand (the backward of a dropout), transposed weights
+    hit, lot = ops.split_weight(w.to(DEV), transpose=True)
+    g = ops.gemm_tc(x, hit, lot, lay, C, C, tuple(-s for s in shifts), relu=True, in_drop_p=0.5, in_drop_rescale=True,
+                    seed=3, stream_id=9)
+    g2 = ops.tapgemm(x, ops.prep_weight(w.to(DEV), transpose=True), lay, C, C, tuple(-s for s in shifts), relu=True,
+                     in_drop_p=0.5, seed=3, stream_id=9)
+    assert _maxabs(g, g2) <= 2e-5

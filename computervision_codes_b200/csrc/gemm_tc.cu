@@ -25,6 +25,180 @@
 
 namespace tcn {
 
+
+// Operand split of one 128 x 32 fp32 tile (TMA layout, 128B swizzle) by 128 threads: X -> (X_hi in place, X_lo).
+// All eight 16-byte chunks of a thread are loaded before any is processed; rows whose tap source leaves the
+// sequence are zeroed with selects (no divergent control flow on the fast path).
+__device__ __forceinline__ void split_tile(float4* __restrict__ xa, float4* __restrict__ xl, int ct, int row0, int sh,
+                                           const BlkMeta& m, int kc, const GemmTcDev& p, uint32_t in_seed) {
+  float4 v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = xa[ct + i * 128];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int src = row0 + ((ct + i * 128) >> 3) + sh;
+    const float keep = (src >= m.lo && src < m.hi) ? 1.f : 0.f;
+    v[i].x *= keep; v[i].y *= keep; v[i].z *= keep; v[i].w *= keep;
+  }
+  if (p.colscale != nullptr || p.in_drop_thresh != 0u) {  // CTA-uniform, rare (projection in training)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = ct + i * 128, r = c >> 3;
+      const int src = row0 + r + sh;
+      const int col = kc * TC_BK + (((c & 7) ^ (r & 7)) << 2);  // undo the 128B swizzle
+      if (p.colscale != nullptr && col < p.c_in) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.colscale + (size_t)m.seq * p.colscale_ld + col));
+        v[i].x *= sc.x; v[i].y *= sc.y; v[i].z *= sc.z; v[i].w *= sc.w;
+      }
+      if (p.in_drop_thresh != 0u) {
+        v[i].x *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col);
+        v[i].y *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col + 1);
+        v[i].z *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col + 2);
+        v[i].w *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col + 3);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xffffe000u); l.x = v[i].x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u); l.y = v[i].y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u); l.z = v[i].z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u); l.w = v[i].w - h.w;
+    xa[ct + i * 128] = h;
+    xl[ct + i * 128] = l;
+  }
+}
+
+// Epilogue of four consecutive output columns of one row: bias, relu, relu-mask, dropout, residual, store.
+__device__ __forceinline__ void epilogue_vec4(float (&o)[4], int row, int n, const GemmTcDev& p, uint32_t out_seed,
+                                              bool vec_ok) {
+  if (n >= p.N) return;
+  const bool full4 = (n + 3 < p.N) && vec_ok;
+  if (full4) {
+    if (p.bias != nullptr) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+      o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+    }
+    if (p.M != nullptr) {
+      const float4 mk = *reinterpret_cast<const float4*>(p.M + (size_t)row * p.ldm + n);
+      if (!(mk.x > 0.f)) o[0] = 0.f;
+      if (!(mk.y > 0.f)) o[1] = 0.f;
+      if (!(mk.z > 0.f)) o[2] = 0.f;
+      if (!(mk.w > 0.f)) o[3] = 0.f;
+    }
+    if (p.drop_thresh != 0u) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] *= drop_factor(out_seed, p.drop_stream, p.drop_thresh, p.drop_scale, row, n + e);
+    }
+    if (p.R != nullptr) {
+      const float4 rr = *reinterpret_cast<const float4*>(p.R + (size_t)row * p.ldr + n);
+      o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+    }
+    *reinterpret_cast<float4*>(p.Y + (size_t)row * p.ldy + n) = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (n + e < p.N) {
+        float x = o[e];
+        if (p.bias != nullptr) x += __ldg(p.bias + n + e);
+        if (p.relu) x = fmaxf(x, 0.f);
+        if (p.M != nullptr && !(p.M[(size_t)row * p.ldm + n + e] > 0.f)) x = 0.f;
+        if (p.drop_thresh != 0u) x *= drop_factor(out_seed, p.drop_stream, p.drop_thresh, p.drop_scale, row, n + e);
+        if (p.R != nullptr) x += p.R[(size_t)row * p.ldr + n + e];
+        p.Y[(size_t)row * p.ldy + n + e] = x;
+      }
+    }
+  }
+}
+
+// Row-per-thread epilogue of 32 accumulator columns (streaming kernel: one tile per CTA).
+__device__ __forceinline__ void epilogue_cols(const float (&v)[32], int row, int n_base, const GemmTcDev& p,
+                                              uint32_t out_seed, bool vec_ok) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    float o[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
+    epilogue_vec4(o, row, n_base + j, p, out_seed, vec_ok);
+  }
+}
+
+// Coalesced epilogue of a warp's 32 x 64 accumulator block: the TMEM layout (one row per lane) is
+// transposed through a private, XOR-swizzled 8 KB staging buffer so that every global access of the
+// epilogue (mask / residual loads, output stores) covers two full 256-byte rows per warp instruction.
+__device__ __forceinline__ void epilogue_block_coalesced(const float (&v0)[32], const float (&v1)[32], float4* st,
+                                                         int lane, int row_base, int row_hi, int n_base,
+                                                         const GemmTcDev& p, uint32_t out_seed, bool vec_ok) {
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const int cs = (c & 8) | ((c & 7) ^ (lane & 7));
+    st[lane * 16 + cs] = (c < 8) ? make_float4(v0[4 * c], v0[4 * c + 1], v0[4 * c + 2], v0[4 * c + 3])
+                                 : make_float4(v1[4 * c - 32], v1[4 * c - 31], v1[4 * c - 30], v1[4 * c - 29]);
+  }
+  __syncwarp();
+  if (vec_ok && n_base + 64 <= p.N) {
+    // fast path (full 64-column block): all mask / residual loads of 8 float4 are in flight before they are used
+    const uint32_t th = p.drop_thresh;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float4 a[8], mk[8], rr[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int f = (half * 8 + i) * 32 + lane;
+        const int r = f >> 4, c = f & 15;
+        const int rowc = min(row_base + r, row_hi - 1);  // clamp: loads stay in bounds, the store is predicated
+        a[i] = st[r * 16 + ((c & 8) | ((c & 7) ^ (r & 7)))];
+        if (p.M != nullptr) mk[i] = *reinterpret_cast<const float4*>(p.M + (size_t)rowc * p.ldm + n_base + c * 4);
+        if (p.R != nullptr) rr[i] = *reinterpret_cast<const float4*>(p.R + (size_t)rowc * p.ldr + n_base + c * 4);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int f = (half * 8 + i) * 32 + lane;
+        const int r = f >> 4, c = f & 15;
+        const int row = row_base + r, n = n_base + c * 4;
+        float o[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+        if (p.bias != nullptr) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+        }
+        if (p.M != nullptr) {
+          if (!(mk[i].x > 0.f)) o[0] = 0.f;
+          if (!(mk[i].y > 0.f)) o[1] = 0.f;
+          if (!(mk[i].z > 0.f)) o[2] = 0.f;
+          if (!(mk[i].w > 0.f)) o[3] = 0.f;
+        }
+        if (th != 0u) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] *= drop_factor(out_seed, p.drop_stream, th, p.drop_scale, row, n + e);
+        }
+        if (p.R != nullptr) { o[0] += rr[i].x; o[1] += rr[i].y; o[2] += rr[i].z; o[3] += rr[i].w; }
+        if (row < row_hi)
+          *reinterpret_cast<float4*>(p.Y + (size_t)row * p.ldy + n) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  } else {
+#pragma unroll 2
+    for (int i = 0; i < 16; ++i) {
+      const int f = i * 32 + lane;
+      const int r = f >> 4, c = f & 15;
+      const float4 a = st[r * 16 + ((c & 8) | ((c & 7) ^ (r & 7)))];
+      const int row = row_base + r;
+      if (row < row_hi) {
+        float o[4] = {a.x, a.y, a.z, a.w};
+        epilogue_vec4(o, row, n_base + c * 4, p, out_seed, vec_ok);
+      }
+    }
+  }
+  __syncwarp();
+}
+
 template <int BN>
 struct TcSmem {
   static constexpr int kStages = BN > 64 ? 3 : 4;
@@ -137,37 +311,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const uint32_t ph = (kb / TC_STAGES) & 1;
         const int sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
         mbar_wait(&full_bar[s], ph);
-        float4* xa = reinterpret_cast<float4*>(tiles + s * S::kStage);
-        float4* xl = reinterpret_cast<float4*>(tiles + s * S::kStage + S::kA);
-#pragma unroll
-        for (int i = 0; i < (TC_BM * TC_BK / 4) / 128; ++i) {
-          const int c = ct + i * 128;  // physical 16-byte chunk inside the tile
-          const int r = c >> 3;
-          const int src = row0 + r + sh;
-          float4 v = xa[c];
-          if (src < m.lo || src >= m.hi) {
-            v = make_float4(0.f, 0.f, 0.f, 0.f);  // the tap leaves its sequence
-          } else if (p.colscale != nullptr || p.in_drop_thresh != 0u) {
-            const int col = kc * TC_BK + (((c & 7) ^ (r & 7)) << 2);  // undo the 128B swizzle
-            if (p.colscale != nullptr && col < p.c_in) {
-              const float4 sc = __ldg(reinterpret_cast<const float4*>(p.colscale + (size_t)m.seq * p.colscale_ld + col));
-              v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
-            }
-            if (p.in_drop_thresh != 0u) {
-              v.x *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col);
-              v.y *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col + 1);
-              v.z *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col + 2);
-              v.w *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col + 3);
-            }
-          }
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-          xa[c] = h;
-          xl[c] = l;
-        }
+        split_tile(reinterpret_cast<float4*>(tiles + s * S::kStage),
+                   reinterpret_cast<float4*>(tiles + s * S::kStage + S::kA), ct, row0, sh, m, kc, p, in_seed);
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(&ready_bar[s]);
         if (++kc == p.kbp) { kc = 0; ++tap; }
@@ -184,57 +329,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
         tmem_ld32(taddr + c0, v);  // warp-collective: every lane takes part, stores are predicated below
-        if (row < m.hi) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int n = ntile * BN + c0 + j;
-            if (n < p.N) {
-              float o[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
-              const bool full4 = (n + 3 < p.N) && vec_ok;
-              if (full4) {
-                if (p.bias != nullptr) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                  o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
-                }
-                if (p.relu) {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
-                }
-                if (p.M != nullptr) {
-                  const float4 mk = *reinterpret_cast<const float4*>(p.M + (size_t)row * p.ldm + n);
-                  if (!(mk.x > 0.f)) o[0] = 0.f;
-                  if (!(mk.y > 0.f)) o[1] = 0.f;
-                  if (!(mk.z > 0.f)) o[2] = 0.f;
-                  if (!(mk.w > 0.f)) o[3] = 0.f;
-                }
-                if (p.drop_thresh != 0u) {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e)
-                    o[e] *= drop_factor(out_seed, p.drop_stream, p.drop_thresh, p.drop_scale, row, n + e);
-                }
-                if (p.R != nullptr) {
-                  const float4 rr = *reinterpret_cast<const float4*>(p.R + (size_t)row * p.ldr + n);
-                  o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
-                }
-                *reinterpret_cast<float4*>(p.Y + (size_t)row * p.ldy + n) = make_float4(o[0], o[1], o[2], o[3]);
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  if (n + e < p.N) {
-                    float x = o[e];
-                    if (p.bias != nullptr) x += __ldg(p.bias + n + e);
-                    if (p.relu) x = fmaxf(x, 0.f);
-                    if (p.M != nullptr && !(p.M[(size_t)row * p.ldm + n + e] > 0.f)) x = 0.f;
-                    if (p.drop_thresh != 0u)
-                      x *= drop_factor(out_seed, p.drop_stream, p.drop_thresh, p.drop_scale, row, n + e);
-                    if (p.R != nullptr) x += p.R[(size_t)row * p.ldr + n + e];
-                    p.Y[(size_t)row * p.ldy + n + e] = x;
-                  }
-                }
-              }
-            }
-          }
-        }
+        if (row < m.hi) epilogue_cols(v, row, ntile * BN + c0, p, out_seed, vec_ok);
       }
     }
   }
@@ -244,6 +339,184 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     constexpr uint32_t kCols = BN < 32 ? 32 : BN;
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(kCols));
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Persistent variant for short contractions (ntaps * ceil(c_in/32) <= 6 k-blocks: every convolution of the
+// residual layers, the FPN lateral, the heads and their input gradients).  One CTA per SM walks over the
+// 128-frame tiles; the split weights stay resident in shared memory, the accumulator is double-buffered in
+// TMEM, and four dedicated epilogue warps drain tile i while the producer / split / MMA warps are already
+// working on tile i + 1.
+//   warp 0: TMA producer | warp 1: MMA issuer + TMEM owner | warps 2-5: operand split | warps 6-9: epilogue
+constexpr int TP_THREADS = 320;
+constexpr int TP_STAGES = 3;
+constexpr int TP_MAX_KB = 6;
+constexpr int TP_KA = TC_BM * TC_BK * 4;  // 16384: one A tile
+constexpr int TP_KB = 64 * TC_BK * 4;     //  8192: one B tile (64 output columns)
+constexpr int TP_EPI = 4 * 32 * 64 * 4;   // 32768: per-warp 32 x 64 fp32 epilogue staging
+static inline int tp_smem_bytes(int kblocks) { return kblocks * 2 * TP_KB + TP_STAGES * 2 * TP_KA + TP_EPI + 1024 + 256; }
+
+__global__ void __launch_bounds__(TP_THREADS, 1)
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
+                       const __grid_constant__ CUtensorMap map_wlo, const GemmTcDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntile = blockIdx.y;
+  const int nblk = p.dyn ? p.dyn->nblk : p.nblk;
+  const int kblocks = p.ntaps * p.kbp;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* wt = smem_raw + (base - smem_u32(smem_raw));   // resident weights: kb -> [hi 8 KB | lo 8 KB]
+  uint8_t* at = wt + kblocks * 2 * TP_KB;                 // A ring: stage -> [X / X_hi 16 KB | X_lo 16 KB]
+  const uint32_t wt_addr = base, at_addr = base + kblocks * 2 * TP_KB;
+  float4* epi = reinterpret_cast<float4*>(at + TP_STAGES * 2 * TP_KA);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(at + TP_STAGES * 2 * TP_KA + TP_EPI);
+  uint64_t* wfull = bars;
+  uint64_t* full_bar = bars + 1;
+  uint64_t* ready_bar = full_bar + TP_STAGES;
+  uint64_t* empty_bar = ready_bar + TP_STAGES;
+  uint64_t* tfull = empty_bar + TP_STAGES;   // [2] accumulator complete (tcgen05.commit)
+  uint64_t* tempty = tfull + 2;              // [2] accumulator drained (128 epilogue threads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  if (threadIdx.x == 0) {
+    mbar_init(wfull, 1);
+    for (int s = 0; s < TP_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&ready_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                 "r"(128u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t dseed = p.dyn ? p.dyn->seed : 0u;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wfull, kblocks * 2 * TP_KB);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        tma_load_2d(wt + kb * 2 * TP_KB, &map_whi, wfull, kb * TC_BK, ntile * 64);
+        tma_load_2d(wt + kb * 2 * TP_KB + TP_KB, &map_wlo, wfull, kb * TC_BK, ntile * 64);
+      }
+      int it = 0;
+      for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const BlkMeta m = p.meta[blk];
+        const int row0 = blk * kBlkRows;
+        if (row0 >= m.hi) continue;
+        const int xrow = row0 + (p.x_unpadded ? m.in_delta : 0);
+        int tap = 0, kc = 0;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % TP_STAGES;
+          const uint32_t ph = (it / TP_STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], TP_KA);
+          const int sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
+          tma_load_2d(at + s * 2 * TP_KA, &map_x, &full_bar[s], kc * TC_BK, xrow + sh);
+          if (++kc == p.kbp) { kc = 0; ++tap; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, 64);
+    mbar_wait(wfull, 0);
+    int it = 0, tcount = 0;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      const BlkMeta m = p.meta[blk];
+      if (blk * kBlkRows >= m.hi) continue;
+      const int a = tcount & 1;
+      const uint32_t tph = (tcount >> 1) & 1;
+      mbar_wait(&tempty[a], tph ^ 1);  // the epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + a * 64;
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const int s = it % TP_STAGES;
+        const uint32_t ph = (it / TP_STAGES) & 1;
+        mbar_wait(&ready_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = at_addr + s * 2 * TP_KA, a_lo = a_hi + TP_KA;
+          const uint32_t b_hi = wt_addr + kb * 2 * TP_KB, b_lo = b_hi + TP_KB;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint32_t ko = k * 32;
+            const uint64_t dah = umma_desc_sw128(a_hi + ko), dal = umma_desc_sw128(a_lo + ko);
+            const uint64_t dbh = umma_desc_sw128(b_hi + ko), dbl = umma_desc_sw128(b_lo + ko);
+            umma_tf32(tacc, dal, dbh, idesc, (kb | k) != 0);
+            umma_tf32(tacc, dah, dbl, idesc, 1u);
+            umma_tf32(tacc, dah, dbh, idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (kb == kblocks - 1) umma_commit(&tfull[a]);
+        }
+        __syncwarp();
+      }
+      ++tcount;
+    }
+  } else if (warp < 6) {
+    // ===================== operand split (warps 2..5) =====================
+    const int ct = threadIdx.x - 64;
+    const uint32_t in_seed = p.in_drop_seed ^ dseed;
+    int it = 0;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      const BlkMeta m = p.meta[blk];
+      const int row0 = blk * kBlkRows;
+      if (row0 >= m.hi) continue;
+      int tap = 0, kc = 0;
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const int s = it % TP_STAGES;
+        const uint32_t ph = (it / TP_STAGES) & 1;
+        const int sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
+        mbar_wait(&full_bar[s], ph);
+        split_tile(reinterpret_cast<float4*>(at + s * 2 * TP_KA), reinterpret_cast<float4*>(at + s * 2 * TP_KA + TP_KA),
+                   ct, row0, sh, m, kc, p, in_seed);
+        fence_proxy_async();
+        mbar_arrive(&ready_bar[s]);
+        if (++kc == p.kbp) { kc = 0; ++tap; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 6..9; TMEM lane quadrant = warp % 4) =====================
+    const int q = warp & 3;
+    const uint32_t out_seed = p.drop_seed ^ dseed;
+    const bool vec_ok = ((p.ldy & 3) == 0) && (p.R == nullptr || (p.ldr & 3) == 0) && (p.M == nullptr || (p.ldm & 3) == 0);
+    int tcount = 0;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      const BlkMeta m = p.meta[blk];
+      const int row0 = blk * kBlkRows;
+      if (row0 >= m.hi) continue;
+      const int a = tcount & 1;
+      const uint32_t tph = (tcount >> 1) & 1;
+      mbar_wait(&tfull[a], tph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * 64;
+      float v0[32], v1[32];
+      tmem_ld32(taddr, v0);
+      tmem_ld32(taddr + 32, v1);
+      tc_fence_before();
+      mbar_arrive(&tempty[a]);  // the MMA warp may overwrite this accumulator
+      epilogue_block_coalesced(v0, v1, epi + (warp - 6) * 512, lane, row0 + q * 32, m.hi, ntile * 64, p, out_seed,
+                               vec_ok);
+      ++tcount;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(128u));
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -346,7 +619,28 @@ int launch_split_batched(const SplitJob* jobs_dev, int njobs, const float* param
 int launch_gemm_tc(const CUtensorMap& mx, const CUtensorMap& mwhi, const CUtensorMap& mwlo, const GemmTcDev& p,
                    int cap_nblk, cudaStream_t stream) {
   const int nb = cap_nblk > 0 ? cap_nblk : p.nblk;
-  dim3 grid(nb, (p.N + 63) / 64);
+  const int kblocks = p.ntaps * p.kbp;
+  const int nty = (p.N + 63) / 64;
+  if (kblocks <= TP_MAX_KB) {  // persistent, weights resident in shared memory
+    static int max_set = 0;
+    const int smem = tp_smem_bytes(kblocks);
+    if (smem > max_set) {
+      const cudaError_t e =
+          cudaFuncSetAttribute(gemm_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tp_smem_bytes(TP_MAX_KB));
+      if (e != cudaSuccess) {
+        set_error("gemm_tc_persist: smem attribute: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return TCN_ERR_CUDA;
+      }
+      max_set = tp_smem_bytes(TP_MAX_KB);
+    }
+    int gx = num_sms() / nty;
+    if (gx < 1) gx = 1;
+    if (gx > nb) gx = nb;
+    gemm_tc_persist_kernel<<<dim3(gx, nty), TP_THREADS, smem, stream>>>(mx, mwhi, mwlo, p);
+    return check_launch("gemm_tc_persist_kernel");
+  }
+  dim3 grid(nb, nty);
   static bool attr_set = false;
   if (!attr_set) {
     const cudaError_t e =

@@ -17,14 +17,20 @@ if os.path.exists("MEASURED_PEAKS.json"):
     PEAK = float(json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"])
 
 
-def timeit(fn, n=20, warm=3):
+def timeit(fn, n=24, warm=3):
+    """Average GPU time per launch: n launches captured in one CUDA graph (no host launch overhead)."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(n):
-        fn()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
@@ -102,6 +108,37 @@ def main():
             print(json.dumps({"kernel": nm, "shape": name, "ms": round(ms, 4),
                               "alg_GBps": round(byt * frames / ms / 1e6, 1),
                               "executed_TFLOPs_3xtf32": round(flops * frames * 3 / ms / 1e9, 1)}))
+        # the same four shapes on the tcgen05 tap GEMM
+        h1, l1 = ops.split_weight(w1)
+        h2, l2 = ops.split_weight(w2)
+        h1t, l1t = ops.split_weight(w1, True)
+        h2t, l2t = ops.split_weight(w2, True)
+
+        def tc_conv3():
+            i = it[0] % nbuf; it[0] += 1
+            ops.gemm_tc(xs[i], h1, l1, lay, C, C, shifts, bias=b, out=ys[i], relu=True)
+
+        def tc_conv1():
+            i = it[0] % nbuf; it[0] += 1
+            ops.gemm_tc(xs[i], h2, l2, lay, C, C, (0,), bias=b, out=ys[i], residual=hs[i], drop_p=0.5, seed=1, stream_id=2)
+
+        def tc_dgrad1():
+            i = it[0] % nbuf; it[0] += 1
+            ops.gemm_tc(xs[i], h2t, l2t, lay, C, C, (0,), out=ys[i], relu_mask=hs[i], in_drop_p=0.5, in_drop_rescale=True,
+                        seed=1, stream_id=2)
+
+        def tc_dgrad2():
+            i = it[0] % nbuf; it[0] += 1
+            ops.gemm_tc(xs[i], h1t, l1t, lay, C, C, tuple(-s for s in shifts), out=ys[i], residual=hs[i])
+
+        for nm, fn, flops, byt in (("gemm_tc conv3+relu", tc_conv3, 6 * C * C, 8 * C),
+                                   ("gemm_tc conv1x1+drop+res", tc_conv1, 2 * C * C, 12 * C),
+                                   ("gemm_tc dgrad1", tc_dgrad1, 2 * C * C, 12 * C),
+                                   ("gemm_tc dgrad2", tc_dgrad2, 6 * C * C, 12 * C)):
+            ms = timeit(fn)
+            print(json.dumps({"kernel": nm, "shape": name, "ms": round(ms, 4),
+                              "alg_GBps": round(byt * frames / ms / 1e6, 1),
+                              "executed_TFLOPs_3xtf32": round(flops * frames * 3 / ms / 1e9, 1)}))
         # stage-input projection 2048 -> 64
         if True:
             D = 2048 if frames <= 100000 else 768
@@ -114,7 +151,7 @@ def main():
                               "frac_hbm": round(4 * (D + C) * frames / ms / 1e6 / PEAK, 4),
                               "executed_TFLOPs_3xtf32": round(2 * D * C * frames * 3 / ms / 1e9, 1)}))
             whi, wlo = ops.split_weight(torch.randn(C, D, device=DEV) / D ** 0.5)
-            ms = timeit(lambda: ops.gemm_tc(x, whi, wlo, lay, bias=b, out=out, x_unpadded=True))
+            ms = timeit(lambda: ops.gemm_tc(x, whi, wlo, lay, D, C, bias=b, out=out, x_unpadded=True))
             print(json.dumps({"kernel": "gemm_tc (tcgen05+TMA) projection 2048->64", "shape": name, "ms": round(ms, 4),
                               "alg_GBps": round(4 * (D + C) * frames / ms / 1e6, 1),
                               "frac_hbm": round(4 * (D + C) * frames / ms / 1e6 / PEAK, 4),

@@ -6,8 +6,11 @@
 // (:98-106, latlayer1 three times, interpolate == identity) -> conv_out / _i / _v / _t on the four
 // levels (:63-67), and the loss of train_loop (Temporal_tenco/run.py:190-212; TERL variant
 // TERL/0_5fold_TCN_black/run.py:307-343).  Backward follows the closed forms of SURVEY.md section 8a.
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "gemm_tc.cuh"
@@ -58,6 +61,20 @@ struct tcn_model {
   float* gbuf[2] = {nullptr, nullptr};
   float* gu = nullptr;
   float* colscale = nullptr;
+  // tcgen05 path: split (hi / lo) copies of every weight + their TMA maps, keyed by the float offset of the
+  // fragment-ordered copy the mma.sync kernels use; TMA maps of the activation buffers keyed by (pointer, columns)
+  struct TcW {
+    long off = 0, rows = 0, cols = 0;
+    CUtensorMap mh, ml;
+  };
+  bool use_tc = false;
+  std::map<long, TcW> tcw;
+  std::map<std::pair<const float*, int>, CUtensorMap> xmaps;
+  float *tc_whi = nullptr, *tc_wlo = nullptr;
+  long tc_wfloats = 0;
+  SplitJob* sjobs_dev = nullptr;
+  int nsjobs = 0;
+  long split_total = 0;
   // tcgen05 projection: split weight halves + their TMA maps (fixed addresses), X map cached per pointer
   bool proj_tc = false;
   float *proj_whi = nullptr, *proj_wlo = nullptr;
@@ -127,7 +144,32 @@ WgradDev base_wgrad(const tcn_model* m) {
   return p;
 }
 
-int gemm(const tcn_model* m, TapGemmDev& p, int c_in, int n_out, cudaStream_t st) {
+int gemm(tcn_model* m, TapGemmDev& p, int c_in, int n_out, cudaStream_t st) {
+  if (m->use_tc && !p.x_unpadded) {
+    const long key = reinterpret_cast<const float*>(p.Wf) - m->wf;
+    auto it = m->tcw.find(key);
+    if (it != m->tcw.end()) {
+      const auto xkey = std::make_pair(p.X, p.ldx);
+      auto xm = m->xmaps.find(xkey);
+      if (xm == m->xmaps.end()) {
+        CUtensorMap map;
+        TCN_CHECK(make_tensor_map_2d(&map, p.X, m->cfg.max_rows, p.ldx, p.ldx, TC_BM));
+        xm = m->xmaps.emplace(xkey, map).first;
+      }
+      GemmTcDev q;
+      memset(&q, 0, sizeof(q));
+      q.Y = p.Y; q.ldy = p.ldy; q.N = n_out; q.bias = p.bias; q.R = p.R; q.ldr = p.ldr; q.M = p.M; q.ldm = p.ldm;
+      q.relu = p.relu; q.meta = p.meta; q.nblk = p.nblk; q.dyn = p.dyn; q.x_unpadded = 0;
+      q.ntaps = p.ntaps;
+      for (int i = 0; i < 3; ++i) q.shift[i] = p.shift[i];
+      q.kbp = tc_kbp(c_in); q.c_in = c_in;
+      q.colscale = p.colscale; q.colscale_ld = p.colscale_ld;
+      q.in_drop_thresh = p.in_drop_thresh; q.in_drop_scale = p.in_drop_scale;
+      q.in_drop_seed = p.in_drop_seed; q.in_drop_stream = p.in_drop_stream;
+      q.drop_thresh = p.drop_thresh; q.drop_scale = p.drop_scale; q.drop_seed = p.drop_seed; q.drop_stream = p.drop_stream;
+      return launch_gemm_tc(xm->second, it->second.mh, it->second.ml, q, m->max_blk, st);
+    }
+  }
   p.c_in = c_in; p.kpt = rup(c_in, 8); p.n_out = n_out; p.NT8 = (n_out + 7) / 8;
   return launch_tapgemm(p, 0, st);
 }
@@ -187,10 +229,24 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
 
   // ---- prepared-weight buffer and the batched prep job table
   std::vector<PrepJob> jobs;
-  long f4 = 0;
+  std::vector<SplitJob> sjobs;
+  long f4 = 0, sfirst = 0, sdst = 0;
   auto reg = [&](long src, int n_out, int c_in, int ntaps, int tr) {
     const long at = f4 * 4;
     add_job(jobs, f4, src, n_out, c_in, ntaps, tr);
+    // the same weight for the tcgen05 kernels
+    SplitJob sj;
+    sj.first = sfirst; sj.src_off = src; sj.dst_off = sdst;
+    sj.n_out = n_out; sj.c_in = c_in; sj.ntaps = ntaps; sj.transpose = tr;
+    sj.rows_pad = (int)tc_weight_rows(n_out, c_in, tr);
+    sj.kcols = (int)tc_weight_cols(n_out, c_in, ntaps, tr);
+    tcn_model::TcW w;
+    w.off = sdst; w.rows = sj.rows_pad; w.cols = sj.kcols;
+    m->tcw[at] = w;
+    const long n = (long)sj.rows_pad * sj.kcols;
+    sfirst += n;
+    sdst += (n + 255) / 256 * 256;  // keep every matrix 1 KB aligned
+    sjobs.push_back(sj);
     return at;
   };
   m->wf_proj = reg(m->off_proj_w, C, D, 1, 0);
@@ -207,6 +263,9 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
   m->njobs = (int)jobs.size();
   m->prep_total_f4 = f4;
   m->wf_floats = f4 * 4;
+  m->nsjobs = (int)sjobs.size();
+  m->split_total = sfirst;
+  m->tc_wfloats = sdst;
 
   // ---- workspace carve-up
   const long rows = cfg->max_rows;
@@ -219,6 +278,8 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
   };
   const size_t o_wf = carve((size_t)m->wf_floats * 4);
   const size_t o_jobs = carve(jobs.size() * sizeof(PrepJob));
+  const size_t o_sjobs = carve(sjobs.size() * sizeof(SplitJob));
+  const size_t o_tcwhi = carve((size_t)m->tc_wfloats * 4), o_tcwlo = carve((size_t)m->tc_wfloats * 4);
   std::vector<size_t> o_act(m->L + 1), o_H(m->L);
   for (int i = 0; i <= m->L; ++i) o_act[i] = carve((size_t)rows * C * 4);
   for (int i = 0; i < m->L; ++i) o_H[i] = carve((size_t)rows * C * 4);
@@ -252,6 +313,9 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
   }
   m->wf = reinterpret_cast<float*>(m->ws + o_wf);
   m->jobs_dev = reinterpret_cast<PrepJob*>(m->ws + o_jobs);
+  m->sjobs_dev = reinterpret_cast<SplitJob*>(m->ws + o_sjobs);
+  m->tc_whi = reinterpret_cast<float*>(m->ws + o_tcwhi);
+  m->tc_wlo = reinterpret_cast<float*>(m->ws + o_tcwlo);
   for (int i = 0; i <= m->L; ++i) m->act.push_back(reinterpret_cast<float*>(m->ws + o_act[i]));
   for (int i = 0; i < m->L; ++i) m->H.push_back(reinterpret_cast<float*>(m->ws + o_H[i]));
   for (int i = 0; i < 3; ++i) m->P[i] = reinterpret_cast<float*>(m->ws + o_P[i]);
@@ -279,6 +343,21 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
   m->col_head = reinterpret_cast<int*>(m->ws + o_ch);
   m->loss8 = reinterpret_cast<float*>(m->ws + o_loss);
   e = cudaMemcpy(m->jobs_dev, jobs.data(), jobs.size() * sizeof(PrepJob), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(m->sjobs_dev, sjobs.data(), sjobs.size() * sizeof(SplitJob), cudaMemcpyHostToDevice);
+  // tcgen05 path available? (needs the driver's tensor-map encoder; TCN_NO_TCGEN05=1 forces the mma.sync kernels)
+  m->use_tc = (std::getenv("TCN_NO_TCGEN05") == nullptr) && (C % 4 == 0);
+  if (m->use_tc) {
+    for (auto& kv : m->tcw) {
+      tcn_model::TcW& w = kv.second;
+      if (make_tensor_map_2d(&w.mh, m->tc_whi + w.off, w.rows, w.cols, w.cols, 64) != TCN_OK ||
+          make_tensor_map_2d(&w.ml, m->tc_wlo + w.off, w.rows, w.cols, w.cols, 64) != TCN_OK) {
+        m->use_tc = false;
+        break;
+      }
+    }
+  }
+  if (!m->use_tc) m->proj_tc = false;
   if (e != cudaSuccess) {
     set_error("tcn_model_create: job table upload failed: %s", cudaGetErrorString(e));
     cudaGetLastError();
@@ -389,6 +468,8 @@ static int model_forward(tcn_model* m, const float* x, long x_rows, int training
   const float pl = training ? m->layer_drop_p : 0.f;
   // 0. weights -> fragment order (one launch)
   TCN_CHECK(launch_prep_batched(m->jobs_dev, m->njobs, m->params, m->wf, m->prep_total_f4, st));
+  if (m->use_tc)
+    TCN_CHECK(launch_split_batched(m->sjobs_dev, m->nsjobs, m->params, m->tc_whi, m->tc_wlo, m->split_total, st));
   // 1. stage-input projection (network.py:113,122-129), input mask + channel dropout folded into the load
   const bool chan = training && m->chan_drop_p > 0.f;
   if (chan) TCN_CHECK(launch_chan_scale(m->colscale, D, m->cfg.max_seqs, m->desc, m->chan_drop_p, 0u, kStreamChan, st));

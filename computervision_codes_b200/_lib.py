@@ -72,6 +72,18 @@ class GemmTcArgs(C.Structure):
     ]
 
 
+class WgradTcArgs(C.Structure):
+    _fields_ = [
+        ("g", C.c_void_p), ("ldg", C.c_int), ("g_cols", C.c_int), ("g_rows", C.c_longlong),
+        ("x", C.c_void_p), ("ldx", C.c_int), ("x_rows", C.c_longlong), ("x_unpadded", C.c_int),
+        ("colscale", C.c_void_p), ("colscale_ld", C.c_int),
+        ("meta", C.c_void_p), ("nblk", C.c_int),
+        ("n_out", C.c_int), ("c_in", C.c_int), ("ntaps", C.c_int), ("shift", C.c_int * 3),
+        ("dw", C.c_void_p), ("db", C.c_void_p),
+        ("g_drop_p", C.c_float), ("drop_seed", C.c_uint), ("drop_stream", C.c_uint),
+    ]
+
+
 class ModelConfig(C.Structure):
     _fields_ = [
         ("layers_pg", C.c_int), ("layers_r", C.c_int), ("num_r", C.c_int), ("channels", C.c_int),
@@ -101,6 +113,7 @@ SIGNATURES = {
     "tcn_prep_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tcn_tapgemm": (C.c_int, [C.POINTER(TapGemmArgs), C.c_void_p]),
     "tcn_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
+    "tcn_wgrad_tc": (C.c_int, [C.POINTER(WgradTcArgs), C.c_void_p]),
     "tcn_layer_fwd": (C.c_int, [C.POINTER(LayerFwdArgs), C.c_void_p]),
     "tcn_gemm_tc_supported": (C.c_int, [C.c_int, C.c_int]),
     "tcn_gemm_tc": (C.c_int, [C.POINTER(GemmTcArgs), C.c_void_p]),
@@ -121,8 +134,8 @@ SIGNATURES = {
                                        C.c_void_p, C.c_void_p]),
     "tcn_model_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_void_p]),
-    "tcn_model_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
-                                     C.c_void_p]),
+    "tcn_model_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_void_p), C.c_void_p]),
     "tcn_bce_rows": (C.c_int, [C.POINTER(BceArgs), C.c_void_p]),
     "tcn_kd_kl_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                  C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),

@@ -539,7 +539,8 @@ static EncodeTiledFn encode_fn() {
 }
 
 // fp32 row-major (rows x cols, leading dimension ld floats) -> 2D map with a (32 x box_rows) box, 128B swizzle
-int make_tensor_map_2d(CUtensorMap* map, const float* ptr, long rows, long cols, long ld, int box_rows) {
+// atom32: 128-byte swizzle with 32-byte atoms (the only layout tcgen05 accepts for MN-major TF32 operands)
+int make_tensor_map_2d(CUtensorMap* map, const float* ptr, long rows, long cols, long ld, int box_rows, bool atom32) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -550,7 +551,8 @@ int make_tensor_map_2d(CUtensorMap* map, const float* ptr, long rows, long cols,
   const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): ptr %p rows %ld cols %ld ld %ld", (int)r, (const void*)ptr, rows,

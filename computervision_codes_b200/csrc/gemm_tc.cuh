@@ -132,12 +132,38 @@ inline long tc_weight_rows(int n_out, int c_in, int transpose) { return ((transp
 inline long tc_weight_cols(int n_out, int c_in, int ntaps, int transpose) {
   return (long)ntaps * tc_kbp(transpose ? n_out : c_in) * TC_BK;
 }
-int make_tensor_map_2d(CUtensorMap* map, const float* ptr, long rows, long cols, long ld, int box_rows);
+int make_tensor_map_2d(CUtensorMap* map, const float* ptr, long rows, long cols, long ld, int box_rows,
+                       bool atom32 = false);
 int launch_split_weight(const float* w, float* whi, float* wlo, int n_out, int c_in, int ntaps, int transpose,
                         cudaStream_t stream);
 int launch_split_batched(const SplitJob* jobs_dev, int njobs, const float* params, float* whi, float* wlo, long total,
                          cudaStream_t stream);
 int launch_gemm_tc(const CUtensorMap& mx, const CUtensorMap& mwhi, const CUtensorMap& mwlo, const GemmTcDev& p,
                    int cap_nblk, cudaStream_t stream);
+
+// tcgen05 weight-gradient kernel (wgrad_tc.cu)
+constexpr int WG_BOX_ROWS = 32;
+struct WgradTcDev {
+  const BlkMeta* meta;
+  int nblk;
+  const BatchDesc* dyn;
+  int x_unpadded;
+  int n_out, c_in, ntaps;
+  int shift[3];
+  int cbn;          // 32-column blocks per tap = ceil(c_in / 32)   (set by the launcher)
+  int row_splits;   // (set by the launcher)
+  float* dW;
+  float* db;        // nullable
+  const float* colscale;
+  int colscale_ld;
+  uint32_t g_drop_thresh;
+  float g_drop_scale;
+  uint32_t g_drop_seed, g_drop_stream;
+  uint32_t x_drop_thresh;
+  float x_drop_scale;
+  uint32_t x_drop_seed, x_drop_stream;
+};
+// mx / mg: maps built with make_tensor_map_2d(..., WG_BOX_ROWS, /*atom32=*/true)
+int launch_wgrad_tc(const CUtensorMap& mx, const CUtensorMap& mg, WgradTcDev& p, int cap_nblk, cudaStream_t stream);
 
 }  // namespace tcn

@@ -70,6 +70,7 @@ struct tcn_model {
   bool use_tc = false;
   std::map<long, TcW> tcw;
   std::map<std::pair<const float*, int>, CUtensorMap> xmaps;
+  std::map<std::pair<const float*, long>, CUtensorMap> wgmaps;  // 32-frame boxes, 32-byte swizzle atoms (wgrad_tc)
   float *tc_whi = nullptr, *tc_wlo = nullptr;
   long tc_wfloats = 0;
   SplitJob* sjobs_dev = nullptr;
@@ -172,6 +173,39 @@ int gemm(tcn_model* m, TapGemmDev& p, int c_in, int n_out, cudaStream_t st) {
   }
   p.c_in = c_in; p.kpt = rup(c_in, 8); p.n_out = n_out; p.NT8 = (n_out + 7) / 8;
   return launch_tapgemm(p, 0, st);
+}
+
+int get_wgmap(tcn_model* m, const float* ptr, long rows, int cols, const CUtensorMap** out) {
+  const auto key = std::make_pair(ptr, rows * 65536 + cols);
+  auto it = m->wgmaps.find(key);
+  if (it == m->wgmaps.end()) {
+    CUtensorMap map;
+    TCN_CHECK(make_tensor_map_2d(&map, ptr, rows, cols, cols, WG_BOX_ROWS, true));
+    it = m->wgmaps.emplace(key, map).first;
+  }
+  *out = &it->second;
+  return TCN_OK;
+}
+
+// weight-gradient dispatcher: tcgen05 kernel when available, mma.sync kernel otherwise
+int wgrad(tcn_model* m, WgradDev& w, long x_rows, cudaStream_t st) {
+  if (m->use_tc && (w.ldx % 4 == 0) && (w.ldg % 4 == 0) && (w.c_in % 4 == 0)) {
+    const CUtensorMap *mx, *mg;
+    TCN_CHECK(get_wgmap(m, w.X, w.x_unpadded ? x_rows : m->cfg.max_rows, w.ldx, &mx));
+    TCN_CHECK(get_wgmap(m, w.G, m->cfg.max_rows, w.ldg, &mg));
+    WgradTcDev q;
+    memset(&q, 0, sizeof(q));
+    q.meta = w.meta; q.nblk = w.nblk; q.dyn = w.dyn; q.x_unpadded = w.x_unpadded;
+    q.n_out = w.n_out; q.c_in = w.c_in; q.ntaps = w.ntaps;
+    for (int i = 0; i < 3; ++i) q.shift[i] = w.shift[i];
+    q.dW = w.dW; q.db = w.db; q.colscale = w.colscale; q.colscale_ld = w.colscale_ld;
+    q.g_drop_thresh = w.g_drop_thresh; q.g_drop_scale = w.g_drop_scale;
+    q.g_drop_seed = w.g_drop_seed; q.g_drop_stream = w.g_drop_stream;
+    q.x_drop_thresh = w.x_drop_thresh; q.x_drop_scale = w.x_drop_scale;
+    q.x_drop_seed = w.x_drop_seed; q.x_drop_stream = w.x_drop_stream;
+    return launch_wgrad_tc(*mx, *mg, q, m->max_blk, st);
+  }
+  return launch_wgrad(w, m->max_blk, st);
 }
 
 }  // namespace
@@ -551,8 +585,8 @@ static int model_forward(tcn_model* m, const float* x, long x_rows, int training
 // ================================================================================================ backward
 // gl[lv]: gradient w.r.t. the logits of level lv (rows, LDH; pad columns zero) or nullptr;
 // gf[lv]: extra gradient w.r.t. feature level lv (rows, C) or nullptr.
-static int model_backward(tcn_model* m, const float* x, const float* const* gl, const float* const* gf,
-                          cudaStream_t st) {
+static int model_backward(tcn_model* m, const float* x, long x_rows, const float* const* gl,
+                          const float* const* gf, cudaStream_t st) {
   const int C = m->C, D = m->D, L = m->L, NH = m->NH, LDH = m->LDH;
   TCN_REQUIRE(m->grads != nullptr, "tcn_model backward: no gradient buffer bound");
   const float pl = m->fwd_training ? m->layer_drop_p : 0.f;
@@ -575,7 +609,7 @@ static int model_backward(tcn_model* m, const float* x, const float* const* gl, 
       WgradDev w = base_wgrad(m);
       w.G = gl[lv]; w.ldg = LDH; w.g_cols = LDH; w.X = plv[lv]; w.ldx = C;
       w.n_out = NH; w.c_in = C; w.dW = m->g_(m->off_head_w); w.db = m->g_(m->off_head_b);
-      TCN_CHECK(launch_wgrad(w, m->max_blk, st));
+      TCN_CHECK(wgrad(m, w, x_rows, st));
       TapGemmDev p = base_tapgemm(m);
       p.X = gl[lv]; p.ldx = LDH; p.Wf = m->wf_(m->wf_headT); p.Y = m->Gp[lv]; p.ldy = C;
       p.R = prev; p.ldr = C;
@@ -591,7 +625,7 @@ static int model_backward(tcn_model* m, const float* x, const float* const* gl, 
     WgradDev w = base_wgrad(m);
     w.G = m->Gp[lv]; w.ldg = C; w.g_cols = C; w.X = f[lv]; w.ldx = C;
     w.n_out = C; w.c_in = C; w.dW = m->g_(m->off_lat_w); w.db = m->g_(m->off_lat_b);
-    TCN_CHECK(launch_wgrad(w, m->max_blk, st));
+    TCN_CHECK(wgrad(m, w, x_rows, st));
   }
   // stages, last to first
   const float* g = m->Gp[3];
@@ -612,14 +646,14 @@ static int model_backward(tcn_model* m, const float* x, const float* const* gl, 
         w.G = g; w.ldg = C; w.g_cols = C; w.X = m->H[l]; w.ldx = C; w.n_out = C; w.c_in = C;
         w.dW = m->g_(m->off_w2[l]); w.db = m->g_(m->off_b2[l]);
         if (pl > 0.f) { w.g_drop_thresh = drop_thresh(pl); w.g_drop_scale = 1.f / (1.f - pl); w.g_drop_stream = (uint32_t)l; }
-        TCN_CHECK(launch_wgrad(w, m->max_blk, st));
+        TCN_CHECK(wgrad(m, w, x_rows, st));
       }
       {
         WgradDev w = base_wgrad(m);
         w.G = m->gu; w.ldg = C; w.g_cols = C; w.X = m->act[l]; w.ldx = C; w.n_out = C; w.c_in = C; w.ntaps = 3;
         for (int i = 0; i < 3; ++i) w.shift[i] = sh[i];
         w.dW = m->g_(m->off_w1[l]); w.db = m->g_(m->off_b1[l]);
-        TCN_CHECK(launch_wgrad(w, m->max_blk, st));
+        TCN_CHECK(wgrad(m, w, x_rows, st));
       }
       {  // gx = gy + sum_k W1_k^T gu[t - s_k]
         TapGemmDev p = base_tapgemm(m);
@@ -648,7 +682,7 @@ static int model_backward(tcn_model* m, const float* x, const float* const* gl, 
     if (m->fwd_training && m->input_mask_p > 0.f) {
       w.x_drop_thresh = drop_thresh(m->input_mask_p); w.x_drop_scale = 1.f; w.x_drop_stream = kStreamMask;
     }
-    TCN_CHECK(launch_wgrad(w, m->max_blk, st));
+    TCN_CHECK(wgrad(m, w, x_rows, st));
   }
   return TCN_OK;
 }
@@ -667,10 +701,10 @@ extern "C" int tcn_model_forward(tcn_model* m, const float* x, long long x_rows,
   return TCN_OK;
 }
 
-extern "C" int tcn_model_backward(tcn_model* m, const float* x, const float* const* glogits,
+extern "C" int tcn_model_backward(tcn_model* m, const float* x, long long x_rows, const float* const* glogits,
                                   const float* const* gfeats, tcn_stream_t stream) {
   TCN_REQUIRE(m && x && m->params, "tcn_model_backward: null pointer / parameters not bound");
-  return model_backward(m, x, glogits, gfeats, (cudaStream_t)stream);
+  return model_backward(m, x, x_rows, glogits, gfeats, (cudaStream_t)stream);
 }
 
 __global__ void finish_loss_kernel(float* loss8, float* out, float w0, float w1, float w2, float w3) {
@@ -706,5 +740,5 @@ extern "C" int tcn_model_train_step(tcn_model* m, const float* x, long long x_ro
   finish_loss_kernel<<<1, 32, 0, st>>>(m->loss8, loss_out, m->head_w[0], m->head_w[1], m->head_w[2], m->head_w[3]);
   TCN_CHECK(check_launch("finish_loss_kernel"));
   const float* gl[4] = {m->dL[0], m->dL[1], m->dL[2], m->dL[3]};
-  return model_backward(m, x, gl, nullptr, st);
+  return model_backward(m, x, x_rows, gl, nullptr, st);
 }

@@ -1,0 +1,346 @@
+// tcgen05 + TMA weight-gradient kernel: contraction over frames (time)
+//
+//     dW[n, c, tap] += sum_r G[r, n] * X[r + shift[tap], c]          db[n] += sum_r G[r, n]
+//
+// the weight / bias gradients of every Conv1d / Linear on the path (closed forms of SURVEY.md 8a:
+// gW2 = sum_t gv[t] h[t]^T, gW1[:, :, k] = sum_t gu[t] x[t + s_k]^T, the projection, lateral and head weights).
+//
+// Tensor-core mapping.  The reduction runs over rows, so both operands are "MN-major": a TMA box of
+// 32 columns x 32 frames (128-byte swizzled rows) is read by tcgen05.mma with K = frames.
+//   D[m, n'] (TMEM, 128 x 64 fp32):  m  = 4 blocks of 32 input channels, each block = one (tap, column block) of X
+//                                    n' = 64 output channels of G
+//   A = X blocks (hi / lo), B = G blocks (hi / lo), both split in the operand-split warps (the kernel's
+//   operands are activations, so neither can be pre-split); 3 MMAs per 8-frame slice (lo*hi + hi*lo + hi*hi).
+// One CTA owns one (m-tile, n-tile) of dW and a slice of the rows; it accumulates over all its rows in TMEM
+// and adds its partial to dW once, at the end (fp32 atomics).  The dropout mask of the layer (gv = keep * gy /
+// (1 - p)), Dropout2d's channel scale and the input mask of the projection are folded into the operand split.
+//   warp 0: TMA producer | warp 1: MMA issuer + TMEM owner | warps 2-5: operand split, bias sums, epilogue
+#include "gemm_tc.cuh"
+
+namespace tcn {
+
+constexpr int WG_RC = 32;                      // frames per pipeline stage
+constexpr int WG_ATOM = WG_RC * 128;           // 4096 B: 32 frames x 32 fp32 columns
+constexpr int WG_RAW = 6 * WG_ATOM;            // 4 X blocks + 2 G blocks
+constexpr int WG_STAGE = 2 * WG_RAW;           // raw / hi + lo
+constexpr int WG_STAGES = 4;
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE + 1024 + 512;
+
+#if 0
+struct WgradTcDev {
+  const BlkMeta* meta;
+  int nblk;
+  const BatchDesc* dyn;
+  int x_unpadded;
+  int n_out, c_in, ntaps;
+  int shift[3];
+  int cbn;          // 32-column blocks per tap = ceil(c_in / 32)
+  int row_splits;
+  float* dW;
+  float* db;        // nullable
+  const float* colscale;
+  int colscale_ld;
+  uint32_t g_drop_thresh;
+  float g_drop_scale;
+  uint32_t g_drop_seed, g_drop_stream;
+  uint32_t x_drop_thresh;
+  float x_drop_scale;
+  uint32_t x_drop_seed, x_drop_stream;
+};
+#endif
+
+// MN-major TF32 operand.  tcgen05 accepts exactly one shared-memory layout for it: 128-byte rows (one frame each,
+// 32 fp32 columns) swizzled with 32-byte atoms (byte-address bits [5,7) ^= bits [7,9); TMA mode 128B_ATOM_32B),
+// K-atoms of 4 frames 512 bytes apart (SBO), 32-column blocks `lbo` bytes apart (LBO).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
+                const WgradTcDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, mtile = blockIdx.y, ntile = blockIdx.z;
+  const int nblk = p.dyn ? p.dyn->nblk : p.nblk;
+  const uint32_t dseed = p.dyn ? p.dyn->seed : 0u;
+  const int blk_begin = (int)((long)split * nblk / p.row_splits);
+  const int blk_end = (int)((long)(split + 1) * nblk / p.row_splits);
+  const int nv = p.ntaps * p.cbn;  // virtual 32-column blocks of X
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + WG_STAGES * WG_STAGE);
+  uint64_t* full_bar = bars;
+  uint64_t* ready_bar = bars + WG_STAGES;
+  uint64_t* empty_bar = bars + 2 * WG_STAGES;
+  uint64_t* accum_bar = bars + 3 * WG_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * WG_STAGES + 1);
+  float* bias_red = reinterpret_cast<float*>(bars + 3 * WG_STAGES + 2);  // 64 floats
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&ready_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (threadIdx.x < 64) bias_red[threadIdx.x] = 0.f;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                 "r"(64u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // the (tap, column block) of each of the four X blocks of this m-tile (blocks past the end repeat the last one)
+  int a_tap[4], a_cb[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int v = min(mtile * 4 + j, nv - 1);
+    a_tap[j] = v / p.cbn;
+    a_cb[j] = v - a_tap[j] * p.cbn;
+  }
+
+  // every role walks the same chunk sequence: 32-frame chunks of the CTA's blocks that contain valid frames
+  int total_chunks = 0;
+  for (int blk = blk_begin; blk < blk_end; ++blk) {
+    const BlkMeta m = p.meta[blk];
+    const int valid = m.hi - blk * kBlkRows;
+    if (valid > 0) total_chunks += min(4, (valid + WG_RC - 1) / WG_RC);
+  }
+
+  if (total_chunks > 0) {
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        int it = 0;
+        for (int blk = blk_begin; blk < blk_end; ++blk) {
+          const BlkMeta m = p.meta[blk];
+          const int dz = p.x_unpadded ? m.in_delta : 0;
+          for (int ch = 0; ch < 4; ++ch) {
+            const int r0 = blk * kBlkRows + ch * WG_RC;
+            if (r0 >= m.hi) break;
+            const int s = it % WG_STAGES;
+            const uint32_t ph = (it / WG_STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* st = tiles + s * WG_STAGE;
+            mbar_arrive_expect_tx(&full_bar[s], WG_RAW);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int sh = a_tap[j] == 0 ? p.shift[0] : (a_tap[j] == 1 ? p.shift[1] : p.shift[2]);
+              tma_load_2d(st + j * WG_ATOM, &map_x, &full_bar[s], a_cb[j] * 32, r0 + dz + sh);
+            }
+            tma_load_2d(st + 4 * WG_ATOM, &map_g, &full_bar[s], (ntile * 2) * 32, r0);
+            tma_load_2d(st + 5 * WG_ATOM, &map_g, &full_bar[s], (ntile * 2 + 1) * 32, r0);
+            ++it;
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = umma_idesc_tf32_mn(128, 64);
+      for (int it = 0; it < total_chunks; ++it) {
+        const int s = it % WG_STAGES;
+        const uint32_t ph = (it / WG_STAGES) & 1;
+        mbar_wait(&ready_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = base + s * WG_STAGE, a_lo = a_hi + WG_RAW;
+          const uint32_t b_hi = a_hi + 4 * WG_ATOM, b_lo = b_hi + WG_RAW;
+#pragma unroll
+          for (int k = 0; k < WG_RC / 8; ++k) {
+            const uint32_t ko = k * 1024;  // 8 frames = one 1024-byte swizzle atom
+            const uint64_t dah = umma_desc_mn_sw128(a_hi + ko, WG_ATOM), dal = umma_desc_mn_sw128(a_lo + ko, WG_ATOM);
+            const uint64_t dbh = umma_desc_mn_sw128(b_hi + ko, WG_ATOM), dbl = umma_desc_mn_sw128(b_lo + ko, WG_ATOM);
+            umma_tf32(tmem_base, dal, dbh, idesc, (it | k) != 0);
+            umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+            umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (it == total_chunks - 1) umma_commit(accum_bar);
+        }
+        __syncwarp();
+      }
+    } else {
+      // ===================== operand split + bias sums (warps 2..5) =====================
+      const int ct = threadIdx.x - 64;  // 0..127
+      const uint32_t g_seed = p.g_drop_seed ^ dseed, x_seed = p.x_drop_seed ^ dseed;
+      // every 16-byte chunk this thread touches has the same position inside its 32 x 32 block up to a row offset:
+      const int lc = ((((ct & 7) >> 1) ^ ((ct >> 3) & 3)) << 1) | (ct & 1);  // logical 16-byte column chunk (swizzle undone)
+      const bool extras = p.colscale != nullptr || p.x_drop_thresh != 0u || p.g_drop_thresh != 0u;
+      float4 bsum[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+      int it = 0;
+      for (int blk = blk_begin; blk < blk_end; ++blk) {
+        const BlkMeta m = p.meta[blk];
+        for (int ch = 0; ch < 4; ++ch) {
+          const int r0 = blk * kBlkRows + ch * WG_RC;
+          if (r0 >= m.hi) break;
+          const int s = it % WG_STAGES;
+          const uint32_t ph = (it / WG_STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          float4* raw = reinterpret_cast<float4*>(tiles + s * WG_STAGE);
+          float4* lo = reinterpret_cast<float4*>(tiles + s * WG_STAGE + WG_RAW);
+          float4 v[12];
+#pragma unroll
+          for (int i = 0; i < 12; ++i) v[i] = raw[ct + i * 128];
+#pragma unroll
+          for (int i = 0; i < 12; ++i) {
+            const int atom = i >> 1;                    // chunk ct + i*128 lies in block i/2 ...
+            const int r = (ct >> 3) + (i & 1) * 16;     // ... at frame r of the chunk
+            int src = r0 + r;
+            if (atom < 4) src += a_tap[atom] == 0 ? p.shift[0] : (a_tap[atom] == 1 ? p.shift[1] : p.shift[2]);
+            const float keep = (src >= m.lo && src < m.hi) ? 1.f : 0.f;
+            v[i].x *= keep; v[i].y *= keep; v[i].z *= keep; v[i].w *= keep;
+            if (extras) {
+              if (atom < 4) {
+                const int col = a_cb[atom] * 32 + lc * 4;
+                if (p.colscale != nullptr && col < p.c_in) {
+                  const float4 sc = __ldg(reinterpret_cast<const float4*>(p.colscale + (size_t)m.seq * p.colscale_ld + col));
+                  v[i].x *= sc.x; v[i].y *= sc.y; v[i].z *= sc.z; v[i].w *= sc.w;
+                }
+                if (p.x_drop_thresh != 0u) {
+                  v[i].x *= drop_factor(x_seed, p.x_drop_stream, p.x_drop_thresh, p.x_drop_scale, src, col);
+                  v[i].y *= drop_factor(x_seed, p.x_drop_stream, p.x_drop_thresh, p.x_drop_scale, src, col + 1);
+                  v[i].z *= drop_factor(x_seed, p.x_drop_stream, p.x_drop_thresh, p.x_drop_scale, src, col + 2);
+                  v[i].w *= drop_factor(x_seed, p.x_drop_stream, p.x_drop_thresh, p.x_drop_scale, src, col + 3);
+                }
+              } else if (p.g_drop_thresh != 0u) {
+                const int col = (ntile * 2 + (atom - 4)) * 32 + lc * 4;
+                v[i].x *= drop_factor(g_seed, p.g_drop_stream, p.g_drop_thresh, p.g_drop_scale, src, col);
+                v[i].y *= drop_factor(g_seed, p.g_drop_stream, p.g_drop_thresh, p.g_drop_scale, src, col + 1);
+                v[i].z *= drop_factor(g_seed, p.g_drop_stream, p.g_drop_thresh, p.g_drop_scale, src, col + 2);
+                v[i].w *= drop_factor(g_seed, p.g_drop_stream, p.g_drop_thresh, p.g_drop_scale, src, col + 3);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 8; i < 12; ++i) {  // G blocks: column sums for the bias gradient
+            bsum[(i - 8) >> 1].x += v[i].x; bsum[(i - 8) >> 1].y += v[i].y;
+            bsum[(i - 8) >> 1].z += v[i].z; bsum[(i - 8) >> 1].w += v[i].w;
+          }
+#pragma unroll
+          for (int i = 0; i < 12; ++i) {
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xffffe000u); l.x = v[i].x - h.x;
+            h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u); l.y = v[i].y - h.y;
+            h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u); l.z = v[i].z - h.z;
+            h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u); l.w = v[i].w - h.w;
+            raw[ct + i * 128] = h;
+            lo[ct + i * 128] = l;
+          }
+          fence_proxy_async();
+          mbar_arrive(&ready_bar[s]);
+          ++it;
+        }
+      }
+      // ---- bias gradient: reduce the per-thread column sums (shared atomics), one global add per column
+      if (p.db != nullptr && mtile == 0) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          atomicAdd(&bias_red[a * 32 + lc * 4 + 0], bsum[a].x);
+          atomicAdd(&bias_red[a * 32 + lc * 4 + 1], bsum[a].y);
+          atomicAdd(&bias_red[a * 32 + lc * 4 + 2], bsum[a].z);
+          atomicAdd(&bias_red[a * 32 + lc * 4 + 3], bsum[a].w);
+        }
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");  // the four split warps only
+        if (ct < 64) {
+          const int n = ntile * 64 + ct;
+          if (n < p.n_out) atomicAdd(p.db + n, bias_red[ct]);
+        }
+      }
+      // ===================== epilogue: add the partial into dW =====================
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+      const int q = warp & 3;  // TMEM lane quadrant == X block of this m-tile
+      const int vblk = mtile * 4 + q;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int c = a_cb[q] * 32 + lane;
+      const bool row_ok = (vblk < nv) && (c < p.c_in);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = ntile * 64 + c0 + j;
+            if (n < p.n_out) atomicAdd(p.dW + ((size_t)n * p.c_in + c) * p.ntaps + a_tap[q], v[j]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(64u));
+}
+
+int launch_wgrad_tc(const CUtensorMap& mx, const CUtensorMap& mg, WgradTcDev& p, int cap_nblk, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    if (e != cudaSuccess) {
+      set_error("wgrad_tc: smem attribute: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return TCN_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  p.cbn = (p.c_in + 31) / 32;
+  const int mt = (p.ntaps * p.cbn + 3) / 4, nt = (p.n_out + 63) / 64;
+  const int nb = cap_nblk > 0 ? cap_nblk : p.nblk;
+  int rs = num_sms() / (mt * nt);
+  if (rs < 1) rs = 1;
+  if (rs > nb) rs = nb;
+  p.row_splits = rs;
+  wgrad_tc_kernel<<<dim3(rs, mt, nt), TC_THREADS, WG_SMEM, stream>>>(mx, mg, p);
+  return check_launch("wgrad_tc_kernel");
+}
+
+}  // namespace tcn
+
+using namespace tcn;
+
+extern "C" int tcn_wgrad_tc(const tcn_wgrad_tc_args* a, tcn_stream_t stream) {
+  TCN_REQUIRE(a && a->g && a->x && a->dw && a->meta, "tcn_wgrad_tc: null pointer");
+  TCN_REQUIRE(a->nblk > 0 && a->c_in > 0 && a->n_out > 0 && a->ntaps >= 1 && a->ntaps <= 3, "tcn_wgrad_tc: bad shape");
+  if (a->ldx % 4 != 0 || a->ldg % 4 != 0 || a->c_in % 4 != 0) {
+    set_error("tcn_wgrad_tc: ldx, ldg and c_in must be multiples of 4 (TMA row pitch); use tcn_wgrad");
+    return TCN_ERR_UNSUPPORTED;
+  }
+  TCN_REQUIRE(a->g_cols >= a->n_out && a->g_cols <= a->ldg && a->x_rows > 0 && a->g_rows > 0, "tcn_wgrad_tc: bad shape");
+  TCN_REQUIRE((reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->g) & 15) == 0,
+              "tcn_wgrad_tc: x and g must be 16-byte aligned");
+  TCN_REQUIRE(a->g_drop_p >= 0.f && a->g_drop_p < 1.f, "tcn_wgrad_tc: g_drop_p must be in [0, 1)");
+  CUtensorMap mx, mg;
+  TCN_CHECK(make_tensor_map_2d(&mx, a->x, a->x_rows, a->c_in, a->ldx, WG_RC, true));
+  TCN_CHECK(make_tensor_map_2d(&mg, a->g, a->g_rows, a->g_cols, a->ldg, WG_RC, true));
+  WgradTcDev p;
+  memset(&p, 0, sizeof(p));
+  p.meta = reinterpret_cast<const BlkMeta*>(a->meta); p.nblk = a->nblk; p.dyn = nullptr;
+  p.x_unpadded = a->x_unpadded; p.n_out = a->n_out; p.c_in = a->c_in; p.ntaps = a->ntaps;
+  for (int i = 0; i < 3; ++i) p.shift[i] = a->shift[i];
+  p.dW = a->dw; p.db = a->db;
+  p.colscale = a->colscale; p.colscale_ld = a->colscale_ld;
+  p.g_drop_thresh = a->g_drop_p > 0.f ? drop_thresh(a->g_drop_p) : 0u;
+  p.g_drop_scale = a->g_drop_p > 0.f ? 1.f / (1.f - a->g_drop_p) : 1.f;
+  p.g_drop_seed = a->drop_seed; p.g_drop_stream = a->drop_stream;
+  p.x_drop_scale = 1.f;
+  return launch_wgrad_tc(mx, mg, p, 0, (cudaStream_t)stream);
+}

@@ -75,6 +75,24 @@ def wgrad(g, x, lay: SeqLayout, n_out, c_in, shifts, dw, db=None, x_unpadded=Fal
     _lib.check(lib.tcn_wgrad(C.byref(a), _lib.stream_ptr()), "tcn_wgrad")
 
 
+def wgrad_tc(g, x, lay: SeqLayout, n_out, c_in, shifts, dw, db=None, x_unpadded=False, colscale=None, g_drop_p=0.0,
+             seed=0, stream_id=0):
+    """tcgen05/TMA weight gradient (same contract as wgrad)."""
+    lib = _lib.load()
+    assert g.is_contiguous() and x.is_contiguous() and dw.is_contiguous()
+    a = _lib.WgradTcArgs()
+    a.g, a.ldg, a.g_cols, a.g_rows = _lib.ptr(g), g.shape[1], min(round_up(n_out, 4), g.shape[1]), g.shape[0]
+    a.x, a.ldx, a.x_rows, a.x_unpadded = _lib.ptr(x), x.shape[1], x.shape[0], int(x_unpadded)
+    a.colscale, a.colscale_ld = _lib.ptr(colscale), (colscale.shape[1] if colscale is not None else 0)
+    a.meta, a.nblk = _lib.ptr(lay.meta), lay.nblk
+    a.n_out, a.c_in, a.ntaps = n_out, c_in, len(shifts)
+    for i, s in enumerate(shifts):
+        a.shift[i] = int(s)
+    a.dw, a.db = _lib.ptr(dw), _lib.ptr(db)
+    a.g_drop_p, a.drop_seed, a.drop_stream = float(g_drop_p), int(seed) & 0xFFFFFFFF, int(stream_id) & 0xFFFFFFFF
+    _lib.check(lib.tcn_wgrad_tc(C.byref(a), _lib.stream_ptr()), "tcn_wgrad_tc")
+
+
 def layer_fwd(x, w1f, w2f, b1, b2, lay: SeqLayout, shifts, save_h=True, drop_p=0.0, seed=0, stream_id=0):
     """Fused residual layer forward (64 channels): returns (y, h)."""
     lib = _lib.load()

@@ -117,6 +117,21 @@ long long tcn_split_weight_floats(int n_out, int c_in, int ntaps, int transpose)
 int tcn_split_weight(const float* w, int n_out, int c_in, int ntaps, int transpose, float* w_hi, float* w_lo,
                      tcn_stream_t stream);
 
+/* tcgen05 + TMA weight gradient (same contract as tcn_wgrad): dw[n, c, tap] += sum_r g[r, n] x[r + shift[tap], c],
+ * db[n] += sum_r g[r, n]; the reduction over frames runs on tcgen05.mma kind::tf32 with both operands MN-major
+ * (TMA boxes of 32 frames x 32 columns), 3-term split of both operands in-kernel, accumulator in TMEM,
+ * one fp32 atomic add per output element and CTA.  g_rows / x_rows = rows addressable behind g / x. */
+typedef struct {
+  const float* g; int ldg; int g_cols; long long g_rows;
+  const float* x; int ldx; long long x_rows; int x_unpadded;
+  const float* colscale; int colscale_ld;
+  const int* meta; int nblk;
+  int n_out; int c_in; int ntaps; int shift[3];
+  float* dw; float* db;
+  float g_drop_p; unsigned drop_seed; unsigned drop_stream;
+} tcn_wgrad_tc_args;
+int tcn_wgrad_tc(const tcn_wgrad_tc_args* args, tcn_stream_t stream);
+
 /* ---- fused residual layer, forward ---------------------------------------------------------------
  * y = x + Dropout_p(W2 relu(W1 (*)_d x + b1) + b2), one launch: DilatedResidualLayer.forward
  * (network.py:193-198; shift = {-d, 0, +d}) and DilatedResidualCausalLayer.forward (network.py:178-183;
@@ -176,8 +191,8 @@ int tcn_model_forward(tcn_model* m, const float* x, long long x_rows, int traini
                       const float** logits, int* ld_logits, tcn_stream_t stream);
 /* backward from externally supplied gradients w.r.t. the 4 logit maps (rows, ld_logits; may be NULL)
  * and the 4 feature maps (rows, C; may be NULL), after tcn_model_forward(training=1) */
-int tcn_model_backward(tcn_model* m, const float* x, const float* const* glogits, const float* const* gfeats,
-                       tcn_stream_t stream);
+int tcn_model_backward(tcn_model* m, const float* x, long long x_rows, const float* const* glogits,
+                       const float* const* gfeats, tcn_stream_t stream);
 
 /* ---- losses ------------------------------------------------------------------------------------
  * Sigmoid-BCE over concatenated heads: nn.BCEWithLogitsLoss(pos_weight) as composed by

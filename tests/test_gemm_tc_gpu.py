@@ -112,3 +112,49 @@ def test_gemm_tc_taps_and_epilogue_match_mma_sync_path_and_fp64(shifts):
     g2 = ops.tapgemm(x, ops.prep_weight(w.to(DEV), transpose=True), lay, C, C, tuple(-s for s in shifts), relu=True,
                      in_drop_p=0.5, seed=3, stream_id=9)
     assert _maxabs(g, g2) <= 2e-5
+
+
+@pytest.mark.parametrize("lengths,c_in,n_out,shifts,unpadded", [([300, 129], 64, 64, (-4, 0, 4), False),
+                                                                 ([1000], 64, 64, (0,), False),
+                                                                 ([200, 77, 513], 64, 131, (0,), False),
+                                                                 ([257], 64, 64, (-512, -256, 0), False),
+                                                                 ([140, 260], 2048, 64, (0,), True),
+                                                                 ([90], 100, 24, (-1, 0, 1), False)])
+def test_wgrad_tc_matches_fp64(lengths, c_in, n_out, shifts, unpadded):
+    from computervision_codes_b200 import ops
+    from computervision_codes_b200.layout import SeqLayout
+    from oracle import tcn_oracle as O
+
+    torch.manual_seed(c_in + n_out + len(shifts))
+    lay = SeqLayout.get(lengths, DEV)
+    ntaps = len(shifts)
+    xs = [torch.randn(T, c_in) for T in lengths]
+    gs = [torch.randn(T, n_out) for T in lengths]
+    ldg = (n_out + 3) // 4 * 4
+    g_rows = torch.zeros(lay.rows, ldg)
+    x_rows = torch.zeros(lay.rows, c_in)
+    for s, T in enumerate(lengths):
+        g_rows[lay.starts[s]:lay.starts[s] + T, :n_out] = gs[s]
+        x_rows[lay.starts[s]:lay.starts[s] + T] = xs[s]
+    x_dev = torch.cat(xs).to(DEV) if unpadded else x_rows.to(DEV)
+    g_dev = g_rows.to(DEV)
+    dw = torch.zeros(n_out, c_in, ntaps, device=DEV)
+    db = torch.zeros(n_out, device=DEV)
+    p = 0.5 if ntaps == 1 and not unpadded else 0.0
+    ops.wgrad_tc(g_dev, x_dev, lay, n_out, c_in, shifts, dw, db, x_unpadded=unpadded, g_drop_p=p, seed=11, stream_id=4)
+    keep = ops.dropout_keep_mask(lay.rows, ldg, 0.5, 11, 4, DEV).cpu().double() * 2.0 if p > 0 else None
+    dw_ref = torch.zeros(n_out, c_in, ntaps, dtype=torch.float64)
+    db_ref = torch.zeros(n_out, dtype=torch.float64)
+    for s, T in enumerate(lengths):
+        gd = gs[s].double()
+        if keep is not None:
+            gd = gd * keep[lay.starts[s]:lay.starts[s] + T, :n_out]
+        gb, xb = gd.t().unsqueeze(0), xs[s].double().t().unsqueeze(0)
+        for k, sh in enumerate(shifts):
+            dw_ref[:, :, k] += torch.einsum("bot,bct->oc", gb, O.shift_time(xb, sh))
+        db_ref += gd.sum(0)
+    assert _maxabs(dw, dw_ref) <= 2e-5 * max(1.0, float(dw_ref.abs().max())), (lengths, c_in, n_out, shifts)
+    assert _maxabs(db, db_ref) <= 2e-5 * max(1.0, float(db_ref.abs().max()))
+    # accumulates: a second call doubles the result
+    ops.wgrad_tc(g_dev, x_dev, lay, n_out, c_in, shifts, dw, db, x_unpadded=unpadded, g_drop_p=p, seed=11, stream_id=4)
+    assert _maxabs(dw, 2 * dw_ref) <= 4e-5 * max(1.0, float(dw_ref.abs().max()))

@@ -139,6 +139,19 @@ def main():
             print(json.dumps({"kernel": nm, "shape": name, "ms": round(ms, 4),
                               "alg_GBps": round(byt * frames / ms / 1e6, 1),
                               "executed_TFLOPs_3xtf32": round(flops * frames * 3 / ms / 1e9, 1)}))
+        def tc_wg1():
+            i = it[0] % nbuf; it[0] += 1
+            ops.wgrad_tc(xs[i], hs[i], lay, C, C, shifts, gw1, gb1)
+
+        def tc_wg2():
+            i = it[0] % nbuf; it[0] += 1
+            ops.wgrad_tc(xs[i], hs[i], lay, C, C, (0,), gw2, gb2, g_drop_p=0.5, seed=1, stream_id=2)
+
+        for nm, fn, flops, byt in (("wgrad_tc W1 (3 taps)", tc_wg1, 6 * C * C, 8 * C), ("wgrad_tc W2", tc_wg2, 2 * C * C, 8 * C)):
+            ms = timeit(fn)
+            print(json.dumps({"kernel": nm, "shape": name, "ms": round(ms, 4),
+                              "alg_GBps": round(byt * frames / ms / 1e6, 1),
+                              "executed_TFLOPs_3xtf32": round(flops * frames * 3 / ms / 1e9, 1)}))
         # stage-input projection 2048 -> 64
         if True:
             D = 2048 if frames <= 100000 else 768
@@ -158,6 +171,11 @@ def main():
                               "executed_TFLOPs_3xtf32": round(2 * D * C * frames * 3 / ms / 1e9, 1)}))
             gw = torch.zeros(C, D, 1, device=DEV)
             g = torch.randn(lay.rows, C, device=DEV)
+            ms = timeit(lambda: ops.wgrad_tc(g, x, lay, C, D, (0,), gw, None, x_unpadded=True))
+            print(json.dumps({"kernel": "wgrad_tc projection", "shape": name, "ms": round(ms, 4),
+                              "alg_GBps": round(4 * (D + C) * frames / ms / 1e6, 1),
+                              "frac_hbm": round(4 * (D + C) * frames / ms / 1e6 / PEAK, 4),
+                              "executed_TFLOPs_3xtf32": round(2 * D * C * frames * 3 / ms / 1e9, 1)}))
             ms = timeit(lambda: ops.wgrad(g, x, lay, C, D, (0,), gw, None, x_unpadded=True))
             print(json.dumps({"kernel": "wgrad projection", "shape": name, "ms": round(ms, 4),
                               "alg_GBps": round(4 * (D + C) * frames / ms / 1e6, 1),

@@ -108,17 +108,25 @@ class TemporalTrainer:
         dev = self.ex.device
         D = self.ex.cfg.in_dim
         self.max_frames = max_frames
-        self.x_static = torch.zeros(max_frames, D, device=dev, dtype=torch.float32)
-        self.lab_static = torch.zeros(max_frames, self.ex.ld_logits, device=dev, dtype=torch.uint8)
+        # two input slots: while the graph of step i runs out of slot i % 2, prefetch() can already stage the
+        # inputs of step i + 1 into the other slot on a copy stream (H2D overlapped with compute)
+        self.x_slots = [torch.zeros(max_frames, D, device=dev, dtype=torch.float32) for _ in range(2)]
+        self.lab_slots = [torch.zeros(max_frames, self.ex.ld_logits, device=dev, dtype=torch.uint8) for _ in range(2)]
+        self.slot = 0
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.slot_free = [torch.cuda.Event(), torch.cuda.Event()]   # compute finished reading the slot
+        self.slot_ready = [torch.cuda.Event(), torch.cuda.Event()]  # copy into the slot finished
+        self._prefetched = None
         self.flat_p, self.flat_g = self.ex.flat_p, self.ex.flat_g
         self.num_params = self.flat_p.numel()
         self.use_graph = use_graph
-        self.graph = None
+        self.graphs = [None, None]
+        self._outs = [None, None]
         self.rng = torch.Generator().manual_seed(seed)
         self.training = True
 
-    def _body(self):
-        out = self.ex.train_step(self.x_static, self.lab_static, training=self.training)
+    def _body(self, slot):
+        out = self.ex.train_step(self.x_slots[slot], self.lab_slots[slot], training=self.training)
         scale = 1.0
         if self.world > 1:
             torch.distributed.all_reduce(self.flat_g, group=self.pg)
@@ -130,41 +138,77 @@ class TemporalTrainer:
         """Kernels of this library enqueued by one step (static count of the executor's schedule)."""
         L = self.ex.cfg.layers_pg + self.ex.cfg.layers_r * self.ex.cfg.num_r
         fwd_layer = 1 if self.ex.cfg.channels == 64 else 2
-        # prep + chan-scale + proj + layers + 3 lateral + 4 heads + 4 bce + finish
-        fwd = 1 + 1 + 1 + L * fwd_layer + 3 + 4 + 4 + 1
+        # 2 weight preps + proj split + chan-scale + proj + layers + 3 lateral + 4 heads + 4 bce + finish
+        fwd = 2 + 1 + 1 + 1 + L * fwd_layer + 3 + 4 + 4 + 1
         # 4 x (head wgrad + dgrad) + 3 lateral wgrad + L x (dgrad1, wgrad2, wgrad1, dgrad2) + 3 lateral dgrad + proj wgrad
         bwd = 8 + 3 + 4 * L + 3 + 1
         return fwd + bwd + 1  # + sgd
 
-    def step(self, x_rows, labels_u8, lengths):
-        """x_rows / labels_u8: one tensor, or a list with one tensor per video (device or pinned host)."""
+    def _stage(self, slot, x_rows, labels_u8, lengths):
+        """Copy one batch into an input slot on the current stream (H2D when the sources are pinned host tensors)."""
         lay = SeqLayout.get(lengths, self.ex.device)
-        n = lay.frames
-        assert n <= self.max_frames
-        seed = int(torch.randint(0, 2 ** 31 - 1, (1,), generator=self.rng).item())
+        assert lay.frames <= self.max_frames
         xs = x_rows if isinstance(x_rows, (list, tuple)) else [x_rows]
         ls = labels_u8 if isinstance(labels_u8, (list, tuple)) else [labels_u8]
         off = 0
         for x in xs:
-            self.x_static[off:off + x.shape[0]].copy_(x, non_blocking=True)
+            self.x_slots[slot][off:off + x.shape[0]].copy_(x, non_blocking=True)
             off += x.shape[0]
-        assert off == n
+        assert off == lay.frames
         off = 0
         for lab in ls:
-            self.lab_static[off:off + lab.shape[0], :lab.shape[1]].copy_(lab, non_blocking=True)
+            self.lab_slots[slot][off:off + lab.shape[0], :lab.shape[1]].copy_(lab, non_blocking=True)
             off += lab.shape[0]
+        return lay
+
+    def prefetch(self, x_rows, labels_u8, lengths):
+        """Stage the NEXT step's batch into the idle input slot on the copy stream; the following step() call
+        (without arguments) consumes it.  Lets the H2D copy of step i + 1 overlap the kernels of step i."""
+        nxt = self.slot ^ 1
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.slot_free[nxt])
+            lay = self._stage(nxt, x_rows, labels_u8, lengths)
+            self.slot_ready[nxt].record(self.copy_stream)
+        self._prefetched = (nxt, lay)
+
+    def step(self, x_rows=None, labels_u8=None, lengths=None):
+        """One optimizer step.  x_rows / labels_u8: one tensor or a list with one tensor per video (device or pinned
+        host); omit them to consume the batch staged by prefetch().  Returns the device loss vector
+        (loss_ivt, loss_i, loss_v, loss_t, total, 0, 0, 0)."""
+        cur = torch.cuda.current_stream()
+        if x_rows is None:
+            assert self._prefetched is not None, "step() without arguments needs a prefetch()"
+            slot, lay = self._prefetched
+            self._prefetched = None
+            cur.wait_event(self.slot_ready[slot])
+        else:
+            slot = self.slot ^ 1 if self._prefetched is None else self.slot  # never the slot a prefetch is filling
+            if self._prefetched is not None and self._prefetched[0] == slot:
+                slot ^= 1
+            lay = self._stage(slot, x_rows, labels_u8, lengths)
+        self.slot = slot
+        seed = int(torch.randint(0, 2 ** 31 - 1, (1,), generator=self.rng).item())
         self.ex.set_batch(lay, seed)
         if not self.use_graph:
-            return self._body()
-        if self.graph is None:
-            # warm-up outside capture (lazy module loading, cudaFuncSetAttribute), then capture once
-            snap_p = self.flat_p.clone()
-            self._body()
-            self.flat_p.copy_(snap_p)
-            torch.cuda.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self._out = self._body()
-            self.flat_p.copy_(snap_p)
-        self.graph.replay()
-        return self._out
+            out = self._body(slot)
+        else:
+            if self.graphs[slot] is None:
+                # warm-up outside capture (lazy module loading, cudaFuncSetAttribute), then capture once per slot
+                snap_p = self.flat_p.clone()
+                self._body(slot)
+                self.flat_p.copy_(snap_p)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._outs[slot] = self._body(slot)
+                self.flat_p.copy_(snap_p)
+                self.graphs[slot] = g
+            self.graphs[slot].replay()
+            out = self._outs[slot]
+        self.slot_free[slot].record(cur)
+        return out
+
+    def close(self):
+        """Drop the captured graphs (do this before destroying a process group they reference)."""
+        self.graphs = [None, None]
+        self._outs = [None, None]

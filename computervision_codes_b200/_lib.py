@@ -84,6 +84,17 @@ class WgradTcArgs(C.Structure):
     ]
 
 
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("ldq", C.c_int), ("k", C.c_void_p), ("ldk", C.c_int), ("v", C.c_void_p), ("ldv", C.c_int),
+        ("o", C.c_void_p), ("ldo", C.c_int), ("lse", C.c_void_p),
+        ("dout", C.c_void_p), ("lddo", C.c_int), ("dq", C.c_void_p), ("lddq", C.c_int),
+        ("dk", C.c_void_p), ("lddk", C.c_int), ("dv", C.c_void_p), ("lddv", C.c_int),
+        ("seq_lo", C.c_void_p), ("seq_len", C.c_void_p), ("nseq", C.c_int), ("max_len", C.c_int),
+        ("heads", C.c_int), ("head_dim", C.c_int), ("scale", C.c_float),
+    ]
+
+
 class ModelConfig(C.Structure):
     _fields_ = [
         ("layers_pg", C.c_int), ("layers_r", C.c_int), ("num_r", C.c_int), ("channels", C.c_int),
@@ -136,6 +147,18 @@ SIGNATURES = {
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_void_p]),
     "tcn_model_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_void_p), C.c_void_p]),
+    "tcn_layernorm_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "tcn_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_void_p]),
+    "tcn_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), C.c_void_p]),
+    "tcn_attn_bwd": (C.c_int, [C.POINTER(AttnArgs), C.c_void_p]),
+    "tcn_dwconv_gelu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_void_p]),
+    "tcn_dwconv_gelu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "tcn_axpby": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_longlong, C.c_void_p]),
     "tcn_bce_rows": (C.c_int, [C.POINTER(BceArgs), C.c_void_p]),
     "tcn_kd_kl_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                  C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),

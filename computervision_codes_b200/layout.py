@@ -42,6 +42,9 @@ class SeqLayout:
         self.meta_np = np.asarray(meta, dtype=np.int32).reshape(-1, 4)
         self.meta = torch.from_numpy(self.meta_np).to(self.device)
         self.uniform_T = self.lengths[0] if len(set(self.lengths)) == 1 else None
+        self.seq_lo = torch.tensor(self.starts, dtype=torch.int32, device=self.device)
+        self.seq_len = torch.tensor(self.lengths, dtype=torch.int32, device=self.device)
+        self.max_len = max(self.lengths)
 
     @staticmethod
     def get(lengths, device) -> "SeqLayout":

@@ -189,21 +189,34 @@ def new_seed() -> int:
 
 
 # ------------------------------------------------------------------------------------ autograd
+def _tc_ok(x, c_in):
+    return x.shape[1] % 4 == 0 and c_in % 4 == 0
+
+
 class TapGemmFn(torch.autograd.Function):
-    """y = sum_tap x[r + s_tap] W[:, :, tap]^T + bias (+ residual), packed time-major rows."""
+    """y = sum_tap drop(x)[r + s_tap] W[:, :, tap]^T + bias (+ residual), packed time-major rows.
+    Runs on the tcgen05 kernels when the row pitch allows TMA (multiple of 16 bytes), else on the mma.sync kernels."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, lay, shifts, x_unpadded, colscale):
+    def forward(ctx, x, weight, bias, residual, lay, shifts, x_unpadded, colscale, in_drop_p, seed, stream_id):
         x = _f32c(x)
         n_out, c_in = weight.shape[0], weight.shape[1]
-        wf = prep_weight(weight)
         res = _f32c(residual) if residual is not None else None
-        y = tapgemm(x, wf, lay, c_in, n_out, shifts, bias=_f32c(bias.detach()) if bias is not None else None,
-                    residual=res, x_unpadded=x_unpadded, colscale=colscale)
+        b = _f32c(bias.detach()) if bias is not None else None
+        tc = _tc_ok(x, c_in)
+        if tc:
+            hi, lo = split_weight(weight)
+            y = gemm_tc(x, hi, lo, lay, c_in, n_out, shifts, bias=b, residual=res, x_unpadded=x_unpadded,
+                        colscale=colscale, in_drop_p=in_drop_p, in_drop_rescale=True, seed=seed, stream_id=stream_id)
+        else:
+            y = tapgemm(x, prep_weight(weight), lay, c_in, n_out, shifts, bias=b, residual=res, x_unpadded=x_unpadded,
+                        colscale=colscale, in_drop_p=in_drop_p, seed=seed, stream_id=stream_id)
         ctx.save_for_backward(x, weight)
         ctx.lay, ctx.shifts, ctx.x_unpadded, ctx.colscale = lay, tuple(shifts), x_unpadded, colscale
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None
         ctx.res_ld = res.shape[1] if res is not None else 0
+        ctx.drop = (in_drop_p, seed, stream_id)
+        ctx.tc = tc
         return y
 
     @staticmethod
@@ -212,24 +225,37 @@ class TapGemmFn(torch.autograd.Function):
         lay, shifts = ctx.lay, ctx.shifts
         gy = _f32c(gy)
         n_out, c_in = weight.shape[0], weight.shape[1]
+        p, seed, sid = ctx.drop
         gx = gw = gb = gres = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             gw = torch.zeros_like(weight, dtype=torch.float32).contiguous()
             gb = torch.zeros(n_out, device=gy.device, dtype=torch.float32) if ctx.has_bias else None
-            wgrad(gy, x, lay, n_out, c_in, shifts, gw.view(n_out, c_in, -1), gb, x_unpadded=ctx.x_unpadded,
-                  colscale=ctx.colscale)
+            xin = dropout_apply(x, p, seed, sid) if p > 0 else x  # the weight gradient sees the dropped input
+            if ctx.tc and gy.shape[1] % 4 == 0:
+                wgrad_tc(gy, xin, lay, n_out, c_in, shifts, gw.view(n_out, c_in, -1), gb, x_unpadded=ctx.x_unpadded,
+                         colscale=ctx.colscale)
+            else:
+                wgrad(gy, xin, lay, n_out, c_in, shifts, gw.view(n_out, c_in, -1), gb, x_unpadded=ctx.x_unpadded,
+                      colscale=ctx.colscale)
         if ctx.needs_input_grad[0]:
             assert not ctx.x_unpadded, "input gradient for unpadded inputs is not needed on this path"
-            wft = prep_weight(weight, transpose=True)
-            gx = tapgemm(gy, wft, lay, min(round_up(n_out, 4), gy.shape[1]), c_in, tuple(-s for s in shifts),
-                         ldy=x.shape[1])
+            kin = min(round_up(n_out, 4), gy.shape[1])
+            nshifts = tuple(-s for s in shifts)
+            if ctx.tc and gy.shape[1] % 4 == 0:
+                hit, lot = split_weight(weight, transpose=True)
+                gx = gemm_tc(gy, hit, lot, lay, kin, c_in, nshifts, ldy=x.shape[1], drop_p=p, seed=seed, stream_id=sid)
+            else:
+                gx = tapgemm(gy, prep_weight(weight, transpose=True), lay, kin, c_in, nshifts, ldy=x.shape[1], drop_p=p,
+                             seed=seed, stream_id=sid)
         if ctx.has_res and ctx.needs_input_grad[3]:
             gres = gy if gy.shape[1] == ctx.res_ld else gy[:, :ctx.res_ld]
-        return gx, gw, gb, gres, None, None, None, None
+        return gx, gw, gb, gres, None, None, None, None, None, None, None
 
 
-def tap_linear(x, weight, bias, lay, shifts=(0,), residual=None, x_unpadded=False, colscale=None):
-    return TapGemmFn.apply(x, weight, bias, residual, lay, tuple(shifts), x_unpadded, colscale)
+def tap_linear(x, weight, bias, lay, shifts=(0,), residual=None, x_unpadded=False, colscale=None, in_drop_p=0.0, seed=0,
+               stream_id=0):
+    return TapGemmFn.apply(x, weight, bias, residual, lay, tuple(shifts), x_unpadded, colscale, float(in_drop_p),
+                           int(seed), int(stream_id))
 
 
 class DilatedResidualFn(torch.autograd.Function):

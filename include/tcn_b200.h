@@ -227,6 +227,35 @@ int tcn_mse(const float* a, const float* b, long long n, float* loss, float loss
 int tcn_ce_rows(const float* x, int ldx, const int* target, const int* meta, int tgt_unpadded, int nrows, int K,
                 float row_scale, float* loss, float* gx, int ldg, float grad_scale, tcn_stream_t stream);
 
+/* ---- MS-TCT blocks (MT4MTLKD/Temporal_mstct/MSTCT/Temporal_Encoder.py) -----------------------------
+ * nn.LayerNorm over channels (:97,103,140,175-199): y = (x - mean) * rstd * gamma + beta, one warp per row;
+ * mean / rstd (nrows floats each) are saved for the backward, which also accumulates dgamma / dbeta. */
+int tcn_layernorm_fwd(const float* x, int ldx, float* y, int ldy, const float* gamma, const float* beta, float* mean,
+                      float* rstd, const int* meta, int nrows, int channels, float eps, tcn_stream_t stream);
+int tcn_layernorm_bwd(const float* x, int ldx, const float* dy, int lddy, float* dx, int lddx, const float* gamma,
+                      const float* mean, const float* rstd, float* dgamma, float* dbeta, const int* meta, int nrows,
+                      int channels, tcn_stream_t stream);
+/* Global_Relational_Block attention (:76-88): per (sequence, head) o = softmax(scale q k^T) v over the frames of
+ * the sequence; head h lives at columns [h*head_dim, (h+1)*head_dim) of q / k / v / o (pass k and v already offset
+ * into the kv projection).  lse: (rows, heads) log-sum-exp saved for the backward (two passes, no atomics). */
+typedef struct {
+  const float* q; int ldq; const float* k; int ldk; const float* v; int ldv;
+  float* o; int ldo; float* lse;
+  const float* dout; int lddo; float* dq; int lddq; float* dk; int lddk; float* dv; int lddv;
+  const int* seq_lo; const int* seq_len; int nseq; int max_len;
+  int heads; int head_dim; float scale;
+} tcn_attn_args;
+int tcn_attn_fwd(const tcn_attn_args* args, tcn_stream_t stream);
+int tcn_attn_bwd(const tcn_attn_args* args, tcn_stream_t stream);
+/* Local_Relational_Block depthwise Conv1d(k=3, pad=1, groups=C) over time + GELU (:13-14,36-39), x / y (rows, C);
+ * w: (C, 1, 3) torch layout.  Backward: du (scratch, rows x C), dx, dw += , db += . */
+int tcn_dwconv_gelu_fwd(const float* x, float* y, const float* w, const float* b, const int* meta, int nrows,
+                        int channels, tcn_stream_t stream);
+int tcn_dwconv_gelu_bwd(const float* x, const float* dy, float* du, float* dx, const float* w, const float* b, float* dw,
+                        float* db, const int* meta, int nrows, int channels, tcn_stream_t stream);
+/* y = a * x + b * y (residual sums of the Temporal_Mixer, TS_Mixer.py:66-76) */
+int tcn_axpby(float* y, const float* x, float a, float b, long long n, tcn_stream_t stream);
+
 /* ---- dropout / optimizer -----------------------------------------------------------------------
  * Counter-based dropout keyed by (seed, stream id, row, column): nn.Dropout() of the residual layers
  * (network.py:175,191) and Dropout2d over input channels (network.py:117,125-127). */

@@ -40,12 +40,9 @@ def build(in_dim, dims, heads, mlp_ratio, num_block, emb, K, seed):
     return enc.eval(), mix.eval(), cls.eval()
 
 
-def main():
-    os.makedirs(OUT, exist_ok=True)
+def one(name, in_dim, dims, heads, ratio, nblk, emb, K, B, T, seed):
     out = {}
-    in_dim, dims, heads, ratio, nblk, emb, K = 24, [16, 24, 32, 40], 8, 2, 1, 16, 10
-    B, T = 2, 20
-    enc, mix, cls = build(in_dim, dims, heads, ratio, nblk, emb, K, seed=21)
+    enc, mix, cls = build(in_dim, dims, heads, ratio, nblk, emb, K, seed=seed)
     x = torch.randn(B, in_dim, T)
     feats = enc(x)
     concat = mix(feats)
@@ -63,7 +60,14 @@ def main():
         for k, v in mod.named_parameters():
             if v.grad is not None:
                 out["grad." + pre + k] = _np(v.grad)
-    np.savez_compressed(os.path.join(OUT, "mstct_small.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, name), **out)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    one("mstct_small.npz", 24, [16, 24, 32, 40], 8, 2, 1, 16, 10, B=2, T=20, seed=21)
+    # longer windows (three key chunks in the attention kernel), head dims 4..10, two blocks per stage
+    one("mstct_mid.npz", 48, [32, 48, 64, 80], 8, 2, 2, 32, 15, B=2, T=150, seed=22)
 
 
 if __name__ == "__main__":

@@ -58,8 +58,11 @@ struct tcn_model {
   float* logits[4] = {nullptr, nullptr, nullptr, nullptr};
   float* dL[4] = {nullptr, nullptr, nullptr, nullptr};
   float* Gp[4] = {nullptr, nullptr, nullptr, nullptr};
-  float* gbuf[2] = {nullptr, nullptr};
-  float* gu = nullptr;
+  std::vector<float*> gpool;  // one gradient buffer per residual layer (+ 3 lateral adds): no reuse inside a step, so
+  std::vector<float*> gus;    // the weight-gradient kernels can run on a second stream behind the input-gradient chain
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> evs;
+  bool overlap_wgrad = true;
   float* colscale = nullptr;
   // tcgen05 path: split (hi / lo) copies of every weight + their TMA maps, keyed by the float offset of the
   // fragment-ordered copy the mma.sync kernels use; TMA maps of the activation buffers keyed by (pointer, columns)
@@ -317,13 +320,14 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
   std::vector<size_t> o_act(m->L + 1), o_H(m->L);
   for (int i = 0; i <= m->L; ++i) o_act[i] = carve((size_t)rows * C * 4);
   for (int i = 0; i < m->L; ++i) o_H[i] = carve((size_t)rows * C * 4);
-  size_t o_P[3], o_log[4], o_dL[4], o_Gp[4], o_gb[2];
+  size_t o_P[3], o_log[4], o_dL[4], o_Gp[4];
+  std::vector<size_t> o_gpool(m->L + 4), o_gus(m->L);
   for (int i = 0; i < 3; ++i) o_P[i] = carve((size_t)rows * C * 4);
   for (int i = 0; i < 4; ++i) o_log[i] = carve((size_t)rows * m->LDH * 4);
   for (int i = 0; i < 4; ++i) o_dL[i] = carve((size_t)rows * m->LDH * 4);
   for (int i = 0; i < 4; ++i) o_Gp[i] = carve((size_t)rows * C * 4);
-  for (int i = 0; i < 2; ++i) o_gb[i] = carve((size_t)rows * C * 4);
-  const size_t o_gu = carve((size_t)rows * C * 4);
+  for (auto& o : o_gpool) o = carve((size_t)rows * C * 4);
+  for (auto& o : o_gus) o = carve((size_t)rows * C * 4);
   const size_t o_cs = carve((size_t)cfg->max_seqs * D * 4);
   m->proj_tc = tcn_gemm_tc_supported(D, C) != 0;
   const size_t proj_wf = (size_t)tcn_split_weight_floats(C, D, 1, 0);
@@ -358,8 +362,14 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
     m->dL[i] = reinterpret_cast<float*>(m->ws + o_dL[i]);
     m->Gp[i] = reinterpret_cast<float*>(m->ws + o_Gp[i]);
   }
-  for (int i = 0; i < 2; ++i) m->gbuf[i] = reinterpret_cast<float*>(m->ws + o_gb[i]);
-  m->gu = reinterpret_cast<float*>(m->ws + o_gu);
+  for (auto o : o_gpool) m->gpool.push_back(reinterpret_cast<float*>(m->ws + o));
+  for (auto o : o_gus) m->gus.push_back(reinterpret_cast<float*>(m->ws + o));
+  m->overlap_wgrad = std::getenv("TCN_NO_WGRAD_STREAM") == nullptr;
+  if (cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess) m->overlap_wgrad = false;
+  m->evs.resize(m->L + 8, nullptr);
+  for (auto& ev : m->evs)
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) m->overlap_wgrad = false;
+  cudaGetLastError();
   m->colscale = reinterpret_cast<float*>(m->ws + o_cs);
   m->proj_whi = reinterpret_cast<float*>(m->ws + o_whi);
   m->proj_wlo = reinterpret_cast<float*>(m->ws + o_wlo);
@@ -409,6 +419,9 @@ extern "C" void tcn_model_destroy(tcn_model* m) {
   if (m->desc_host) cudaFreeHost(m->desc_host);
   for (int i = 0; i < tcn_model::kSlots; ++i)
     if (m->slot_done[i]) cudaEventDestroy(m->slot_done[i]);
+  for (auto ev : m->evs)
+    if (ev) cudaEventDestroy(ev);
+  if (m->side) cudaStreamDestroy(m->side);
   delete m;
 }
 
@@ -587,7 +600,7 @@ static int model_forward(tcn_model* m, const float* x, long x_rows, int training
 // gf[lv]: extra gradient w.r.t. feature level lv (rows, C) or nullptr.
 static int model_backward(tcn_model* m, const float* x, long x_rows, const float* const* gl,
                           const float* const* gf, cudaStream_t st) {
-  const int C = m->C, D = m->D, L = m->L, NH = m->NH, LDH = m->LDH;
+  const int C = m->C, D = m->D, NH = m->NH, LDH = m->LDH;
   TCN_REQUIRE(m->grads != nullptr, "tcn_model backward: no gradient buffer bound");
   const float pl = m->fwd_training ? m->layer_drop_p : 0.f;
   if (cudaMemsetAsync(m->grads, 0, (size_t)m->n_params * 4, st) != cudaSuccess) {
@@ -595,82 +608,98 @@ static int model_backward(tcn_model* m, const float* x, long x_rows, const float
     cudaGetLastError();
     return TCN_ERR_CUDA;
   }
+  // The input-gradient chain (critical path) stays on `st`; weight gradients only feed the optimizer, so they run
+  // on a second stream, ordered by events (inside a graph capture these become plain graph edges).
+  cudaStream_t ws = m->overlap_wgrad ? m->side : st;
+  int nev = 0;
+  auto hand_over = [&]() -> int {  // everything enqueued on st so far is visible to ws
+    if (ws == st) return TCN_OK;
+    cudaEvent_t ev = m->evs[nev++];
+    if (cudaEventRecord(ev, st) != cudaSuccess || cudaStreamWaitEvent(ws, ev, 0) != cudaSuccess) {
+      set_error("tcn_model backward: event hand-over failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return TCN_ERR_CUDA;
+    }
+    return TCN_OK;
+  };
   const float* f[4];
   for (int s = 0; s < 4; ++s) f[s] = m->act[m->stage_first[s + 1]];
   const float* plv[4] = {m->P[0], m->P[1], m->P[2], f[3]};
-  // heads: weight grads, then the gradient of each FPN level, accumulated top-down (p_l feeds p_{l-1})
-  const float* prev = nullptr;
   for (int lv = 0; lv < 4; ++lv) {
     if (gf && gf[lv]) {
       set_error("tcn_model backward: gradients w.r.t. the feature maps are not supported yet");
       return TCN_ERR_UNSUPPORTED;
     }
-    if (gl && gl[lv]) {
-      WgradDev w = base_wgrad(m);
-      w.G = gl[lv]; w.ldg = LDH; w.g_cols = LDH; w.X = plv[lv]; w.ldx = C;
-      w.n_out = NH; w.c_in = C; w.dW = m->g_(m->off_head_w); w.db = m->g_(m->off_head_b);
-      TCN_CHECK(wgrad(m, w, x_rows, st));
-      TapGemmDev p = base_tapgemm(m);
-      p.X = gl[lv]; p.ldx = LDH; p.Wf = m->wf_(m->wf_headT); p.Y = m->Gp[lv]; p.ldy = C;
-      p.R = prev; p.ldr = C;
-      TCN_CHECK(gemm(m, p, LDH, C, st));
-    } else {
+    if (!(gl && gl[lv])) {
       set_error("tcn_model backward: every level needs a logits gradient");
       return TCN_ERR_UNSUPPORTED;
     }
+  }
+  TCN_CHECK(hand_over());  // gradient buffer zeroed, logits gradients ready
+  // heads: weight grads (side stream), then the gradient of each FPN level, accumulated top-down (p_l feeds p_{l-1})
+  const float* prev = nullptr;
+  for (int lv = 0; lv < 4; ++lv) {
+    WgradDev w = base_wgrad(m);
+    w.G = gl[lv]; w.ldg = LDH; w.g_cols = LDH; w.X = plv[lv]; w.ldx = C;
+    w.n_out = NH; w.c_in = C; w.dW = m->g_(m->off_head_w); w.db = m->g_(m->off_head_b);
+    TCN_CHECK(wgrad(m, w, x_rows, ws));
+    TapGemmDev p = base_tapgemm(m);
+    p.X = gl[lv]; p.ldx = LDH; p.Wf = m->wf_(m->wf_headT); p.Y = m->Gp[lv]; p.ldy = C;
+    p.R = prev; p.ldr = C;
+    TCN_CHECK(gemm(m, p, LDH, C, st));
     prev = m->Gp[lv];
   }
+  TCN_CHECK(hand_over());  // Gp[0..3] ready
   // lateral weight grads: p_l = p_{l+1} + lat(f_l) for l = 0..2
   for (int lv = 0; lv < 3; ++lv) {
     WgradDev w = base_wgrad(m);
     w.G = m->Gp[lv]; w.ldg = C; w.g_cols = C; w.X = f[lv]; w.ldx = C;
     w.n_out = C; w.c_in = C; w.dW = m->g_(m->off_lat_w); w.db = m->g_(m->off_lat_b);
-    TCN_CHECK(wgrad(m, w, x_rows, st));
+    TCN_CHECK(wgrad(m, w, x_rows, ws));
   }
   // stages, last to first
   const float* g = m->Gp[3];
-  int pp = 0;
+  int gi = 0;
   for (int s = 3; s >= 0; --s) {
     for (int l = m->stage_first[s + 1] - 1; l >= m->stage_first[s]; --l) {
       int sh[3];
       layer_shifts(m, l, sh);
+      float* gu = m->gus[l];
       // gu = (gv W2) * [h > 0],   gv = keep * gy / (1 - p) applied as gy is loaded
       {
         TapGemmDev p = base_tapgemm(m);
-        p.X = g; p.ldx = C; p.Wf = m->wf_(m->wf_w2T[l]); p.Y = m->gu; p.ldy = C; p.M = m->H[l]; p.ldm = C;
+        p.X = g; p.ldx = C; p.Wf = m->wf_(m->wf_w2T[l]); p.Y = gu; p.ldy = C; p.M = m->H[l]; p.ldm = C;
         if (pl > 0.f) { p.in_drop_thresh = drop_thresh(pl); p.in_drop_scale = 1.f / (1.f - pl); p.in_drop_stream = (uint32_t)l; }
         TCN_CHECK(gemm(m, p, C, C, st));
       }
+      TCN_CHECK(hand_over());  // gy (= g) and gu of this layer are final
       {
         WgradDev w = base_wgrad(m);
         w.G = g; w.ldg = C; w.g_cols = C; w.X = m->H[l]; w.ldx = C; w.n_out = C; w.c_in = C;
         w.dW = m->g_(m->off_w2[l]); w.db = m->g_(m->off_b2[l]);
         if (pl > 0.f) { w.g_drop_thresh = drop_thresh(pl); w.g_drop_scale = 1.f / (1.f - pl); w.g_drop_stream = (uint32_t)l; }
-        TCN_CHECK(wgrad(m, w, x_rows, st));
+        TCN_CHECK(wgrad(m, w, x_rows, ws));
       }
       {
         WgradDev w = base_wgrad(m);
-        w.G = m->gu; w.ldg = C; w.g_cols = C; w.X = m->act[l]; w.ldx = C; w.n_out = C; w.c_in = C; w.ntaps = 3;
+        w.G = gu; w.ldg = C; w.g_cols = C; w.X = m->act[l]; w.ldx = C; w.n_out = C; w.c_in = C; w.ntaps = 3;
         for (int i = 0; i < 3; ++i) w.shift[i] = sh[i];
         w.dW = m->g_(m->off_w1[l]); w.db = m->g_(m->off_b1[l]);
-        TCN_CHECK(wgrad(m, w, x_rows, st));
+        TCN_CHECK(wgrad(m, w, x_rows, ws));
       }
       {  // gx = gy + sum_k W1_k^T gu[t - s_k]
         TapGemmDev p = base_tapgemm(m);
-        p.X = m->gu; p.ldx = C; p.Wf = m->wf_(m->wf_w1T[l]); p.Y = m->gbuf[pp]; p.ldy = C; p.R = g; p.ldr = C;
+        p.X = gu; p.ldx = C; p.Wf = m->wf_(m->wf_w1T[l]); p.Y = m->gpool[gi]; p.ldy = C; p.R = g; p.ldr = C;
         p.ntaps = 3;
         for (int i = 0; i < 3; ++i) p.shift[i] = -sh[i];
         TCN_CHECK(gemm(m, p, C, C, st));
-        g = m->gbuf[pp];
-        pp ^= 1;
+        g = m->gpool[gi++];
       }
     }
     if (s > 0) {  // f_{s-1} also feeds the lateral of level s-1
       TapGemmDev p = base_tapgemm(m);
-      p.X = m->Gp[s - 1]; p.ldx = C; p.Wf = m->wf_(m->wf_latT); p.Y = m->gbuf[pp]; p.ldy = C; p.R = g; p.ldr = C;
+      p.X = m->Gp[s - 1]; p.ldx = C; p.Wf = m->wf_(m->wf_latT); p.Y = m->gpool[gi]; p.ldy = C; p.R = g; p.ldr = C;
       TCN_CHECK(gemm(m, p, C, C, st));
-      g = m->gbuf[pp];
-      pp ^= 1;
+      g = m->gpool[gi++];
     }
   }
   // projection weight grads (x is a leaf: no input gradient); same mask / channel scale as the forward
@@ -683,6 +712,13 @@ static int model_backward(tcn_model* m, const float* x, long x_rows, const float
       w.x_drop_thresh = drop_thresh(m->input_mask_p); w.x_drop_scale = 1.f; w.x_drop_stream = kStreamMask;
     }
     TCN_CHECK(wgrad(m, w, x_rows, st));
+  }
+  if (ws != st) {  // join: the caller's stream owns every gradient again
+    cudaEvent_t ev = m->evs[nev++];
+    if (cudaEventRecord(ev, ws) != cudaSuccess || cudaStreamWaitEvent(st, ev, 0) != cudaSuccess) {
+      set_error("tcn_model backward: join failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return TCN_ERR_CUDA;
+    }
   }
   return TCN_OK;
 }

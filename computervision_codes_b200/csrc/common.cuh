@@ -12,6 +12,24 @@ namespace tcn {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);  // cudaGetLastError() -> TCN_ERR_CUDA
 int num_sms();
+bool pdl_enabled();  // TCN_NO_PDL=1 turns programmatic dependent launch off
+
+// Launch with (optionally) the programmatic-stream-serialization attribute.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 #define TCN_REQUIRE(cond, ...)                 \
   do {                                         \
@@ -71,6 +89,12 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may start
+// while its stream predecessor is still running; it must execute pdl_wait() before it touches anything the
+// predecessor wrote.  pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as soon as SMs free up.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 
 // fp32 -> (big, small) tf32 pair, big + small == x to ~2^-21 relative (the 3xTF32 split).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {

@@ -248,6 +248,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   const bool active = blk < nblk;
   BlkMeta m = {0, 0, 0, 0};
@@ -403,6 +405,9 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t dseed = p.dyn ? p.dyn->seed : 0u;
+  // everything above (barriers, TMEM) overlapped the tail of the previous kernel; its results are needed from here on
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -639,7 +644,7 @@ int launch_gemm_tc(const CUtensorMap& mx, const CUtensorMap& mwhi, const CUtenso
     int gx = num_sms() / nty;
     if (gx < 1) gx = 1;
     if (gx > nb) gx = nb;
-    gemm_tc_persist_kernel<<<dim3(gx, nty), TP_THREADS, smem, stream>>>(mx, mwhi, mwlo, p);
+    launch_kernel(gemm_tc_persist_kernel, dim3(gx, nty), dim3(TP_THREADS), smem, stream, true, mx, mwhi, mwlo, p);
     return check_launch("gemm_tc_persist_kernel");
   }
   dim3 grid(nb, nty);
@@ -654,7 +659,7 @@ int launch_gemm_tc(const CUtensorMap& mx, const CUtensorMap& mwhi, const CUtenso
     }
     attr_set = true;
   }
-  gemm_tc_kernel<64><<<grid, TC_THREADS, TcSmem<64>::kBytes, stream>>>(mx, mwhi, mwlo, p);
+  launch_kernel(gemm_tc_kernel<64>, grid, dim3(TC_THREADS), TcSmem<64>::kBytes, stream, true, mx, mwhi, mwlo, p);
   return check_launch("gemm_tc_kernel");
 }
 

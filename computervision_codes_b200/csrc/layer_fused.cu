@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(LF_THREADS, 3) layer_fwd64_kernel(const LayerF
   const int tb1 = halo ? (s1 - s0) : LF_TM, tb2 = halo ? (s2 - s0) : 2 * LF_TM;  // slab row of tap k, frame 0
   const int zbase = (s1 == 0) ? tb1 : ((s2 == 0) ? tb2 : 0);                      // the tap with shift 0
   const uint32_t seed = p.drop_seed ^ (p.dyn ? p.dyn->seed : 0u);
+  pdl_launch_dependents();
+  pdl_wait();
 
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const int blk = tile >> 1;
@@ -184,7 +186,7 @@ int launch_layer_fwd64(const LayerFwdDev& p, int cap_nblk, cudaStream_t stream) 
   const long cap = (long)num_sms() * 3;
   if (tiles > cap) tiles = cap;
   if (tiles < 1) tiles = 1;
-  layer_fwd64_kernel<<<(int)tiles, LF_THREADS, LF_SMEM, stream>>>(p);
+  launch_kernel(layer_fwd64_kernel, dim3((int)tiles), dim3(LF_THREADS), LF_SMEM, stream, true, p);
   return check_launch("layer_fwd64_kernel");
 }
 

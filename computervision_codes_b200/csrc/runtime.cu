@@ -1,6 +1,7 @@
 // Library runtime: error strings, device queries.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -22,6 +23,12 @@ int check_launch(const char* what) {
     return TCN_ERR_CUDA;
   }
   return TCN_OK;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) v = (getenv("TCN_NO_PDL") == nullptr) ? 1 : 0;
+  return v == 1;
 }
 
 int num_sms() {

@@ -107,6 +107,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   // the (tap, column block) of each of the four X blocks of this m-tile (blocks past the end repeat the last one)
   int a_tap[4], a_cb[4];
@@ -309,7 +311,7 @@ int launch_wgrad_tc(const CUtensorMap& mx, const CUtensorMap& mg, WgradTcDev& p,
   if (rs < 1) rs = 1;
   if (rs > nb) rs = nb;
   p.row_splits = rs;
-  wgrad_tc_kernel<<<dim3(rs, mt, nt), TC_THREADS, WG_SMEM, stream>>>(mx, mg, p);
+  launch_kernel(wgrad_tc_kernel, dim3(rs, mt, nt), dim3(TC_THREADS), WG_SMEM, stream, true, mx, mg, p);
   return check_launch("wgrad_tc_kernel");
 }
 

@@ -326,10 +326,30 @@ def main():
     os._exit(0)
 
 
+def _graph_time(fn, n=24):
+    """Average GPU time of fn(): n calls captured in one CUDA graph, replayed once under CUDA events."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
 def measure_layer_roofline(model, lengths, batch, dev):
-    """Fused residual-layer forward kernel (the kernel every stage is made of): average duration over
-    back-to-back launches on this batch shape, CUDA events on the launch stream, training variant
-    (writes y and h).  Algorithmic bytes per frame per SURVEY 8(d): 8*C (read x, write y)."""
+    """Dominant kernel by time share (profiles/): the residual layers' tensor-core kernels.  Reported here: the
+    input-gradient tap GEMM `gemm_tc_persist_kernel` (3 taps; gx = gy + sum_k W1_k^T gu[t - s_k]) timed live on this
+    step's batch shape, and the same kernel on the TERL stress shape (64 x 8000 frames) where the HBM roofline is
+    the binding limit.  Algorithmic bytes per frame: 12*C (read gu, read gy, write gx)."""
     from computervision_codes_b200 import ops
     from computervision_codes_b200.layout import SeqLayout
 
@@ -337,42 +357,35 @@ def measure_layer_roofline(model, lengths, batch, dev):
     peak, src = 6650.0, "fallback"
     if os.path.exists(peaks_path):
         peak, src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
-    lens = [lengths[v] for v in batch]
-    lay = SeqLayout.get(lens, dev)
-    frames = sum(lens)
-    layer = model.PG.layers[3]
-    w1f = ops.prep_weight(layer.conv_dilated.weight)
-    w2f = ops.prep_weight(layer.conv_1x1.weight)
-    b1, b2 = layer.conv_dilated.bias.detach(), layer.conv_1x1.bias.detach()
-    shifts = ops.tap_shifts(layer.dilation, layer.causal)
-    nbuf = 8  # rotate over several activation buffers, as the 41 layers of a step do
-    xs = [torch.randn(lay.rows, C_MAPS, device=dev) for _ in range(nbuf)]
-    lib_args = dict(save_h=True, drop_p=0.5, seed=1, stream_id=3)
-    for i in range(3):
-        ops.layer_fwd(xs[i % nbuf], w1f, w2f, b1, b2, lay, shifts, **lib_args)
-    torch.cuda.synchronize()
-    n = 40
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(n):
-        ops.layer_fwd(xs[i % nbuf], w1f, w2f, b1, b2, lay, shifts, **lib_args)
-    e1.record()
-    torch.cuda.synchronize()
-    # the loop above also pays two torch.zeros_like allocations + fills per call; time those alone and subtract
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for i in range(n):
-        torch.zeros_like(xs[0]); torch.zeros_like(xs[0])
-    e3.record()
-    torch.cuda.synchronize()
-    ms = max((e0.elapsed_time(e1) - e2.elapsed_time(e3)) / n, 1e-6)
-    alg_bytes = 8 * C_MAPS * frames
-    achieved = alg_bytes / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "layer_fwd64_kernel (fused dilated residual layer forward, training variant)",
-            "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "frames_per_launch": frames, "ms_per_launch": ms,
-            "note": "one launch covers the step's ragged batch (a few MB of activations, L2-resident, ~1 wave of "
-                    "CTAs): latency-bound at this size; profiles/ holds the stress shape (64 x 8000 frames)"}
+    layer = model.PG.layers[4]
+    w1 = layer.conv_dilated.weight.detach()
+    hi, lo = ops.split_weight(w1, transpose=True)
+    shifts = tuple(-s for s in ops.tap_shifts(layer.dilation, layer.causal))
+
+    def run(lens, nbuf):
+        lay = SeqLayout.get(lens, dev)
+        gu = [torch.randn(lay.rows, C_MAPS, device=dev) for _ in range(nbuf)]
+        gy = [torch.randn(lay.rows, C_MAPS, device=dev) for _ in range(nbuf)]
+        out = [torch.zeros(lay.rows, C_MAPS, device=dev) for _ in range(nbuf)]
+        it = [0]
+
+        def fn():
+            i = it[0] % nbuf
+            it[0] += 1
+            ops.gemm_tc(gu[i], hi, lo, lay, C_MAPS, C_MAPS, shifts, out=out[i], residual=gy[i])
+
+        ms = _graph_time(fn)
+        frames = sum(lens)
+        return frames, ms, 12 * C_MAPS * frames / (ms * 1e-3) / 1e9
+
+    frames, ms, gbs = run([lengths[v] for v in batch], 8)
+    sframes, sms, sgbs = run([8000] * 64, 6)
+    return {"bound": "hbm", "kernel": "gemm_tc_persist_kernel (tcgen05 tap GEMM, input gradient of the dilated conv)",
+            "achieved": gbs, "peak": peak, "peak_source": src, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+            "frames_per_launch": frames, "ms_per_launch": ms,
+            "stress_shape": {"frames_per_launch": sframes, "ms_per_launch": sms, "achieved": sgbs, "frac": sgbs / peak},
+            "note": "at this step's batch (a few MB per activation, L2-resident, one wave of CTAs) the kernel is "
+                    "latency-bound; the stress shape (64 x 8000 frames, 131 MB per activation) is HBM-bound"}
 
 
 if __name__ == "__main__":

@@ -21,6 +21,8 @@
 //              releases the smem stage back to the producer
 //   warps 2-5: epilogue      -- tcgen05.ld (32 lanes x 32 columns) -> epi -> 128-bit stores of Y
 // Accuracy: 3xTF32 == fp32 to ~1e-6 relative (see tests), the bar is 1e-3 on logits.
+#include <cstdlib>
+
 #include "gemm_tc.cuh"
 
 namespace tcn {
@@ -524,6 +526,211 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(128u));
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Slab variant of the persistent kernel for the k = 3 dilated convolutions with a small dilation
+// (max shift - min shift <= 64 frames, 64 input channels).  tcgen05 shared-memory descriptors may start at ANY row
+// of a TMA-swizzled tile (the 128B swizzle is a function of the absolute shared-memory address; verified on
+// B200, tools/exp/exp_desc.cu), so the three taps are read as row-offset views of ONE staged time slab
+// x[t0 + s_min .. t0 + 128 + s_max): every frame is loaded and split once per tile instead of once per tap.
+//   ring: 2 slots (one per 32-channel block), each [hi 192 x 128 B | lo 192 x 128 B]
+constexpr int SL_ROWS = 192;
+constexpr int SL_HALF = SL_ROWS * 128;      // 24576
+constexpr int SL_SLOT = 2 * SL_HALF;        // 49152
+static inline int sl_smem_bytes() { return 6 * 2 * TP_KB + 2 * SL_SLOT + TP_EPI + 1024 + 256; }
+
+__global__ void __launch_bounds__(TP_THREADS, 1)
+gemm_tc_slab_kernel(const __grid_constant__ CUtensorMap map_x32, const __grid_constant__ CUtensorMap map_whi,
+                    const __grid_constant__ CUtensorMap map_wlo, const GemmTcDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntile = blockIdx.y;
+  const int nblk = p.dyn ? p.dyn->nblk : p.nblk;
+  const int smin = min(p.shift[0], min(p.shift[1], p.shift[2]));
+  const int smax = max(p.shift[0], max(p.shift[1], p.shift[2]));
+  const int nrows = ((kBlkRows + (smax - smin)) + 31) & ~31;  // slab rows staged per tile (<= 192)
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* wt = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* sl = wt + 6 * 2 * TP_KB;
+  const uint32_t wt_addr = base, sl_addr = base + 6 * 2 * TP_KB;
+  float4* epi = reinterpret_cast<float4*>(sl + 2 * SL_SLOT);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sl + 2 * SL_SLOT + TP_EPI);
+  uint64_t* wfull = bars;
+  uint64_t* full_bar = bars + 1;    // [2]
+  uint64_t* ready_bar = bars + 3;   // [2]
+  uint64_t* empty_bar = bars + 5;   // [2]
+  uint64_t* tfull = bars + 7;       // [2]
+  uint64_t* tempty = bars + 9;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  if (threadIdx.x == 0) {
+    mbar_init(wfull, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&ready_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                 "r"(128u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t dseed = p.dyn ? p.dyn->seed : 0u;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wfull, 6 * 2 * TP_KB);
+      for (int kb = 0; kb < 6; ++kb) {
+        tma_load_2d(wt + kb * 2 * TP_KB, &map_whi, wfull, kb * TC_BK, ntile * 64);
+        tma_load_2d(wt + kb * 2 * TP_KB + TP_KB, &map_wlo, wfull, kb * TC_BK, ntile * 64);
+      }
+      int it = 0;
+      for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const BlkMeta m = p.meta[blk];
+        const int row0 = blk * kBlkRows;
+        if (row0 >= m.hi) continue;
+        for (int kc = 0; kc < 2; ++kc, ++it) {
+          const int s = it & 1;
+          const uint32_t ph = (it >> 1) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], nrows * 128);
+          for (int i = 0; i < nrows / 32; ++i)
+            tma_load_2d(sl + s * SL_SLOT + i * 4096, &map_x32, &full_bar[s], kc * TC_BK, row0 + smin + 32 * i);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, 64);
+    mbar_wait(wfull, 0);
+    int it = 0, tcount = 0;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      const BlkMeta m = p.meta[blk];
+      if (blk * kBlkRows >= m.hi) continue;
+      const int a = tcount & 1;
+      const uint32_t tph = (tcount >> 1) & 1;
+      mbar_wait(&tempty[a], tph ^ 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + a * 64;
+      for (int kc = 0; kc < 2; ++kc, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(&ready_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int tap = 0; tap < 3; ++tap) {
+            const int sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
+            const uint32_t a_hi = sl_addr + s * SL_SLOT + (uint32_t)(sh - smin) * 128, a_lo = a_hi + SL_HALF;
+            const uint32_t b_hi = wt_addr + (tap * 2 + kc) * 2 * TP_KB, b_lo = b_hi + TP_KB;
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; ++k) {
+              const uint32_t ko = k * 32;
+              const uint64_t dah = umma_desc_sw128(a_hi + ko), dal = umma_desc_sw128(a_lo + ko);
+              const uint64_t dbh = umma_desc_sw128(b_hi + ko), dbl = umma_desc_sw128(b_lo + ko);
+              umma_tf32(tacc, dal, dbh, idesc, (kc | tap | k) != 0);
+              umma_tf32(tacc, dah, dbl, idesc, 1u);
+              umma_tf32(tacc, dah, dbh, idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          if (kc == 1) umma_commit(&tfull[a]);
+        }
+        __syncwarp();
+      }
+      ++tcount;
+    }
+  } else if (warp < 6) {
+    // ===================== operand split of the slab (warps 2..5) =====================
+    const int ct = threadIdx.x - 64;
+    const int nchunks = nrows * 8;
+    int it = 0;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      const BlkMeta m = p.meta[blk];
+      const int row0 = blk * kBlkRows;
+      if (row0 >= m.hi) continue;
+      for (int kc = 0; kc < 2; ++kc, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(&full_bar[s], ph);
+        float4* xa = reinterpret_cast<float4*>(sl + s * SL_SLOT);
+        float4* xl = reinterpret_cast<float4*>(sl + s * SL_SLOT + SL_HALF);
+        for (int c0 = ct; c0 < nchunks; c0 += 4 * 128) {  // nchunks is a multiple of 256
+          float4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = (c0 + i * 128 < nchunks) ? xa[c0 + i * 128] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c = c0 + i * 128;
+            if (c < nchunks) {
+              const int src = row0 + smin + (c >> 3);  // a slab row is valid iff its source frame is inside the sequence
+              const float keep = (src >= m.lo && src < m.hi) ? 1.f : 0.f;
+              float4 h, l;
+              const float x0 = v[i].x * keep, x1 = v[i].y * keep, x2 = v[i].z * keep, x3 = v[i].w * keep;
+              h.x = __uint_as_float(__float_as_uint(x0) & 0xffffe000u); l.x = x0 - h.x;
+              h.y = __uint_as_float(__float_as_uint(x1) & 0xffffe000u); l.y = x1 - h.y;
+              h.z = __uint_as_float(__float_as_uint(x2) & 0xffffe000u); l.z = x2 - h.z;
+              h.w = __uint_as_float(__float_as_uint(x3) & 0xffffe000u); l.w = x3 - h.w;
+              xa[c] = h;
+              xl[c] = l;
+            }
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&ready_bar[s]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 6..9) =====================
+    const int q = warp & 3;
+    const uint32_t out_seed = p.drop_seed ^ dseed;
+    const bool vec_ok = ((p.ldy & 3) == 0) && (p.R == nullptr || (p.ldr & 3) == 0) && (p.M == nullptr || (p.ldm & 3) == 0);
+    int tcount = 0;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      const BlkMeta m = p.meta[blk];
+      const int row0 = blk * kBlkRows;
+      if (row0 >= m.hi) continue;
+      const int a = tcount & 1;
+      const uint32_t tph = (tcount >> 1) & 1;
+      mbar_wait(&tfull[a], tph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * 64;
+      float v0[32], v1[32];
+      tmem_ld32(taddr, v0);
+      tmem_ld32(taddr + 32, v1);
+      tc_fence_before();
+      mbar_arrive(&tempty[a]);
+      epilogue_block_coalesced(v0, v1, epi + (warp - 6) * 512, lane, row0 + q * 32, m.hi, ntile * 64, p, out_seed,
+                               vec_ok);
+      ++tcount;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(128u));
+}
+
+static bool slab_eligible(const GemmTcDev& p) {
+  if (p.ntaps != 3 || p.kbp != 2 || p.x_unpadded || p.colscale != nullptr || p.in_drop_thresh != 0u) return false;
+  const int smin = p.shift[0] < p.shift[1] ? (p.shift[0] < p.shift[2] ? p.shift[0] : p.shift[2])
+                                           : (p.shift[1] < p.shift[2] ? p.shift[1] : p.shift[2]);
+  const int smax = p.shift[0] > p.shift[1] ? (p.shift[0] > p.shift[2] ? p.shift[0] : p.shift[2])
+                                           : (p.shift[1] > p.shift[2] ? p.shift[1] : p.shift[2]);
+  return (smax - smin) <= 64;
+}
+
 // ------------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -623,11 +830,35 @@ int launch_split_batched(const SplitJob* jobs_dev, int njobs, const float* param
   return check_launch("split_weight_batched_kernel");
 }
 
+bool gemm_tc_wants_slab(const GemmTcDev& p) {
+  static int on = -1;
+  if (on < 0) on = getenv("TCN_NO_SLAB") == nullptr ? 1 : 0;
+  return on == 1 && slab_eligible(p);
+}
+
 int launch_gemm_tc(const CUtensorMap& mx, const CUtensorMap& mwhi, const CUtensorMap& mwlo, const GemmTcDev& p,
-                   int cap_nblk, cudaStream_t stream) {
+                   int cap_nblk, cudaStream_t stream, const CUtensorMap* mx32) {
   const int nb = cap_nblk > 0 ? cap_nblk : p.nblk;
   const int kblocks = p.ntaps * p.kbp;
   const int nty = (p.N + 63) / 64;
+  if (mx32 != nullptr && gemm_tc_wants_slab(p)) {
+    static bool slab_set = false;
+    if (!slab_set) {
+      const cudaError_t e =
+          cudaFuncSetAttribute(gemm_tc_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sl_smem_bytes());
+      if (e != cudaSuccess) {
+        set_error("gemm_tc_slab: smem attribute: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return TCN_ERR_CUDA;
+      }
+      slab_set = true;
+    }
+    int gx = num_sms() / nty;
+    if (gx < 1) gx = 1;
+    if (gx > nb) gx = nb;
+    launch_kernel(gemm_tc_slab_kernel, dim3(gx, nty), dim3(TP_THREADS), sl_smem_bytes(), stream, true, *mx32, mwhi, mwlo, p);
+    return check_launch("gemm_tc_slab_kernel");
+  }
   if (kblocks <= TP_MAX_KB) {  // persistent, weights resident in shared memory
     static int max_set = 0;
     const int smem = tp_smem_bytes(kblocks);
@@ -716,5 +947,8 @@ extern "C" int tcn_gemm_tc(const tcn_gemm_tc_args* a, tcn_stream_t stream) {
   p.drop_thresh = a->drop_p > 0.f ? drop_thresh(a->drop_p) : 0u;
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
   p.drop_seed = a->drop_seed; p.drop_stream = a->drop_stream;
-  return launch_gemm_tc(mx, mh, ml, p, 0, (cudaStream_t)stream);
+  CUtensorMap mx32;
+  const bool slab = gemm_tc_wants_slab(p);
+  if (slab) TCN_CHECK(make_tensor_map_2d(&mx32, a->x, a->x_rows, a->c_in, a->ldx, 32));
+  return launch_gemm_tc(mx, mh, ml, p, 0, (cudaStream_t)stream, slab ? &mx32 : nullptr);
 }

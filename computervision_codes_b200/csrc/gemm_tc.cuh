@@ -138,8 +138,11 @@ int launch_split_weight(const float* w, float* whi, float* wlo, int n_out, int c
                         cudaStream_t stream);
 int launch_split_batched(const SplitJob* jobs_dev, int njobs, const float* params, float* whi, float* wlo, long total,
                          cudaStream_t stream);
+// mx32: optional map of the same tensor with 32-row boxes; when given and the problem is a small-dilation k = 3
+// convolution over 64 channels the slab kernel is used (each frame staged once per tile instead of once per tap)
 int launch_gemm_tc(const CUtensorMap& mx, const CUtensorMap& mwhi, const CUtensorMap& mwlo, const GemmTcDev& p,
-                   int cap_nblk, cudaStream_t stream);
+                   int cap_nblk, cudaStream_t stream, const CUtensorMap* mx32 = nullptr);
+bool gemm_tc_wants_slab(const GemmTcDev& p);
 
 // tcgen05 weight-gradient kernel (wgrad_tc.cu)
 constexpr int WG_BOX_ROWS = 32;

@@ -73,6 +73,7 @@ struct tcn_model {
   bool use_tc = false;
   std::map<long, TcW> tcw;
   std::map<std::pair<const float*, int>, CUtensorMap> xmaps;
+  std::map<std::pair<const float*, int>, CUtensorMap> xmaps32;  // same tensors, 32-row boxes (slab kernel)
   std::map<std::pair<const float*, long>, CUtensorMap> wgmaps;  // 32-frame boxes, 32-byte swizzle atoms (wgrad_tc)
   float *tc_whi = nullptr, *tc_wlo = nullptr;
   long tc_wfloats = 0;
@@ -171,7 +172,17 @@ int gemm(tcn_model* m, TapGemmDev& p, int c_in, int n_out, cudaStream_t st) {
       q.in_drop_thresh = p.in_drop_thresh; q.in_drop_scale = p.in_drop_scale;
       q.in_drop_seed = p.in_drop_seed; q.in_drop_stream = p.in_drop_stream;
       q.drop_thresh = p.drop_thresh; q.drop_scale = p.drop_scale; q.drop_seed = p.drop_seed; q.drop_stream = p.drop_stream;
-      return launch_gemm_tc(xm->second, it->second.mh, it->second.ml, q, m->max_blk, st);
+      const CUtensorMap* mx32 = nullptr;
+      if (gemm_tc_wants_slab(q)) {
+        auto x32 = m->xmaps32.find(xkey);
+        if (x32 == m->xmaps32.end()) {
+          CUtensorMap map;
+          TCN_CHECK(make_tensor_map_2d(&map, p.X, m->cfg.max_rows, p.ldx, p.ldx, 32));
+          x32 = m->xmaps32.emplace(xkey, map).first;
+        }
+        mx32 = &x32->second;
+      }
+      return launch_gemm_tc(xm->second, it->second.mh, it->second.ml, q, m->max_blk, st, mx32);
     }
   }
   p.c_in = c_in; p.kpt = rup(c_in, 8); p.n_out = n_out; p.NT8 = (n_out + 7) / 8;
@@ -550,7 +561,9 @@ static int model_forward(tcn_model* m, const float* x, long x_rows, int training
   for (int l = 0; l < L; ++l) {
     int s[3];
     layer_shifts(m, l, s);
-    if (C == 64) {
+    // one wave of tiles or less: the fused mma.sync kernel has the shorter latency; beyond that two tcgen05 launches
+    // (conv3 + ReLU -> h, 1x1 + dropout + residual -> y) move more frames per second
+    if (C == 64 && !(m->use_tc && m->max_blk > 2 * num_sms())) {
       LayerFwdDev p;
       p.X = m->act[l]; p.Y = m->act[l + 1]; p.H = save_h ? m->H[l] : nullptr;
       p.W1f = m->wf_(m->wf_w1[l]); p.W2f = m->wf_(m->wf_w2[l]);

@@ -98,20 +98,20 @@ def test_gemm_tc_taps_and_epilogue_match_mma_sync_path_and_fp64(shifts):
                     stream_id=9)
     y2 = ops.tapgemm(x, ops.prep_weight(w.to(DEV)), lay, C, C, shifts, bias=b.to(DEV), residual=res, relu_mask=msk,
                      drop_p=0.5, seed=3, stream_id=9)
-    assert _maxabs(y, y2) <= 2e-5
+    assert _maxabs(y, y2) <= 5e-5
     keep = ops.dropout_keep_mask(lay.rows, C, 0.5, 3, 9, DEV).cpu().double()
     for s, T in enumerate(lengths):
         r0 = lay.starts[s]
         u = O.conv_taps(xs[s].double().t().unsqueeze(0), w.double(), b.double(), shifts)[0].t()
         u = u * (msk[r0:r0 + T].cpu().double() > 0) * keep[r0:r0 + T] * 2.0 + res[r0:r0 + T].cpu().double()
-        assert _maxabs(y[r0:r0 + T], u) <= 2e-5
+        assert _maxabs(y[r0:r0 + T], u) <= 5e-5
     # relu + dropout applied to the loaded operand (the backward of a dropout), transposed weights
     hit, lot = ops.split_weight(w.to(DEV), transpose=True)
     g = ops.gemm_tc(x, hit, lot, lay, C, C, tuple(-s for s in shifts), relu=True, in_drop_p=0.5, in_drop_rescale=True,
                     seed=3, stream_id=9)
     g2 = ops.tapgemm(x, ops.prep_weight(w.to(DEV), transpose=True), lay, C, C, tuple(-s for s in shifts), relu=True,
                      in_drop_p=0.5, seed=3, stream_id=9)
-    assert _maxabs(g, g2) <= 2e-5
+    assert _maxabs(g, g2) <= 5e-5
 
 
 @pytest.mark.parametrize("lengths,c_in,n_out,shifts,unpadded", [([300, 129], 64, 64, (-4, 0, 4), False),

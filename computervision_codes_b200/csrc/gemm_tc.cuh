@@ -168,5 +168,7 @@ struct WgradTcDev {
 };
 // mx / mg: maps built with make_tensor_map_2d(..., WG_BOX_ROWS, /*atom32=*/true)
 int launch_wgrad_tc(const CUtensorMap& mx, const CUtensorMap& mg, WgradTcDev& p, int cap_nblk, cudaStream_t stream);
+int launch_wgrad_tc_pair(const CUtensorMap& mx0, const CUtensorMap& mg0, WgradTcDev& p0, const CUtensorMap& mx1,
+                         const CUtensorMap& mg1, WgradTcDev& p1, int cap_nblk, cudaStream_t stream);
 
 }  // namespace tcn

@@ -201,25 +201,51 @@ int get_wgmap(tcn_model* m, const float* ptr, long rows, int cols, const CUtenso
   return TCN_OK;
 }
 
+bool wgrad_tc_ok(const tcn_model* m, const WgradDev& w) {
+  return m->use_tc && (w.ldx % 4 == 0) && (w.ldg % 4 == 0) && (w.c_in % 4 == 0);
+}
+
+WgradTcDev to_tc(const WgradDev& w) {
+  WgradTcDev q;
+  memset(&q, 0, sizeof(q));
+  q.meta = w.meta; q.nblk = w.nblk; q.dyn = w.dyn; q.x_unpadded = w.x_unpadded;
+  q.n_out = w.n_out; q.c_in = w.c_in; q.ntaps = w.ntaps;
+  for (int i = 0; i < 3; ++i) q.shift[i] = w.shift[i];
+  q.dW = w.dW; q.db = w.db; q.colscale = w.colscale; q.colscale_ld = w.colscale_ld;
+  q.g_drop_thresh = w.g_drop_thresh; q.g_drop_scale = w.g_drop_scale;
+  q.g_drop_seed = w.g_drop_seed; q.g_drop_stream = w.g_drop_stream;
+  q.x_drop_thresh = w.x_drop_thresh; q.x_drop_scale = w.x_drop_scale;
+  q.x_drop_seed = w.x_drop_seed; q.x_drop_stream = w.x_drop_stream;
+  return q;
+}
+
 // weight-gradient dispatcher: tcgen05 kernel when available, mma.sync kernel otherwise
 int wgrad(tcn_model* m, WgradDev& w, long x_rows, cudaStream_t st) {
-  if (m->use_tc && (w.ldx % 4 == 0) && (w.ldg % 4 == 0) && (w.c_in % 4 == 0)) {
+  if (wgrad_tc_ok(m, w)) {
     const CUtensorMap *mx, *mg;
     TCN_CHECK(get_wgmap(m, w.X, w.x_unpadded ? x_rows : m->cfg.max_rows, w.ldx, &mx));
     TCN_CHECK(get_wgmap(m, w.G, m->cfg.max_rows, w.ldg, &mg));
-    WgradTcDev q;
-    memset(&q, 0, sizeof(q));
-    q.meta = w.meta; q.nblk = w.nblk; q.dyn = w.dyn; q.x_unpadded = w.x_unpadded;
-    q.n_out = w.n_out; q.c_in = w.c_in; q.ntaps = w.ntaps;
-    for (int i = 0; i < 3; ++i) q.shift[i] = w.shift[i];
-    q.dW = w.dW; q.db = w.db; q.colscale = w.colscale; q.colscale_ld = w.colscale_ld;
-    q.g_drop_thresh = w.g_drop_thresh; q.g_drop_scale = w.g_drop_scale;
-    q.g_drop_seed = w.g_drop_seed; q.g_drop_stream = w.g_drop_stream;
-    q.x_drop_thresh = w.x_drop_thresh; q.x_drop_scale = w.x_drop_scale;
-    q.x_drop_seed = w.x_drop_seed; q.x_drop_stream = w.x_drop_stream;
+    WgradTcDev q = to_tc(w);
     return launch_wgrad_tc(*mx, *mg, q, m->max_blk, st);
   }
   return launch_wgrad(w, m->max_blk, st);
+}
+
+// the two weight gradients of one residual layer in a single launch
+int wgrad_pair(tcn_model* m, WgradDev& w0, WgradDev& w1, long x_rows, cudaStream_t st) {
+  static const bool pair_on = std::getenv("TCN_NO_WGRAD_PAIR") == nullptr;
+  // (a single launch wins while the step is latency-bound; with several waves of rows two full-width launches do)
+  if (pair_on && m->max_blk <= 2 * num_sms() && wgrad_tc_ok(m, w0) && wgrad_tc_ok(m, w1) && w0.n_out <= 64 && w1.n_out <= 64 && !w0.x_unpadded && !w1.x_unpadded) {
+    const CUtensorMap *mx0, *mg0, *mx1, *mg1;
+    TCN_CHECK(get_wgmap(m, w0.X, m->cfg.max_rows, w0.ldx, &mx0));
+    TCN_CHECK(get_wgmap(m, w0.G, m->cfg.max_rows, w0.ldg, &mg0));
+    TCN_CHECK(get_wgmap(m, w1.X, m->cfg.max_rows, w1.ldx, &mx1));
+    TCN_CHECK(get_wgmap(m, w1.G, m->cfg.max_rows, w1.ldg, &mg1));
+    WgradTcDev q0 = to_tc(w0), q1 = to_tc(w1);
+    return launch_wgrad_tc_pair(*mx0, *mg0, q0, *mx1, *mg1, q1, m->max_blk, st);
+  }
+  TCN_CHECK(wgrad(m, w0, x_rows, st));
+  return wgrad(m, w1, x_rows, st);
 }
 
 }  // namespace
@@ -686,18 +712,15 @@ static int model_backward(tcn_model* m, const float* x, long x_rows, const float
       }
       TCN_CHECK(hand_over());  // gy (= g) and gu of this layer are final
       {
-        WgradDev w = base_wgrad(m);
-        w.G = g; w.ldg = C; w.g_cols = C; w.X = m->H[l]; w.ldx = C; w.n_out = C; w.c_in = C;
-        w.dW = m->g_(m->off_w2[l]); w.db = m->g_(m->off_b2[l]);
-        if (pl > 0.f) { w.g_drop_thresh = drop_thresh(pl); w.g_drop_scale = 1.f / (1.f - pl); w.g_drop_stream = (uint32_t)l; }
-        TCN_CHECK(wgrad(m, w, x_rows, ws));
-      }
-      {
-        WgradDev w = base_wgrad(m);
-        w.G = gu; w.ldg = C; w.g_cols = C; w.X = m->act[l]; w.ldx = C; w.n_out = C; w.c_in = C; w.ntaps = 3;
-        for (int i = 0; i < 3; ++i) w.shift[i] = sh[i];
-        w.dW = m->g_(m->off_w1[l]); w.db = m->g_(m->off_b1[l]);
-        TCN_CHECK(wgrad(m, w, x_rows, ws));
+        WgradDev w2 = base_wgrad(m);
+        w2.G = g; w2.ldg = C; w2.g_cols = C; w2.X = m->H[l]; w2.ldx = C; w2.n_out = C; w2.c_in = C;
+        w2.dW = m->g_(m->off_w2[l]); w2.db = m->g_(m->off_b2[l]);
+        if (pl > 0.f) { w2.g_drop_thresh = drop_thresh(pl); w2.g_drop_scale = 1.f / (1.f - pl); w2.g_drop_stream = (uint32_t)l; }
+        WgradDev w1 = base_wgrad(m);
+        w1.G = gu; w1.ldg = C; w1.g_cols = C; w1.X = m->act[l]; w1.ldx = C; w1.n_out = C; w1.c_in = C; w1.ntaps = 3;
+        for (int i = 0; i < 3; ++i) w1.shift[i] = sh[i];
+        w1.dW = m->g_(m->off_w1[l]); w1.db = m->g_(m->off_b1[l]);
+        TCN_CHECK(wgrad_pair(m, w1, w2, x_rows, ws));
       }
       {  // gx = gy + sum_k W1_k^T gu[t - s_k]
         TapGemmDev p = base_tapgemm(m);

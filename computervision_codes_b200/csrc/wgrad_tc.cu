@@ -66,12 +66,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int M, int N) {
          ((uint32_t)(M >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
-                const WgradTcDev p) {
+__device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const CUtensorMap* map_gp, const WgradTcDev& p,
+                                              const int split, const int mtile, const int ntile) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int split = blockIdx.x, mtile = blockIdx.y, ntile = blockIdx.z;
   const int nblk = p.dyn ? p.dyn->nblk : p.nblk;
   const uint32_t dseed = p.dyn ? p.dyn->seed : 0u;
   const int blk_begin = (int)((long)split * nblk / p.row_splits);
@@ -146,10 +144,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int sh = a_tap[j] == 0 ? p.shift[0] : (a_tap[j] == 1 ? p.shift[1] : p.shift[2]);
-              tma_load_2d(st + j * WG_ATOM, &map_x, &full_bar[s], a_cb[j] * 32, r0 + dz + sh);
+              tma_load_2d(st + j * WG_ATOM, map_xp, &full_bar[s], a_cb[j] * 32, r0 + dz + sh);
             }
-            tma_load_2d(st + 4 * WG_ATOM, &map_g, &full_bar[s], (ntile * 2) * 32, r0);
-            tma_load_2d(st + 5 * WG_ATOM, &map_g, &full_bar[s], (ntile * 2 + 1) * 32, r0);
+            tma_load_2d(st + 4 * WG_ATOM, map_gp, &full_bar[s], (ntile * 2) * 32, r0);
+            tma_load_2d(st + 5 * WG_ATOM, map_gp, &full_bar[s], (ntile * 2 + 1) * 32, r0);
             ++it;
           }
         }
@@ -293,6 +291,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(64u));
 }
 
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
+                const WgradTcDev p) {
+  wgrad_tc_body(&map_x, &map_g, p, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// two independent problems in one launch (the two weight gradients of a residual layer): blockIdx.y < mt0 -> problem 0
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_g0,
+                     const WgradTcDev p0, const __grid_constant__ CUtensorMap map_x1,
+                     const __grid_constant__ CUtensorMap map_g1, const WgradTcDev p1, int mt0) {
+  if ((int)blockIdx.y < mt0)
+    wgrad_tc_body(&map_x0, &map_g0, p0, blockIdx.x, blockIdx.y, 0);
+  else
+    wgrad_tc_body(&map_x1, &map_g1, p1, blockIdx.x, blockIdx.y - mt0, 0);
+}
+
 int launch_wgrad_tc(const CUtensorMap& mx, const CUtensorMap& mg, WgradTcDev& p, int cap_nblk, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -313,6 +328,37 @@ int launch_wgrad_tc(const CUtensorMap& mx, const CUtensorMap& mg, WgradTcDev& p,
   p.row_splits = rs;
   launch_kernel(wgrad_tc_kernel, dim3(rs, mt, nt), dim3(TC_THREADS), WG_SMEM, stream, true, mx, mg, p);
   return check_launch("wgrad_tc_kernel");
+}
+
+int launch_wgrad_tc_pair(const CUtensorMap& mx0, const CUtensorMap& mg0, WgradTcDev& p0, const CUtensorMap& mx1,
+                         const CUtensorMap& mg1, WgradTcDev& p1, int cap_nblk, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e =
+        cudaFuncSetAttribute(wgrad_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    if (e != cudaSuccess) {
+      set_error("wgrad_tc_pair: smem attribute: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return TCN_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  p0.cbn = (p0.c_in + 31) / 32;
+  p1.cbn = (p1.c_in + 31) / 32;
+  const int mt0 = (p0.ntaps * p0.cbn + 3) / 4, mt1 = (p1.ntaps * p1.cbn + 3) / 4;
+  if (p0.n_out > 64 || p1.n_out > 64) {
+    set_error("wgrad_tc_pair: both problems must have n_out <= 64");
+    return TCN_ERR_INVALID_ARG;
+  }
+  const int nb = cap_nblk > 0 ? cap_nblk : p0.nblk;
+  int rs = num_sms() / (mt0 + mt1);
+  if (rs < 1) rs = 1;
+  if (rs > nb) rs = nb;
+  p0.row_splits = rs;
+  p1.row_splits = rs;
+  launch_kernel(wgrad_tc_pair_kernel, dim3(rs, mt0 + mt1, 1), dim3(TC_THREADS), WG_SMEM, stream, true, mx0, mg0, p0, mx1,
+                mg1, p1, mt0);
+  return check_launch("wgrad_tc_pair_kernel");
 }
 
 }  // namespace tcn

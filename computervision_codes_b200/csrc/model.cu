@@ -762,7 +762,8 @@ static int model_backward(tcn_model* m, const float* x, long x_rows, const float
 extern "C" int tcn_model_forward(tcn_model* m, const float* x, long long x_rows, int training, const float** feats,
                                  const float** logits, int* ld_logits, tcn_stream_t stream) {
   TCN_REQUIRE(m && x && m->params && x_rows > 0, "tcn_model_forward: null pointer / parameters not bound");
-  TCN_CHECK(model_forward(m, x, x_rows, training, training != 0, (cudaStream_t)stream));
+  // training: 0 = inference, 1 = train (dropout on, activations kept for backward), 2 = keep activations, no dropout
+  TCN_CHECK(model_forward(m, x, x_rows, training == 1, training != 0, (cudaStream_t)stream));
   if (feats) {
     for (int lv = 0; lv < 3; ++lv) feats[lv] = m->P[lv];
     feats[3] = m->act[m->stage_first[4]];

@@ -111,18 +111,30 @@ class ModelExecutor:
                                                     _lib.stream_ptr()), "tcn_model_train_step")
         return self.loss
 
-    def forward(self, x_rows, training=False):
+    def forward(self, x_rows, training=False, keep_activations=False):
         """Returns (feature pointers, logits pointers) wrapped as torch views over executor memory:
-        4 x (rows, C) and 4 x (rows, ld_logits) tensors, valid until the next executor call."""
+        4 x (rows, C) and 4 x (rows, ld_logits) tensors, valid until the next executor call.
+        keep_activations: keep what backward() needs even when dropout is off (eval-mode gradients)."""
         lib = _lib.load()
         feats, logits = (C.c_void_p * 4)(), (C.c_void_p * 4)()
         ld = C.c_int()
-        _lib.check(lib.tcn_model_forward(self.h, _lib.ptr(x_rows), x_rows.shape[0], int(training), feats, logits, C.byref(ld),
+        mode = 1 if training else (2 if keep_activations else 0)
+        _lib.check(lib.tcn_model_forward(self.h, _lib.ptr(x_rows), x_rows.shape[0], mode, feats, logits, C.byref(ld),
                                          _lib.stream_ptr()), "tcn_model_forward")
         rows = self._lay.rows
         Cc = self.cfg.channels
         return ([_view(feats[i], rows, Cc, self.device) for i in range(4)],
                 [_view(logits[i], rows, ld.value, self.device) for i in range(4)])
+
+
+    def backward(self, x_rows, glogits):
+        """Backward of the last forward(training or keep_activations) from the gradients w.r.t. the four logit maps
+        (rows, ld_logits; pad columns zero).  Gradients land in flat_g / p.grad (zeroed first)."""
+        lib = _lib.load()
+        gl = (C.c_void_p * 4)(*[_lib.ptr(g) for g in glogits])
+        gf = (C.c_void_p * 4)(None, None, None, None)
+        _lib.check(lib.tcn_model_backward(self.h, _lib.ptr(x_rows), x_rows.shape[0], gl, gf, _lib.stream_ptr()),
+                   "tcn_model_backward")
 
 
 class _RawCudaBuffer:

@@ -201,6 +201,44 @@ class FPN(nn.Module):
         return [lay.as_bct(p, Cc) for p in ps]
 
 
+class _VideoNasExecFn(torch.autograd.Function):
+    """VideoNas forward / backward through the native executor (csrc/model.cu): two C calls per step instead of a
+    few hundred Python-dispatched launches.  Outputs: 4 packed logit maps (rows, 132) + 4 packed feature maps."""
+
+    @staticmethod
+    def forward(ctx, module, x_rows, lay, training, need_grad, *params):
+        ex = module._get_executor(lay)
+        ex.set_batch(lay, ops.new_seed() if training else 0)
+        feats, logits = ex.forward(x_rows, training=training, keep_activations=need_grad)
+        outs = [t.clone() for t in logits] + [t.clone() for t in feats]  # executor memory is reused by the next call
+        ctx.module, ctx.x_rows, ctx.nparams = module, x_rows, len(params)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(*outs[4:])  # gradients w.r.t. the returned feature maps are not supported
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        module = ctx.module
+        ex = module._executor
+        glogits = []
+        for i in range(4):
+            g = gouts[i]
+            if g is None:
+                g = torch.zeros(ex._lay.rows, ex.ld_logits, device=ex.device, dtype=torch.float32)
+            glogits.append(g.contiguous())
+        ex.backward(ctx.x_rows, glogits)
+        flat = ex.flat_g.clone()  # one copy: later backward calls reuse (and zero) the executor's buffer
+        grads = []
+        offs = module._exec_offsets
+        for name, p in module._exec_params:
+            if name in offs:
+                o, n = offs[name]
+                grads.append(flat[o:o + n].view(p.shape))
+            else:
+                grads.append(None)
+        return (None, None, None, None, None) + tuple(grads)
+
+
 class VideoNas(nn.Module):
     """network.py:14-68."""
 
@@ -245,6 +283,35 @@ class VideoNas(nn.Module):
             logits = [ops.tap_linear(p, w, b, lay) for p in f_list]
         return f_list, logits
 
+    # ---- native executor path --------------------------------------------------------------------------
+    _executor = None
+
+    def _get_executor(self, lay):
+        from ..executor import ModelExecutor, canonical_param_names
+
+        ex = self._executor
+        if ex is None or ex.max_rows < lay.rows or ex.max_seqs < lay.num_seqs or ex.device != next(self.parameters()).device:
+            rows = max(lay.rows, ex.max_rows if ex is not None else 0)
+            self._executor = ex = ModelExecutor(self, max_rows=rows, max_seqs=max(lay.num_seqs, 8))
+            ex.set_dropout(0.0, self.PG.channel_dropout.p, self.PG.layers[0].dropout.p)
+            names = ex.names
+            lib_offs = {}
+            params = dict(self.named_parameters())
+            base = ex.flat_p.data_ptr()
+            for n in names:
+                p = params[n]
+                lib_offs[n] = ((p.data_ptr() - base) // 4, p.numel())
+            self._exec_offsets = lib_offs
+            self._exec_params = list(self.named_parameters())
+            for _, p in self._exec_params:
+                p.grad = None  # autograd assigns the gradients this path returns (the trainer binds flat views instead)
+        return ex
+
+    def _executor_ok(self):
+        c = self.PG.conv_1x1.out_channels
+        return (self.use_fpn and not self.use_output and len(self.Rs) == 3 and c % 4 == 0
+                and self.PG.conv_1x1.in_channels % 4 == 0)
+
     def forward(self, x, ismask):
         """x: (B, T, D).  Returns (out_list, out_list_i, out_list_v, out_list_t, f_list, f_list)."""
         _check_input(x)
@@ -258,7 +325,17 @@ class VideoNas(nn.Module):
             mask = torch.cat((torch.zeros(n - num_mask), torch.ones(num_mask)))
             mask = mask[torch.randperm(n)].view(B, D, T).to(x.device)  # network.py:43-48 (flat (B, D, T) order)
             mask_btd = mask.permute(0, 2, 1)
-        f_rows, logit_rows = self.forward_packed(x_btd, lay, mask_btd)
+        if self._executor_ok() and not x.requires_grad:
+            xin = x_btd if mask_btd is None else x_btd * mask_btd
+            x_rows = xin.reshape(B * T, D).contiguous()
+            lay_e = lay
+            self._get_executor(lay_e)
+            plist = [p for _, p in self._exec_params]
+            need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in plist)
+            outs = _VideoNasExecFn.apply(self, x_rows, lay_e, self.training, need_grad, *plist)
+            logit_rows, f_rows = list(outs[:4]), list(outs[4:])
+        else:
+            f_rows, logit_rows = self.forward_packed(x_btd, lay, mask_btd)
         Cc = f_rows[0].shape[1]
         out_list, out_i, out_v, out_t = [], [], [], []
         if not self.use_fpn:

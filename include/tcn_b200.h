@@ -185,8 +185,9 @@ int tcn_model_set_batch(tcn_model* m, const int* meta_host, int nblk, int rows, 
  * loss_out (device, 8 floats): [0..3] = per-head mean BCE summed over levels (ivt, i, v, t), [4] = total. */
 int tcn_model_train_step(tcn_model* m, const float* x, long long x_rows, const unsigned char* labels, int ldlab,
                          int training, float* loss_out, tcn_stream_t stream);
-/* inference / feature extraction: fills pointers to the 4 FPN feature maps (rows, C) and the 4 logit
- * maps (rows, ld_logits) owned by the model (valid until the next call) */
+/* forward only: fills pointers to the 4 FPN feature maps (rows, C) and the 4 logit maps (rows, ld_logits) owned
+ * by the model (valid until the next call).  training: 0 = inference, 1 = train mode (dropout on, activations kept
+ * for tcn_model_backward), 2 = eval-mode arithmetic but activations kept for tcn_model_backward */
 int tcn_model_forward(tcn_model* m, const float* x, long long x_rows, int training, const float** feats,
                       const float** logits, int* ld_logits, tcn_stream_t stream);
 /* backward from externally supplied gradients w.r.t. the 4 logit maps (rows, ld_logits; may be NULL)

@@ -193,7 +193,8 @@ def test_videonas_against_golden(golden_dir):
     m = VideoNas(args, nl_pg, nl_r, n_r, C, D, K).to(DEV).eval()
     m.load_state_dict({k[3:]: _t(z[k]) for k in z.files if k.startswith("sd.")})
     x = _t(z["x"]).to(DEV)
-    outs = m(x, False)
+    outs = m(x, False)  # goes through the native executor (two C calls)
+    assert m._executor is not None
     for name, lst in zip(("ivt", "i", "v", "t", "f"), (outs[0], outs[1], outs[2], outs[3], outs[4])):
         assert len(lst) == 4
         for lvl, t in enumerate(lst):
@@ -301,3 +302,40 @@ def test_videonas_cfg_baseline_shape_vs_oracle():
             assert torch.equal(a.argmax(1).cpu(), r.argmax(1))
             flips = (a > 0).cpu() != (r > 0)   # sigmoid > 0.5 decisions: only ties (|logit| ~ 0) may differ
             assert float(r[flips].abs().max()) < 1e-4 if bool(flips.any()) else True
+
+
+def test_drop_in_training_loop_matches_cpu_port_for_two_sgd_steps():
+    """The reference's train_loop pattern (run.py:182-235: model(img, True) -> 16 x BCEWithLogitsLoss -> grads = None ->
+    backward -> torch.optim.SGD(weight_decay)) on the drop-in module, against the CPU port doing the same
+    (dropout off in both so that the trajectories are comparable)."""
+    from computervision_codes_b200.tcn import VideoNas
+    from oracle import torch_port as P
+
+    args = types.SimpleNamespace(fpn=True, output=False, feature=False, trans=False, mask=False, hier=False)
+    torch.manual_seed(5)
+    m = VideoNas(args, 4, 3, 3, 64, 96, 100)
+    ref = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    m = m.to(DEV).eval()
+    g = torch.Generator().manual_seed(6)
+    videos = [(torch.randn(1, T, 96, generator=g), [(torch.rand(T, k, generator=g) < 0.1).float() for k in (6, 10, 15, 100)])
+              for T in (150, 333)]
+    opt = torch.optim.SGD(m.parameters(), lr=0.05, weight_decay=1e-5)
+    opt_ref = torch.optim.SGD(list(ref.values()), lr=0.05, weight_decay=1e-5)
+    bce = torch.nn.BCEWithLogitsLoss()
+    for x, labels in videos:
+        outs = m(x.to(DEV), True)
+        terms = [sum(bce(pd[0].transpose(0, 1), y.to(DEV)) for pd in lst)
+                 for lst, y in zip((outs[1], outs[2], outs[3], outs[0]), labels)]
+        loss = 0.1 * (terms[0] + terms[1] + terms[2]) + terms[3]
+        for p in m.parameters():
+            p.grad = None
+        loss.backward()
+        opt.step()
+        for p in ref.values():
+            p.grad = None
+        loss_ref = P.train_step_loss(x, ref, tuple(labels), train=False)
+        loss_ref.backward()
+        opt_ref.step()
+        assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+    for k, v in m.state_dict().items():
+        assert _maxabs(v, ref[k]) <= 2e-5, (k, _maxabs(v, ref[k]))

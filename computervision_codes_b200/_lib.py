@@ -92,6 +92,7 @@ class AttnArgs(C.Structure):
         ("dk", C.c_void_p), ("lddk", C.c_int), ("dv", C.c_void_p), ("lddv", C.c_int),
         ("seq_lo", C.c_void_p), ("seq_len", C.c_void_p), ("nseq", C.c_int), ("max_len", C.c_int),
         ("heads", C.c_int), ("head_dim", C.c_int), ("scale", C.c_float),
+        ("delta", C.c_void_p),
     ]
 
 

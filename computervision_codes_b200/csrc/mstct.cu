@@ -1,7 +1,7 @@
 // MS-TCT temporal blocks (MT4MTLKD/Temporal_mstct/MSTCT/Temporal_Encoder.py): the pieces that are not
 // per-frame dense contractions (those run on gemm_tc / wgrad_tc):
 //   layernorm_{fwd,bwd}      nn.LayerNorm over channels           (Temporal_Encoder.py:97,103,140,160,175-199)
-//   attn_fwd / attn_bwd_*    Global_Relational_Block attention     (:76-88) softmax(q k^T * hd^-0.5) v per (window, head)
+//   (the Global_Relational_Block attention, :76-88, lives in attention.cu)
 //   dwconv_gelu_{fwd,bwd}    Local_Relational_Block depthwise conv k=3 + GELU over time (:13-14,36-39)
 //   axpby                    y = a x + b y (residual bookkeeping of the Temporal_Mixer, TS_Mixer.py:66-76)
 // All tensors time-major fp32 (rows = frames of the packed windows, columns = channels), fp32 arithmetic.
@@ -78,279 +78,6 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     if (sg[c] != 0.f) atomicAdd(dgamma + c, sg[c]);
     if (sb[c] != 0.f) atomicAdd(dbeta + c, sb[c]);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ attention
-// q: (rows, ldq) with head h at columns [h*hd, (h+1)*hd); k and v likewise inside their buffers (column offsets
-// given by the caller).  One CTA = (sequence, head, 16 queries); 4 warps x 4 queries; keys / values streamed through
-// shared memory in chunks of 64 with an online softmax.  lse[row * heads + h] = log sum exp of the scaled scores.
-constexpr int AT_Q = 16, AT_KC = 64, AT_THREADS = 128, AT_MAXHD = 128;
-
-struct AttnDev {
-  const float* q; int ldq;
-  const float* k; int ldk;
-  const float* v; int ldv;
-  float* o; int ldo;
-  float* lse;
-  const float* dout; int lddo;
-  float* dq; int lddq;
-  float* dk; int lddk;
-  float* dv; int lddv;
-  const int* seq_lo;  // [nseq] first row of each sequence
-  const int* seq_len; // [nseq]
-  int heads, hd;
-  float scale;
-};
-
-__global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnDev p, int qtiles) {
-  extern __shared__ float sm[];
-  const int hd = p.hd, ldh = hd + 1;
-  float* ks = sm;                       // [AT_KC][ldh]
-  float* vs = ks + AT_KC * ldh;         // [AT_KC][ldh]
-  float* qs = vs + AT_KC * ldh;         // [AT_Q][ldh]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int bid = blockIdx.x;
-  const int qt = bid % qtiles; bid /= qtiles;
-  const int h = bid % p.heads;
-  const int seq = bid / p.heads;
-  const int lo = p.seq_lo[seq], T = p.seq_len[seq];
-  const int q0 = qt * AT_Q;
-  if (q0 >= T) return;
-  const int col = h * hd;
-  for (int i = threadIdx.x; i < AT_Q * hd; i += AT_THREADS) {
-    const int r = i / hd, d = i - r * hd;
-    qs[r * ldh + d] = (q0 + r < T) ? p.q[(size_t)(lo + q0 + r) * p.ldq + col + d] * p.scale : 0.f;
-  }
-  float m_run[4], l_run[4], acc[4][4];  // 4 queries per warp, up to 128 value columns = 4 per lane
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    m_run[a] = -INFINITY; l_run[a] = 0.f;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-  }
-  for (int k0 = 0; k0 < T; k0 += AT_KC) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < AT_KC * hd; i += AT_THREADS) {
-      const int r = i / hd, d = i - r * hd;
-      const bool ok = k0 + r < T;
-      ks[r * ldh + d] = ok ? p.k[(size_t)(lo + k0 + r) * p.ldk + col + d] : 0.f;
-      vs[r * ldh + d] = ok ? p.v[(size_t)(lo + k0 + r) * p.ldv + col + d] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int qi = warp * 4 + a;
-      if (q0 + qi >= T) continue;  // warp-uniform
-      const float* qr = qs + qi * ldh;
-      float s[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int j = lane + u * 32;
-        float d = 0.f;
-        const float* kr = ks + j * ldh;
-        for (int e = 0; e < hd; ++e) d += qr[e] * kr[e];
-        s[u] = (k0 + j < T) ? d : -INFINITY;
-      }
-      const float mx = fmaxf(m_run[a], warp_max(fmaxf(s[0], s[1])));
-      const float corr = expf(m_run[a] - mx);
-      const float p0 = expf(s[0] - mx), p1 = expf(s[1] - mx);
-      l_run[a] = l_run[a] * corr + warp_sum(p0 + p1);
-      m_run[a] = mx;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] *= corr;
-      for (int j = 0; j < AT_KC; ++j) {
-        const float pj = __shfl_sync(0xffffffffu, (j < 32) ? p0 : p1, j & 31);
-        const float* vr = vs + j * ldh;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int d = lane + b * 32;
-          if (d < hd) acc[a][b] += pj * vr[d];
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int qi = q0 + warp * 4 + a;
-    if (qi >= T) continue;
-    const float inv = 1.f / l_run[a];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int d = lane + b * 32;
-      if (d < hd) p.o[(size_t)(lo + qi) * p.ldo + col + d] = acc[a][b] * inv;
-    }
-    if (lane == 0) p.lse[(size_t)(lo + qi) * p.heads + h] = m_run[a] + logf(l_run[a]);
-  }
-}
-
-// backward, pass 1: one CTA = (sequence, head, 64 keys) accumulates dK, dV for its keys over all queries.
-// pass 2: one CTA = (sequence, head, 16 queries) accumulates dQ over all keys.  No atomics.
-// P_ij = exp(scale q_i.k_j - lse_i);  D_i = dO_i . O_i;  dV_j = sum_i P_ij dO_i;  dS_ij = P_ij (dO_i.v_j - D_i);
-// dQ_i = scale sum_j dS_ij k_j;  dK_j = scale sum_i dS_ij q_i
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const AttnDev p, int ktiles) {
-  extern __shared__ float sm[];
-  const int hd = p.hd, ldh = hd + 1;
-  float* ks = sm;                 // [64][ldh]
-  float* vs = ks + AT_KC * ldh;   // [64][ldh]
-  float* qs = vs + AT_KC * ldh;   // [AT_Q][ldh]  (scaled q)
-  float* gs = qs + AT_Q * ldh;    // [AT_Q][ldh]  dO
-  float* ps = gs + AT_Q * ldh;    // [AT_Q][64]   P
-  float* ds = ps + AT_Q * AT_KC;  // [AT_Q][64]   dS
-  float* Di = ds + AT_Q * AT_KC;  // [AT_Q]
-  int bid = blockIdx.x;
-  const int kt = bid % ktiles; bid /= ktiles;
-  const int h = bid % p.heads;
-  const int seq = bid / p.heads;
-  const int lo = p.seq_lo[seq], T = p.seq_len[seq];
-  const int k0 = kt * AT_KC;
-  if (k0 >= T) return;
-  const int col = h * hd;
-  for (int i = threadIdx.x; i < AT_KC * hd; i += AT_THREADS) {
-    const int r = i / hd, d = i - r * hd;
-    const bool ok = k0 + r < T;
-    ks[r * ldh + d] = ok ? p.k[(size_t)(lo + k0 + r) * p.ldk + col + d] : 0.f;
-    vs[r * ldh + d] = ok ? p.v[(size_t)(lo + k0 + r) * p.ldv + col + d] : 0.f;
-  }
-  // thread t owns key j = t & 63 and half of the head columns: accumulators in registers
-  // thread t owns key j = t & 63 and the head columns d = half + 2 e
-  const int j = threadIdx.x & 63, half = threadIdx.x >> 6;
-  float dk_acc[AT_MAXHD / 2], dv_acc[AT_MAXHD / 2];
-#pragma unroll
-  for (int e = 0; e < AT_MAXHD / 2; ++e) { dk_acc[e] = 0.f; dv_acc[e] = 0.f; }
-
-  for (int q0 = 0; q0 < T; q0 += AT_Q) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < AT_Q * hd; i += AT_THREADS) {
-      const int r = i / hd, d = i - r * hd;
-      const bool ok = q0 + r < T;
-      qs[r * ldh + d] = ok ? p.q[(size_t)(lo + q0 + r) * p.ldq + col + d] * p.scale : 0.f;
-      gs[r * ldh + d] = ok ? p.dout[(size_t)(lo + q0 + r) * p.lddo + col + d] : 0.f;
-    }
-    if (threadIdx.x < AT_Q) {
-      const int r = threadIdx.x;
-      float dsum = 0.f;
-      if (q0 + r < T)
-        for (int d = 0; d < hd; ++d)
-          dsum += p.dout[(size_t)(lo + q0 + r) * p.lddo + col + d] * p.o[(size_t)(lo + q0 + r) * p.ldo + col + d];
-      Di[r] = dsum;
-    }
-    __syncthreads();
-    // P and dS for (16 queries x 64 keys): 1024 entries, 8 per thread
-    for (int e = threadIdx.x; e < AT_Q * AT_KC; e += AT_THREADS) {
-      const int r = e >> 6, jj = e & 63;
-      float pv = 0.f, dsv = 0.f;
-      if (q0 + r < T && k0 + jj < T) {
-        float s = 0.f, dp = 0.f;
-        for (int d = 0; d < hd; ++d) {
-          s += qs[r * ldh + d] * ks[jj * ldh + d];
-          dp += gs[r * ldh + d] * vs[jj * ldh + d];
-        }
-        pv = expf(s - p.lse[(size_t)(lo + q0 + r) * p.heads + h]);
-        dsv = pv * (dp - Di[r]);
-      }
-      ps[e] = pv;
-      ds[e] = dsv;
-    }
-    __syncthreads();
-    for (int r = 0; r < AT_Q; ++r) {
-      const float pv = ps[r * AT_KC + j], dsv = ds[r * AT_KC + j];
-#pragma unroll
-      for (int e = 0; e < AT_MAXHD / 2; ++e) {
-        const int d = half + 2 * e;
-        if (d < hd) {
-          dv_acc[e] += pv * gs[r * ldh + d];
-          dk_acc[e] += dsv * qs[r * ldh + d];  // qs already carries the scale
-        }
-      }
-    }
-  }
-  if (k0 + j < T) {
-#pragma unroll
-    for (int e = 0; e < AT_MAXHD / 2; ++e) {
-      const int d = half + 2 * e;
-      if (d < hd) {
-        p.dk[(size_t)(lo + k0 + j) * p.lddk + col + d] = dk_acc[e];
-        p.dv[(size_t)(lo + k0 + j) * p.lddv + col + d] = dv_acc[e];
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnDev p, int qtiles) {
-  extern __shared__ float sm[];
-  const int hd = p.hd, ldh = hd + 1;
-  float* ks = sm;
-  float* vs = ks + AT_KC * ldh;
-  float* qs = vs + AT_KC * ldh;
-  float* gs = qs + AT_Q * ldh;
-  float* ds = gs + AT_Q * ldh;    // [AT_Q][64]
-  float* Di = ds + AT_Q * AT_KC;  // [AT_Q]
-  int bid = blockIdx.x;
-  const int qt = bid % qtiles; bid /= qtiles;
-  const int h = bid % p.heads;
-  const int seq = bid / p.heads;
-  const int lo = p.seq_lo[seq], T = p.seq_len[seq];
-  const int q0 = qt * AT_Q;
-  if (q0 >= T) return;
-  const int col = h * hd;
-  for (int i = threadIdx.x; i < AT_Q * hd; i += AT_THREADS) {
-    const int r = i / hd, d = i - r * hd;
-    const bool ok = q0 + r < T;
-    qs[r * ldh + d] = ok ? p.q[(size_t)(lo + q0 + r) * p.ldq + col + d] * p.scale : 0.f;
-    gs[r * ldh + d] = ok ? p.dout[(size_t)(lo + q0 + r) * p.lddo + col + d] : 0.f;
-  }
-  if (threadIdx.x < AT_Q) {
-    const int r = threadIdx.x;
-    float dsum = 0.f;
-    if (q0 + r < T)
-      for (int d = 0; d < hd; ++d)
-        dsum += p.dout[(size_t)(lo + q0 + r) * p.lddo + col + d] * p.o[(size_t)(lo + q0 + r) * p.ldo + col + d];
-    Di[r] = dsum;
-  }
-  // thread t owns query r = t & 15 and an eighth of the head columns
-  const int r_own = threadIdx.x & 15, part = threadIdx.x >> 4;  // columns d = part + 8 e
-  float dq_acc[AT_MAXHD / 8];
-#pragma unroll
-  for (int e = 0; e < AT_MAXHD / 8; ++e) dq_acc[e] = 0.f;
-  for (int k0 = 0; k0 < T; k0 += AT_KC) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < AT_KC * hd; i += AT_THREADS) {
-      const int r = i / hd, d = i - r * hd;
-      const bool ok = k0 + r < T;
-      ks[r * ldh + d] = ok ? p.k[(size_t)(lo + k0 + r) * p.ldk + col + d] : 0.f;
-      vs[r * ldh + d] = ok ? p.v[(size_t)(lo + k0 + r) * p.ldv + col + d] : 0.f;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < AT_Q * AT_KC; e += AT_THREADS) {
-      const int r = e >> 6, jj = e & 63;
-      float dsv = 0.f;
-      if (q0 + r < T && k0 + jj < T) {
-        float s = 0.f, dp = 0.f;
-        for (int d = 0; d < hd; ++d) {
-          s += qs[r * ldh + d] * ks[jj * ldh + d];
-          dp += gs[r * ldh + d] * vs[jj * ldh + d];
-        }
-        dsv = expf(s - p.lse[(size_t)(lo + q0 + r) * p.heads + h]) * (dp - Di[r]);
-      }
-      ds[e] = dsv;
-    }
-    __syncthreads();
-    for (int jj = 0; jj < AT_KC; ++jj) {
-      const float dsv = ds[r_own * AT_KC + jj];
-#pragma unroll
-      for (int e = 0; e < AT_MAXHD / 8; ++e) {
-        const int d = part + 8 * e;
-        if (d < hd) dq_acc[e] += dsv * ks[jj * ldh + d];
-      }
-    }
-  }
-  if (q0 + r_own < T) {
-#pragma unroll
-    for (int e = 0; e < AT_MAXHD / 8; ++e) {
-      const int d = part + 8 * e;
-      if (d < hd) p.dq[(size_t)(lo + q0 + r_own) * p.lddq + col + d] = dq_acc[e] * p.scale;
-    }
   }
 }
 
@@ -471,49 +198,6 @@ extern "C" int tcn_layernorm_bwd(const float* x, int ldx, const float* dy, int l
       x, ldx, dy, lddy, dx, lddx, gamma, mean, rstd, dgamma, dbeta, reinterpret_cast<const BlkMeta*>(meta), nrows,
       channels);
   return check_launch("layernorm_bwd_kernel");
-}
-
-static int attn_common(const tcn_attn_args* a, AttnDev* p) {
-  TCN_REQUIRE(a && a->q && a->k && a->v && a->o && a->lse && a->seq_lo && a->seq_len, "tcn_attn: null pointer");
-  TCN_REQUIRE(a->nseq > 0 && a->heads > 0 && a->head_dim > 0 && a->max_len > 0, "tcn_attn: bad shape");
-  if (a->head_dim > AT_MAXHD) {
-    set_error("tcn_attn: head_dim %d > %d is not supported", a->head_dim, AT_MAXHD);
-    return TCN_ERR_UNSUPPORTED;
-  }
-  p->q = a->q; p->ldq = a->ldq; p->k = a->k; p->ldk = a->ldk; p->v = a->v; p->ldv = a->ldv; p->o = a->o; p->ldo = a->ldo;
-  p->lse = a->lse; p->dout = a->dout; p->lddo = a->lddo; p->dq = a->dq; p->lddq = a->lddq; p->dk = a->dk;
-  p->lddk = a->lddk; p->dv = a->dv; p->lddv = a->lddv; p->seq_lo = a->seq_lo; p->seq_len = a->seq_len;
-  p->heads = a->heads; p->hd = a->head_dim; p->scale = a->scale;
-  return TCN_OK;
-}
-
-extern "C" int tcn_attn_fwd(const tcn_attn_args* a, tcn_stream_t stream) {
-  AttnDev p;
-  TCN_CHECK(attn_common(a, &p));
-  const int qtiles = (a->max_len + AT_Q - 1) / AT_Q;
-  const int ldh = a->head_dim + 1;
-  const size_t smem = (size_t)(2 * AT_KC + AT_Q) * ldh * sizeof(float);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  attn_fwd_kernel<<<a->nseq * a->heads * qtiles, AT_THREADS, smem, (cudaStream_t)stream>>>(p, qtiles);
-  return check_launch("attn_fwd_kernel");
-}
-
-extern "C" int tcn_attn_bwd(const tcn_attn_args* a, tcn_stream_t stream) {
-  AttnDev p;
-  TCN_CHECK(attn_common(a, &p));
-  TCN_REQUIRE(a->dout && a->dq && a->dk && a->dv, "tcn_attn_bwd: null gradient pointer");
-  const int qtiles = (a->max_len + AT_Q - 1) / AT_Q, ktiles = (a->max_len + AT_KC - 1) / AT_KC;
-  const int ldh = a->head_dim + 1;
-  const size_t smem_kv = (size_t)((2 * AT_KC + 2 * AT_Q) * ldh + 2 * AT_Q * AT_KC + AT_Q) * sizeof(float);
-  const size_t smem_q = (size_t)((2 * AT_KC + 2 * AT_Q) * ldh + AT_Q * AT_KC + AT_Q) * sizeof(float);
-  if (smem_kv > 48 * 1024) {
-    cudaFuncSetAttribute(attn_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv);
-    cudaFuncSetAttribute(attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q);
-  }
-  attn_bwd_kv_kernel<<<a->nseq * a->heads * ktiles, AT_THREADS, smem_kv, (cudaStream_t)stream>>>(p, ktiles);
-  TCN_CHECK(check_launch("attn_bwd_kv_kernel"));
-  attn_bwd_q_kernel<<<a->nseq * a->heads * qtiles, AT_THREADS, smem_q, (cudaStream_t)stream>>>(p, qtiles);
-  return check_launch("attn_bwd_q_kernel");
 }
 
 extern "C" int tcn_dwconv_gelu_fwd(const float* x, float* y, const float* w, const float* b, const int* meta, int nrows,

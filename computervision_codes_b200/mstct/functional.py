@@ -50,7 +50,7 @@ def layer_norm(x, weight, bias, lay: SeqLayout, eps=1e-5):
     return LayerNormFn.apply(x, weight, bias, lay, eps)
 
 
-def _attn_args(q, kv, o, lse, lay, heads, dout=None, dq=None, dkv=None):
+def _attn_args(q, kv, o, lse, lay, heads, dout=None, dq=None, dkv=None, delta=None):
     d = q.shape[1]
     hd = d // heads
     a = _lib.AttnArgs()
@@ -63,6 +63,7 @@ def _attn_args(q, kv, o, lse, lay, heads, dout=None, dq=None, dkv=None):
         a.dq, a.lddq = _lib.ptr(dq), d
         a.dk, a.lddk = dkv.data_ptr(), 2 * d
         a.dv, a.lddv = dkv.data_ptr() + d * 4, 2 * d
+        a.delta = _lib.ptr(delta)
     a.seq_lo, a.seq_len, a.nseq, a.max_len = _lib.ptr(lay.seq_lo), _lib.ptr(lay.seq_len), lay.num_seqs, lay.max_len
     a.heads, a.head_dim, a.scale = heads, hd, float(hd) ** -0.5
     return a
@@ -89,7 +90,8 @@ class AttentionFn(torch.autograd.Function):
         q, kv, o, lse = ctx.saved_tensors
         go = _c(go)
         dq, dkv = torch.zeros_like(q), torch.zeros_like(kv)
-        a = _attn_args(q, kv, o, lse, ctx.lay, ctx.heads, go, dq, dkv)
+        delta = torch.empty_like(lse)
+        a = _attn_args(q, kv, o, lse, ctx.lay, ctx.heads, go, dq, dkv, delta)
         _lib.check(lib.tcn_attn_bwd(C.byref(a), _lib.stream_ptr()), "tcn_attn_bwd")
         return dq, dkv, None, None
 

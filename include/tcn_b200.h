@@ -238,13 +238,15 @@ int tcn_layernorm_bwd(const float* x, int ldx, const float* dy, int lddy, float*
                       int channels, tcn_stream_t stream);
 /* Global_Relational_Block attention (:76-88): per (sequence, head) o = softmax(scale q k^T) v over the frames of
  * the sequence; head h lives at columns [h*head_dim, (h+1)*head_dim) of q / k / v / o (pass k and v already offset
- * into the kv projection).  lse: (rows, heads) log-sum-exp saved for the backward (two passes, no atomics). */
+ * into the kv projection).  lse: (rows, heads) log-sum-exp saved for the backward (two passes, no atomics).  All products run as
+ * 3xTF32 mma.sync tiles (csrc/attention.cu). */
 typedef struct {
   const float* q; int ldq; const float* k; int ldk; const float* v; int ldv;
   float* o; int ldo; float* lse;
   const float* dout; int lddo; float* dq; int lddq; float* dk; int lddk; float* dv; int lddv;
   const int* seq_lo; const int* seq_len; int nseq; int max_len;
   int heads; int head_dim; float scale;
+  float* delta; /* backward scratch, (rows, heads): dO_i . O_i */
 } tcn_attn_args;
 int tcn_attn_fwd(const tcn_attn_args* args, tcn_stream_t stream);
 int tcn_attn_bwd(const tcn_attn_args* args, tcn_stream_t stream);

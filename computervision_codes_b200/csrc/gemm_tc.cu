@@ -528,6 +528,239 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
 
 
 // ------------------------------------------------------------------------------------------------
+// Wide persistent variant for the dense per-frame contractions with many output columns (the MS-TCT Linear layers:
+// qkv / proj / fc1 / fc2 and their input gradients).  One CTA per SM walks over (frame tile, BN-column tile) pairs;
+// the 128 x 32 activation tile is split ONCE per BN = 128 / 256 output columns (vs. once per 64 in the streaming
+// kernel, which made the split warps the bottleneck), X and the pre-split weights stream through one ring, the
+// accumulator is double-buffered in TMEM (2 x BN columns) and four epilogue warps drain tile i while tile i + 1 is
+// being multiplied.  Tile order: frame tile fastest, so that the CTAs running at the same time share a weight tile
+// through L2.
+template <int BN>
+struct TwSmem {
+  static constexpr int kStages = BN > 128 ? 2 : 3;
+  static constexpr int kA = TC_BM * TC_BK * 4;  // 16384
+  static constexpr int kB = BN * TC_BK * 4;
+  static constexpr int kStage = 2 * kA + 2 * kB;
+  static constexpr int kBytes = kStages * kStage + TP_EPI + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TP_THREADS, 1)
+gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
+                    const __grid_constant__ CUtensorMap map_wlo, const GemmTcDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  using S = TwSmem<BN>;
+  constexpr int NST = S::kStages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nblk = p.dyn ? p.dyn->nblk : p.nblk;
+  const int kblocks = p.ntaps * p.kbp;
+  const int nty = (p.N + BN - 1) / BN;
+  const int ntiles = nblk * nty;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
+  float4* epi = reinterpret_cast<float4*>(tiles + NST * S::kStage);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + NST * S::kStage + TP_EPI);
+  uint64_t* full_bar = bars;
+  uint64_t* ready_bar = full_bar + NST;
+  uint64_t* empty_bar = ready_bar + NST;
+  uint64_t* tfull = empty_bar + NST;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&ready_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)(2 * BN)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t dseed = p.dyn ? p.dyn->seed : 0u;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int blk = tile % nblk, ntile = tile / nblk;
+        const BlkMeta m = p.meta[blk];
+        const int row0 = blk * kBlkRows;
+        if (row0 >= m.hi) continue;
+        const int xrow = row0 + (p.x_unpadded ? m.in_delta : 0);
+        int tap = 0, kc = 0;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % NST;
+          const uint32_t ph = (it / NST) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = tiles + s * S::kStage;
+          mbar_arrive_expect_tx(&full_bar[s], S::kA + 2 * S::kB);
+          const int sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
+          tma_load_2d(st, &map_x, &full_bar[s], kc * TC_BK, xrow + sh);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) {  // weight maps have 64-row boxes; rows past the end are zero filled
+            tma_load_2d(st + 2 * S::kA + j * TP_KB, &map_whi, &full_bar[s], kb * TC_BK, ntile * BN + j * 64);
+            tma_load_2d(st + 2 * S::kA + S::kB + j * TP_KB, &map_wlo, &full_bar[s], kb * TC_BK, ntile * BN + j * 64);
+          }
+          if (++kc == p.kbp) { kc = 0; ++tap; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
+    int it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int blk = tile % nblk;
+      const BlkMeta m = p.meta[blk];
+      if (blk * kBlkRows >= m.hi) continue;
+      const int a = tcount & 1;
+      const uint32_t tph = (tcount >> 1) & 1;
+      mbar_wait(&tempty[a], tph ^ 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + a * BN;
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const int s = it % NST;
+        const uint32_t ph = (it / NST) & 1;
+        mbar_wait(&ready_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = base + s * S::kStage, a_lo = a_hi + S::kA;
+          const uint32_t b_hi = a_hi + 2 * S::kA, b_lo = b_hi + S::kB;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint32_t ko = k * 32;
+            const uint64_t dah = umma_desc_sw128(a_hi + ko), dal = umma_desc_sw128(a_lo + ko);
+            const uint64_t dbh = umma_desc_sw128(b_hi + ko), dbl = umma_desc_sw128(b_lo + ko);
+            umma_tf32(tacc, dal, dbh, idesc, (kb | k) != 0);
+            umma_tf32(tacc, dah, dbl, idesc, 1u);
+            umma_tf32(tacc, dah, dbh, idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (kb == kblocks - 1) umma_commit(&tfull[a]);
+        }
+        __syncwarp();
+      }
+      ++tcount;
+    }
+  } else if (warp < 6) {
+    // ===================== operand split (warps 2..5) =====================
+    const int ct = threadIdx.x - 64;
+    const uint32_t in_seed = p.in_drop_seed ^ dseed;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int blk = tile % nblk;
+      const BlkMeta m = p.meta[blk];
+      const int row0 = blk * kBlkRows;
+      if (row0 >= m.hi) continue;
+      int tap = 0, kc = 0;
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const int s = it % NST;
+        const uint32_t ph = (it / NST) & 1;
+        const int sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
+        mbar_wait(&full_bar[s], ph);
+        split_tile(reinterpret_cast<float4*>(tiles + s * S::kStage),
+                   reinterpret_cast<float4*>(tiles + s * S::kStage + S::kA), ct, row0, sh, m, kc, p, in_seed);
+        fence_proxy_async();
+        mbar_arrive(&ready_bar[s]);
+        if (++kc == p.kbp) { kc = 0; ++tap; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 6..9; TMEM lane quadrant = warp % 4) =====================
+    const int q = warp & 3;
+    const uint32_t out_seed = p.drop_seed ^ dseed;
+    const bool vec_ok = ((p.ldy & 3) == 0) && (p.R == nullptr || (p.ldr & 3) == 0) && (p.M == nullptr || (p.ldm & 3) == 0);
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int blk = tile % nblk, ntile = tile / nblk;
+      const BlkMeta m = p.meta[blk];
+      const int row0 = blk * kBlkRows;
+      if (row0 >= m.hi) continue;
+      const int a = tcount & 1;
+      const uint32_t tph = (tcount >> 1) & 1;
+      mbar_wait(&tfull[a], tph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 64) {
+        float v0[32], v1[32];
+        tmem_ld32(taddr + c0, v0);
+        tmem_ld32(taddr + c0 + 32, v1);
+        if (c0 + 64 >= BN) {  // last read of this accumulator: hand it back before the stores
+          tc_fence_before();
+          mbar_arrive(&tempty[a]);
+        }
+        if (ntile * BN + c0 < p.N)
+          epilogue_block_coalesced(v0, v1, epi + (warp - 6) * 512, lane, row0 + q * 32, m.hi, ntile * BN + c0, p,
+                                   out_seed, vec_ok);
+      }
+      ++tcount;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)));
+}
+
+template <int BN>
+static int launch_wide(const CUtensorMap& mx, const CUtensorMap& mwhi, const CUtensorMap& mwlo, const GemmTcDev& p, int nb,
+                       cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e = cudaFuncSetAttribute(gemm_tc_wide_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               TwSmem<BN>::kBytes);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc_wide: smem attribute: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return TCN_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const long tiles = (long)nb * ((p.N + BN - 1) / BN);
+  const int gx = (int)(tiles < num_sms() ? tiles : num_sms());
+  launch_kernel(gemm_tc_wide_kernel<BN>, dim3(gx), dim3(TP_THREADS), TwSmem<BN>::kBytes, stream, true, mx, mwhi, mwlo, p);
+  return check_launch("gemm_tc_wide_kernel");
+}
+
+// 0: not the wide kernel; else the column-tile width.  Cost model: waves of tiles x (MMA time ~ BN, plus a fixed
+// split / pipeline-fill share).
+static int wide_bn(const GemmTcDev& p, int nb) {
+  static int forced = -2;
+  if (forced == -2) {
+    const char* e = getenv("TCN_WIDE_BN");
+    forced = e ? atoi(e) : -1;
+  }
+  if (forced >= 0) return (forced == 128 || forced == 256) && p.N > 64 ? forced : 0;
+  if (p.N < 128 || p.ntaps * p.kbp < 4) return 0;
+  const int sms = num_sms();
+  long best = -1;
+  int best_bn = 0;
+  for (int bn = 128; bn <= 256; bn += 128) {
+    const long tiles = (long)nb * ((p.N + bn - 1) / bn);
+    const long cost = ((tiles + sms - 1) / sms) * (bn + 48);
+    if (best < 0 || cost < best) { best = cost; best_bn = bn; }
+  }
+  return best_bn;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Slab variant of the persistent kernel for the k = 3 dilated convolutions with a small dilation
 // (max shift - min shift <= 64 frames, 64 input channels).  tcgen05 shared-memory descriptors may start at ANY row
 // of a TMA-swizzled tile (the 128B swizzle is a function of the absolute shared-memory address; verified on
@@ -858,6 +1091,9 @@ int launch_gemm_tc(const CUtensorMap& mx, const CUtensorMap& mwhi, const CUtenso
     if (gx > nb) gx = nb;
     launch_kernel(gemm_tc_slab_kernel, dim3(gx, nty), dim3(TP_THREADS), sl_smem_bytes(), stream, true, *mx32, mwhi, mwlo, p);
     return check_launch("gemm_tc_slab_kernel");
+  }
+  if (const int bn = wide_bn(p, nb)) {
+    return bn == 256 ? launch_wide<256>(mx, mwhi, mwlo, p, nb, stream) : launch_wide<128>(mx, mwhi, mwlo, p, nb, stream);
   }
   if (kblocks <= TP_MAX_KB) {  // persistent, weights resident in shared memory
     static int max_set = 0;

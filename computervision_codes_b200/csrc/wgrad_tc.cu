@@ -15,16 +15,25 @@
 // and adds its partial to dW once, at the end (fp32 atomics).  The dropout mask of the layer (gv = keep * gy /
 // (1 - p)), Dropout2d's channel scale and the input mask of the projection are folded into the operand split.
 //   warp 0: TMA producer | warp 1: MMA issuer + TMEM owner | warps 2-5: operand split, bias sums, epilogue
+#include <cstdlib>
+
 #include "gemm_tc.cuh"
 
 namespace tcn {
 
 constexpr int WG_RC = 32;                      // frames per pipeline stage
 constexpr int WG_ATOM = WG_RC * 128;           // 4096 B: 32 frames x 32 fp32 columns
-constexpr int WG_RAW = 6 * WG_ATOM;            // 4 X blocks + 2 G blocks
-constexpr int WG_STAGE = 2 * WG_RAW;           // raw / hi + lo
-constexpr int WG_STAGES = 4;
-constexpr int WG_SMEM = WG_STAGES * WG_STAGE + 1024 + 512;
+// NGA = 32-column G blocks per tile (output-channel tile = 32 NGA): 2 for the 64-channel layers of the TCN, 4 for the
+// wide Linear layers of MS-TCT, where a 128 x 128 tile cuts the shared-memory operand traffic per MAC by a third and
+// splits every X block once per 128 output channels instead of once per 64 (8 = 128 x 256 is kept behind
+// TCN_WGRAD_NGA=8: with only two stages fitting it measured slower).
+template <int NGA>
+struct WgSmem {
+  static constexpr int kRaw = (4 + NGA) * WG_ATOM;   // 4 X blocks + NGA G blocks
+  static constexpr int kStage = 2 * kRaw;            // raw / hi + lo
+  static constexpr int kStages = NGA <= 2 ? 4 : (NGA <= 4 ? 3 : 2);
+  static constexpr int kBytes = kStages * kStage + 1024 + 512 + NGA * 32 * 4;
+};
 
 #if 0
 struct WgradTcDev {
@@ -66,9 +75,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int M, int N) {
          ((uint32_t)(M >> 4) << 24);
 }
 
+template <int NGA>
 __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const CUtensorMap* map_gp, const WgradTcDev& p,
                                               const int split, const int mtile, const int ntile) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr int WG_RAW = WgSmem<NGA>::kRaw, WG_STAGE = WgSmem<NGA>::kStage, WG_STAGES = WgSmem<NGA>::kStages;
+  constexpr int NCH = (4 + NGA) * 2;   // 16-byte chunks per split thread and stage
+  constexpr int NCOL = NGA * 32;       // output channels per tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = p.dyn ? p.dyn->nblk : p.nblk;
   const uint32_t dseed = p.dyn ? p.dyn->seed : 0u;
@@ -84,7 +97,7 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
   uint64_t* empty_bar = bars + 2 * WG_STAGES;
   uint64_t* accum_bar = bars + 3 * WG_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * WG_STAGES + 1);
-  float* bias_red = reinterpret_cast<float*>(bars + 3 * WG_STAGES + 2);  // 64 floats
+  float* bias_red = reinterpret_cast<float*>(bars + 3 * WG_STAGES + 2);  // NCOL floats
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < WG_STAGES; ++s) {
@@ -95,10 +108,10 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (threadIdx.x < 64) bias_red[threadIdx.x] = 0.f;
+  for (int i = threadIdx.x; i < NCOL; i += blockDim.x) bias_red[i] = 0.f;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
-                 "r"(64u));
+                 "r"((uint32_t)NCOL));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
   }
   tc_fence_before();
@@ -146,15 +159,16 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
               const int sh = a_tap[j] == 0 ? p.shift[0] : (a_tap[j] == 1 ? p.shift[1] : p.shift[2]);
               tma_load_2d(st + j * WG_ATOM, map_xp, &full_bar[s], a_cb[j] * 32, r0 + dz + sh);
             }
-            tma_load_2d(st + 4 * WG_ATOM, map_gp, &full_bar[s], (ntile * 2) * 32, r0);
-            tma_load_2d(st + 5 * WG_ATOM, map_gp, &full_bar[s], (ntile * 2 + 1) * 32, r0);
+#pragma unroll
+            for (int j = 0; j < NGA; ++j)  // column blocks past the end of G are zero filled
+              tma_load_2d(st + (4 + j) * WG_ATOM, map_gp, &full_bar[s], (ntile * NGA + j) * 32, r0);
             ++it;
           }
         }
       }
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = umma_idesc_tf32_mn(128, 64);
+      constexpr uint32_t idesc = umma_idesc_tf32_mn(128, NCOL);
       for (int it = 0; it < total_chunks; ++it) {
         const int s = it % WG_STAGES;
         const uint32_t ph = (it / WG_STAGES) & 1;
@@ -184,7 +198,9 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
       // every 16-byte chunk this thread touches has the same position inside its 32 x 32 block up to a row offset:
       const int lc = ((((ct & 7) >> 1) ^ ((ct >> 3) & 3)) << 1) | (ct & 1);  // logical 16-byte column chunk (swizzle undone)
       const bool extras = p.colscale != nullptr || p.x_drop_thresh != 0u || p.g_drop_thresh != 0u;
-      float4 bsum[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+      float4 bsum[NGA];
+#pragma unroll
+      for (int a = 0; a < NGA; ++a) bsum[a] = make_float4(0.f, 0.f, 0.f, 0.f);
       int it = 0;
       for (int blk = blk_begin; blk < blk_end; ++blk) {
         const BlkMeta m = p.meta[blk];
@@ -196,11 +212,11 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
           mbar_wait(&full_bar[s], ph);
           float4* raw = reinterpret_cast<float4*>(tiles + s * WG_STAGE);
           float4* lo = reinterpret_cast<float4*>(tiles + s * WG_STAGE + WG_RAW);
-          float4 v[12];
+          float4 v[NCH];
 #pragma unroll
-          for (int i = 0; i < 12; ++i) v[i] = raw[ct + i * 128];
+          for (int i = 0; i < NCH; ++i) v[i] = raw[ct + i * 128];
 #pragma unroll
-          for (int i = 0; i < 12; ++i) {
+          for (int i = 0; i < NCH; ++i) {
             const int atom = i >> 1;                    // chunk ct + i*128 lies in block i/2 ...
             const int r = (ct >> 3) + (i & 1) * 16;     // ... at frame r of the chunk
             int src = r0 + r;
@@ -221,7 +237,7 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
                   v[i].w *= drop_factor(x_seed, p.x_drop_stream, p.x_drop_thresh, p.x_drop_scale, src, col + 3);
                 }
               } else if (p.g_drop_thresh != 0u) {
-                const int col = (ntile * 2 + (atom - 4)) * 32 + lc * 4;
+                const int col = (ntile * NGA + (atom - 4)) * 32 + lc * 4;
                 v[i].x *= drop_factor(g_seed, p.g_drop_stream, p.g_drop_thresh, p.g_drop_scale, src, col);
                 v[i].y *= drop_factor(g_seed, p.g_drop_stream, p.g_drop_thresh, p.g_drop_scale, src, col + 1);
                 v[i].z *= drop_factor(g_seed, p.g_drop_stream, p.g_drop_thresh, p.g_drop_scale, src, col + 2);
@@ -230,12 +246,12 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
             }
           }
 #pragma unroll
-          for (int i = 8; i < 12; ++i) {  // G blocks: column sums for the bias gradient
+          for (int i = 8; i < NCH; ++i) {  // G blocks: column sums for the bias gradient
             bsum[(i - 8) >> 1].x += v[i].x; bsum[(i - 8) >> 1].y += v[i].y;
             bsum[(i - 8) >> 1].z += v[i].z; bsum[(i - 8) >> 1].w += v[i].w;
           }
 #pragma unroll
-          for (int i = 0; i < 12; ++i) {
+          for (int i = 0; i < NCH; ++i) {
             float4 h, l;
             h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xffffe000u); l.x = v[i].x - h.x;
             h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u); l.y = v[i].y - h.y;
@@ -252,16 +268,16 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
       // ---- bias gradient: reduce the per-thread column sums (shared atomics), one global add per column
       if (p.db != nullptr && mtile == 0) {
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < NGA; ++a) {
           atomicAdd(&bias_red[a * 32 + lc * 4 + 0], bsum[a].x);
           atomicAdd(&bias_red[a * 32 + lc * 4 + 1], bsum[a].y);
           atomicAdd(&bias_red[a * 32 + lc * 4 + 2], bsum[a].z);
           atomicAdd(&bias_red[a * 32 + lc * 4 + 3], bsum[a].w);
         }
         asm volatile("bar.sync 1, 128;\n" ::: "memory");  // the four split warps only
-        if (ct < 64) {
-          const int n = ntile * 64 + ct;
-          if (n < p.n_out) atomicAdd(p.db + n, bias_red[ct]);
+        for (int i = ct; i < NCOL; i += 128) {
+          const int n = ntile * NCOL + i;
+          if (n < p.n_out) atomicAdd(p.db + n, bias_red[i]);
         }
       }
       // ===================== epilogue: add the partial into dW =====================
@@ -273,13 +289,14 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
       const int c = a_cb[q] * 32 + lane;
       const bool row_ok = (vblk < nv) && (c < p.c_in);
 #pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 32) {
+      for (int c0 = 0; c0 < NCOL; c0 += 32) {
+        if (ntile * NCOL + c0 >= p.n_out) break;  // warp-uniform
         float v[32];
         tmem_ld32(taddr + c0, v);
         if (row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int n = ntile * 64 + c0 + j;
+            const int n = ntile * NCOL + c0 + j;
             if (n < p.n_out) atomicAdd(p.dW + ((size_t)n * p.c_in + c) * p.ntaps + a_tap[q], v[j]);
           }
         }
@@ -288,13 +305,15 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(64u));
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)NCOL));
 }
 
+template <int NGA>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
                 const WgradTcDev p) {
-  wgrad_tc_body(&map_x, &map_g, p, blockIdx.x, blockIdx.y, blockIdx.z);
+  wgrad_tc_body<NGA>(&map_x, &map_g, p, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 // two independent problems in one launch (the two weight gradients of a residual layer): blockIdx.y < mt0 -> problem 0
@@ -303,15 +322,17 @@ wgrad_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_co
                      const WgradTcDev p0, const __grid_constant__ CUtensorMap map_x1,
                      const __grid_constant__ CUtensorMap map_g1, const WgradTcDev p1, int mt0) {
   if ((int)blockIdx.y < mt0)
-    wgrad_tc_body(&map_x0, &map_g0, p0, blockIdx.x, blockIdx.y, 0);
+    wgrad_tc_body<2>(&map_x0, &map_g0, p0, blockIdx.x, blockIdx.y, 0);
   else
-    wgrad_tc_body(&map_x1, &map_g1, p1, blockIdx.x, blockIdx.y - mt0, 0);
+    wgrad_tc_body<2>(&map_x1, &map_g1, p1, blockIdx.x, blockIdx.y - mt0, 0);
 }
 
-int launch_wgrad_tc(const CUtensorMap& mx, const CUtensorMap& mg, WgradTcDev& p, int cap_nblk, cudaStream_t stream) {
+template <int NGA>
+static int launch_wgrad_tc_n(const CUtensorMap& mx, const CUtensorMap& mg, WgradTcDev& p, int nb, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    const cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    const cudaError_t e =
+        cudaFuncSetAttribute(wgrad_tc_kernel<NGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<NGA>::kBytes);
     if (e != cudaSuccess) {
       set_error("wgrad_tc: smem attribute: %s", cudaGetErrorString(e));
       cudaGetLastError();
@@ -319,15 +340,44 @@ int launch_wgrad_tc(const CUtensorMap& mx, const CUtensorMap& mg, WgradTcDev& p,
     }
     attr_set = true;
   }
-  p.cbn = (p.c_in + 31) / 32;
-  const int mt = (p.ntaps * p.cbn + 3) / 4, nt = (p.n_out + 63) / 64;
-  const int nb = cap_nblk > 0 ? cap_nblk : p.nblk;
-  int rs = num_sms() / (mt * nt);
+  const int mt = (p.ntaps * p.cbn + 3) / 4, nt = (p.n_out + NGA * 32 - 1) / (NGA * 32);
+  const int sms = num_sms();
+  int rs;
+  if (mt * nt <= sms) {
+    rs = sms / (mt * nt);
+  } else {  // more tiles than SMs: split the rows so that the last wave is (nearly) full
+    rs = 1;
+    double best = 0.0;
+    for (int r = 1; r <= 6; ++r) {
+      const long units = (long)mt * nt * r;
+      const double eff = (double)units / (double)(((units + sms - 1) / sms) * sms);
+      if (eff > best + 0.03) { best = eff; rs = r; }
+    }
+  }
   if (rs < 1) rs = 1;
   if (rs > nb) rs = nb;
   p.row_splits = rs;
-  launch_kernel(wgrad_tc_kernel, dim3(rs, mt, nt), dim3(TC_THREADS), WG_SMEM, stream, true, mx, mg, p);
+  launch_kernel(wgrad_tc_kernel<NGA>, dim3(rs, mt, nt), dim3(TC_THREADS), WgSmem<NGA>::kBytes, stream, true, mx, mg, p);
   return check_launch("wgrad_tc_kernel");
+}
+
+int launch_wgrad_tc(const CUtensorMap& mx, const CUtensorMap& mg, WgradTcDev& p, int cap_nblk, cudaStream_t stream) {
+  p.cbn = (p.c_in + 31) / 32;
+  const int nb = cap_nblk > 0 ? cap_nblk : p.nblk;
+  static int forced = -2;
+  if (forced == -2) {
+    const char* e = getenv("TCN_WGRAD_NGA");
+    forced = e ? atoi(e) : -1;
+  }
+  int nga = 2;
+  if (forced == 2 || forced == 4 || forced == 8) {
+    nga = forced;
+  } else if (p.n_out >= 128 && p.ntaps * p.cbn >= 4) {
+    nga = 4;  // measured (tools/gemm_shapes_bench.py): 128 x 128 tiles with 3 stages beat 128 x 256 with 2
+  }
+  if (nga == 8) return launch_wgrad_tc_n<8>(mx, mg, p, nb, stream);
+  if (nga == 4) return launch_wgrad_tc_n<4>(mx, mg, p, nb, stream);
+  return launch_wgrad_tc_n<2>(mx, mg, p, nb, stream);
 }
 
 int launch_wgrad_tc_pair(const CUtensorMap& mx0, const CUtensorMap& mg0, WgradTcDev& p0, const CUtensorMap& mx1,
@@ -335,7 +385,7 @@ int launch_wgrad_tc_pair(const CUtensorMap& mx0, const CUtensorMap& mg0, WgradTc
   static bool attr_set = false;
   if (!attr_set) {
     const cudaError_t e =
-        cudaFuncSetAttribute(wgrad_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+        cudaFuncSetAttribute(wgrad_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<2>::kBytes);
     if (e != cudaSuccess) {
       set_error("wgrad_tc_pair: smem attribute: %s", cudaGetErrorString(e));
       cudaGetLastError();
@@ -356,7 +406,7 @@ int launch_wgrad_tc_pair(const CUtensorMap& mx0, const CUtensorMap& mg0, WgradTc
   if (rs > nb) rs = nb;
   p0.row_splits = rs;
   p1.row_splits = rs;
-  launch_kernel(wgrad_tc_pair_kernel, dim3(rs, mt0 + mt1, 1), dim3(TC_THREADS), WG_SMEM, stream, true, mx0, mg0, p0, mx1,
+  launch_kernel(wgrad_tc_pair_kernel, dim3(rs, mt0 + mt1, 1), dim3(TC_THREADS), WgSmem<2>::kBytes, stream, true, mx0, mg0, p0, mx1,
                 mg1, p1, mt0);
   return check_launch("wgrad_tc_pair_kernel");
 }

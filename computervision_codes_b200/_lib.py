@@ -171,6 +171,7 @@ SIGNATURES = {
                                     C.c_uint, C.c_uint, C.c_void_p]),
     "tcn_dropout_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_uint, C.c_uint, C.c_void_p]),
     "tcn_sgd_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "tcn_sgd_step_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -214,6 +214,17 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, l
   }
 }
 
+// same update with the hyper-parameters in device memory {lr, weight_decay, grad_scale}: a captured CUDA graph then
+// follows the learning-rate schedule (LinearLR warm-up + ExponentialLR, run.py:345-350) without re-capture
+__global__ void sgd_dev_kernel(float* __restrict__ p, const float* __restrict__ g, long n,
+                               const float* __restrict__ hyper) {
+  const float lr = hyper[0], wd = hyper[1], grad_scale = hyper[2];
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float w = p[i];
+    p[i] = w - lr * (g[i] * grad_scale + wd * w);
+  }
+}
+
 int launch_bce(const BceDev& p, int cap_rows, cudaStream_t stream) {
   const long rows = cap_rows > 0 ? cap_rows : p.nrows;
   long b = (rows + 7) / 8;
@@ -320,4 +331,11 @@ extern "C" int tcn_sgd_step(float* params, const float* grads, long long n, floa
   sgd_kernel<<<grid_for(n, 1024, num_sms() * 4), 256, 0, (cudaStream_t)stream>>>(params, grads, (long)n, lr,
                                                                                 weight_decay, grad_scale);
   return check_launch("sgd_kernel");
+}
+
+extern "C" int tcn_sgd_step_dev(float* params, const float* grads, long long n, const float* hyper,
+                                tcn_stream_t stream) {
+  TCN_REQUIRE(params && grads && hyper && n > 0, "tcn_sgd_step_dev: bad arguments");
+  sgd_dev_kernel<<<grid_for(n, 1024, num_sms() * 4), 256, 0, (cudaStream_t)stream>>>(params, grads, (long)n, hyper);
+  return check_launch("sgd_dev_kernel");
 }

@@ -179,6 +179,14 @@ def sgd_step(params_flat, grads_flat, lr, weight_decay=0.0, grad_scale=1.0):
                                 float(weight_decay), float(grad_scale), _lib.stream_ptr()), "tcn_sgd_step")
 
 
+def sgd_step_dev(params_flat, grads_flat, hyper):
+    """SGD step with hyper = device tensor (lr, weight_decay, grad_scale): graph-capturable under an LR schedule."""
+    lib = _lib.load()
+    assert hyper.is_cuda and hyper.dtype == torch.float32 and hyper.numel() >= 3
+    _lib.check(lib.tcn_sgd_step_dev(_lib.ptr(params_flat), _lib.ptr(grads_flat), params_flat.numel(), _lib.ptr(hyper),
+                                    _lib.stream_ptr()), "tcn_sgd_step_dev")
+
+
 def tap_shifts(dilation: int, causal: bool):
     d = int(dilation)
     return (-2 * d, -d, 0) if causal else (-d, 0, d)

@@ -61,11 +61,9 @@ class TemporalTrainerEager:
 
     def step(self, x_rows, labels_u8, lengths):
         out = self.forward_backward(x_rows, labels_u8, lengths)
-        scale = 1.0
         if self.world > 1:
             torch.distributed.all_reduce(self.flat_g, group=self.pg)
-            scale = 1.0 / self.world
-        ops.sgd_step(self.flat_p, self.flat_g, self.lr, self.weight_decay, grad_scale=scale)
+        ops.sgd_step(self.flat_p, self.flat_g, self.lr, self.weight_decay, grad_scale=1.0 / max(1, self.world))
         return out
 
 
@@ -124,14 +122,26 @@ class TemporalTrainer:
         self._outs = [None, None]
         self.rng = torch.Generator().manual_seed(seed)
         self.training = True
+        # {lr, weight_decay, grad_scale} live on the device: the captured graph follows set_lr() / an LR schedule
+        self._hyper_host = torch.tensor([lr, weight_decay, 1.0 / max(1, world_size)], dtype=torch.float32).pin_memory()
+        self.hyper = self._hyper_host.to(dev)
+
+    def set_lr(self, lr: float):
+        """New learning rate for the following steps (stream-ordered H2D of 4 bytes; no graph re-capture)."""
+        self.lr = float(lr)
+        self._hyper_host[0] = self.lr
+        self.hyper.copy_(self._hyper_host, non_blocking=True)
+
+    def step_cached(self, cache, items):
+        """One step on clips / videos of a ``data.FeatureCache``: items = [(video, start, length), ...]."""
+        xs, ls, lens = cache.batch(items)
+        return self.step(xs, ls, lens)
 
     def _body(self, slot):
         out = self.ex.train_step(self.x_slots[slot], self.lab_slots[slot], training=self.training)
-        scale = 1.0
         if self.world > 1:
             torch.distributed.all_reduce(self.flat_g, group=self.pg)
-            scale = 1.0 / self.world
-        ops.sgd_step(self.flat_p, self.flat_g, self.lr, self.weight_decay, grad_scale=scale)
+        ops.sgd_step_dev(self.flat_p, self.flat_g, self.hyper)
         return out
 
     def launches_per_step(self):

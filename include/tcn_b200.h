@@ -270,6 +270,10 @@ int tcn_dropout_mask(unsigned char* keep, int nrows, int ncols, float p, unsigne
  * p -= lr * (grad_scale * g + weight_decay * p). */
 int tcn_sgd_step(float* params, const float* grads, long long n, float lr, float weight_decay, float grad_scale,
                  tcn_stream_t stream);
+/* Same update with hyper = {lr, weight_decay, grad_scale} read from DEVICE memory, so that a captured CUDA graph
+ * follows the per-epoch schedule LinearLR(start_factor=power, warmups) -> ExponentialLR(decay_rate)
+ * (Temporal_tenco/run.py:345-350, stepped at :235-236) without re-capture. */
+int tcn_sgd_step_dev(float* params, const float* grads, long long n, const float* hyper, tcn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -153,3 +153,73 @@ def test_trainer_graph_replay_equals_eager_steps():
     la, lb = results[0][0], results[1][0]
     assert all(abs(a - b) <= 2e-4 * abs(a) for a, b in zip(la, lb)), (la, lb)
     assert _maxabs(results[0][1], results[1][1]) <= 1e-4
+
+
+def test_trainer_follows_lr_schedule_inside_the_captured_graph():
+    """f2: the SGD hyper-parameters live on the device, so set_lr() changes the update of an already captured graph;
+    the update itself is torch.optim.SGD's p -= lr * (g + wd * p) (Temporal_tenco/run.py:345-346)."""
+    from computervision_codes_b200.schedule import WarmupExponentialLR
+    from computervision_codes_b200.tcn import VideoNas
+    from computervision_codes_b200.trainer import TemporalTrainer
+
+    D = 32
+    g = torch.Generator().manual_seed(2)
+    lengths = [150, 131]
+    xs = torch.cat([torch.randn(T, D, generator=g) for T in lengths]).to(DEV)
+    lab = (torch.rand(sum(lengths), 132, generator=g) < 0.1).to(torch.uint8).to(DEV)
+    sched = WarmupExponentialLR(lr=0.01, power=0.1, warmup=3, decay_rate=0.5)
+    finals = []
+    for use_graph in (True, False):
+        torch.manual_seed(4)
+        m = VideoNas(ARGS, 3, 2, 3, 64, D, 100).to(DEV).train()
+        tr = TemporalTrainer(m, lr=123.0, weight_decay=1e-3, max_frames=512, max_seqs=4, use_graph=use_graph, seed=8)
+        for epoch in range(7):
+            lr = sched.lr(epoch)
+            tr.set_lr(lr)
+            before = tr.flat_p.clone()
+            tr.step(xs, lab, lengths)
+            want = before - lr * (tr.flat_g + 1e-3 * before)
+            assert _maxabs(tr.flat_p, want) <= 1e-6, (use_graph, epoch)
+        finals.append(tr.flat_p.clone())
+    assert _maxabs(finals[0], finals[1]) <= 1e-4
+
+
+def test_step_cached_reads_clips_from_the_gpu_resident_feature_cache():
+    """f1: a step on (video, start, length) items of the FeatureCache equals a step on the same frames passed from the
+    host, and the reference-rule ClipSampler drives it."""
+    import random
+
+    import numpy as np
+
+    from computervision_codes_b200.data import ClipSampler, FeatureCache
+    from computervision_codes_b200.losses import pack_labels
+    from computervision_codes_b200.tcn import VideoNas
+    from computervision_codes_b200.trainer import TemporalTrainer
+
+    D = 32
+    rng = np.random.default_rng(6)
+    cache = FeatureCache(DEV)
+    host = {}
+    for vid, T in (("01", 400), ("02", 260), ("03", 1100)):
+        f = rng.standard_normal((T, D)).astype(np.float32)
+        ys = [(rng.random((T, k)) < 0.1).astype(np.int64) for k in (6, 10, 15, 100)]
+        cache.add_video(vid, f, *ys)
+        host[vid] = (torch.from_numpy(f), pack_labels(*[torch.from_numpy(y) for y in ys]))
+    sampler = ClipSampler("train", random.Random(1))
+    items = []
+    while len({n == cache.frames(v) for v, _, n in items}) < 2:   # make sure both a clip and a whole video occur
+        items = [(v, *sampler.sample(cache.frames(v))) for v in ("03", "01", "02")]
+    out = []
+    for cached in (True, False):
+        torch.manual_seed(4)
+        m = VideoNas(ARGS, 3, 2, 3, 64, D, 100).to(DEV).train()
+        tr = TemporalTrainer(m, lr=0.05, weight_decay=1e-5, max_frames=2048, max_seqs=4, seed=8)
+        for _ in range(2):
+            if cached:
+                loss = tr.step_cached(cache, items)
+            else:
+                xs = [host[v][0][s:s + n].pin_memory() for v, s, n in items]
+                ls = [host[v][1][s:s + n].pin_memory() for v, s, n in items]
+                loss = tr.step(xs, ls, [n for _, _, n in items])
+        out.append((loss.clone(), tr.flat_p.clone()))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])

@@ -222,4 +222,5 @@ def test_step_cached_reads_clips_from_the_gpu_resident_feature_cache():
                 ls = [host[v][1][s:s + n].pin_memory() for v, s, n in items]
                 loss = tr.step(xs, ls, [n for _, _, n in items])
         out.append((loss.clone(), tr.flat_p.clone()))
-    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    # same frames, same seeds; fp32 atomics in the weight-gradient kernels make runs differ in the last bits only
+    assert _maxabs(out[0][0], out[1][0]) <= 1e-5 and _maxabs(out[0][1], out[1][1]) <= 1e-5

@@ -96,6 +96,19 @@ class AttnArgs(C.Structure):
     ]
 
 
+class KdAttnArgs(C.Structure):
+    _fields_ = [
+        ("s", C.c_void_p), ("lds", C.c_int),
+        ("tea", C.c_void_p * 3), ("ldt", C.c_int),
+        ("z", C.c_void_p * 3), ("ldz", C.c_int),
+        ("tsum", C.c_void_p),
+        ("gz", C.c_void_p * 3),
+        ("gs", C.c_void_p), ("ldgs", C.c_int),
+        ("gtea", C.c_void_p * 3),
+        ("n_rows", C.c_int), ("feat_dim", C.c_int),
+    ]
+
+
 class ModelConfig(C.Structure):
     _fields_ = [
         ("layers_pg", C.c_int), ("layers_r", C.c_int), ("num_r", C.c_int), ("channels", C.c_int),
@@ -161,6 +174,8 @@ SIGNATURES = {
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "tcn_axpby": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_longlong, C.c_void_p]),
     "tcn_bce_rows": (C.c_int, [C.POINTER(BceArgs), C.c_void_p]),
+    "tcn_kd_attn_fwd": (C.c_int, [C.POINTER(KdAttnArgs), C.c_void_p]),
+    "tcn_kd_attn_bwd": (C.c_int, [C.POINTER(KdAttnArgs), C.c_void_p]),
     "tcn_kd_kl_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                  C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
     "tcn_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_float, C.c_void_p, C.c_float,

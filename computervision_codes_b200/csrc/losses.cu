@@ -225,6 +225,81 @@ __global__ void sgd_dev_kernel(float* __restrict__ p, const float* __restrict__ 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Multi-teacher attention re-weighting of the student feature (MT4MTLKD/Spatial_cnn/network.py:47-71).
+// The reference's einsum over F stacked copies of s collapses to  logit[b, c, n] = s[b, c] * S[b, n] / sqrt(F)  with
+// S[b, n] = sum_d m_n(t_n)[b, d]; attn = softmax over the three teachers; z_n = s * attn_n feeds w_n.
+// One warp per frame.  tsum (N, 3) keeps S for the backward pass.
+struct KdAttnDev {
+  const float* s; int lds;
+  const float* tea[3]; int ldt;
+  float* z[3]; int ldz;
+  float* tsum;
+  const float* gz[3];
+  float* gs; int ldgs;
+  float* gtea[3];
+  int N, F;
+};
+
+__device__ __forceinline__ void softmax3(float l0, float l1, float l2, float& a0, float& a1, float& a2) {
+  const float m = fmaxf(l0, fmaxf(l1, l2));
+  a0 = expf(l0 - m); a1 = expf(l1 - m); a2 = expf(l2 - m);
+  const float inv = 1.f / (a0 + a1 + a2);
+  a0 *= inv; a1 *= inv; a2 *= inv;
+}
+
+__global__ void __launch_bounds__(128) kd_attn_fwd_kernel(const KdAttnDev p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + warp;
+  if (b >= p.N) return;
+  float S[3];
+#pragma unroll
+  for (int n = 0; n < 3; ++n) {
+    float acc = 0.f;
+    for (int d = lane; d < p.F; d += 32) acc += p.tea[n][(size_t)b * p.ldt + d];
+    S[n] = warp_sum(acc);
+    if (lane == 0) p.tsum[b * 3 + n] = S[n];
+  }
+  const float scale = rsqrtf((float)p.F);
+  for (int c = lane; c < p.F; c += 32) {
+    const float sv = p.s[(size_t)b * p.lds + c];
+    float a0, a1, a2;
+    softmax3(sv * scale * S[0], sv * scale * S[1], sv * scale * S[2], a0, a1, a2);
+    p.z[0][(size_t)b * p.ldz + c] = sv * a0;
+    p.z[1][(size_t)b * p.ldz + c] = sv * a1;
+    p.z[2][(size_t)b * p.ldz + c] = sv * a2;
+  }
+}
+
+// gl_k = s a_k (gz_k - sum_n gz_n a_n);  gs = sum_n gz_n a_n + sum_k gl_k S_k / sqrt(F);
+// gS_k = sum_c gl_k s / sqrt(F), broadcast to every column of the projected teacher (S is a plain row sum)
+__global__ void __launch_bounds__(128) kd_attn_bwd_kernel(const KdAttnDev p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + warp;
+  if (b >= p.N) return;
+  const float S0 = p.tsum[b * 3], S1 = p.tsum[b * 3 + 1], S2 = p.tsum[b * 3 + 2];
+  const float scale = rsqrtf((float)p.F);
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+  for (int c = lane; c < p.F; c += 32) {
+    const float sv = p.s[(size_t)b * p.lds + c];
+    float a0, a1, a2;
+    softmax3(sv * scale * S0, sv * scale * S1, sv * scale * S2, a0, a1, a2);
+    const float z0 = p.gz[0][(size_t)b * p.ldz + c], z1 = p.gz[1][(size_t)b * p.ldz + c],
+                z2 = p.gz[2][(size_t)b * p.ldz + c];
+    const float dot = z0 * a0 + z1 * a1 + z2 * a2;
+    const float l0 = sv * a0 * (z0 - dot), l1 = sv * a1 * (z1 - dot), l2 = sv * a2 * (z2 - dot);
+    p.gs[(size_t)b * p.ldgs + c] = dot + (l0 * S0 + l1 * S1 + l2 * S2) * scale;
+    g0 += l0 * sv; g1 += l1 * sv; g2 += l2 * sv;
+  }
+  g0 = warp_sum(g0) * scale; g1 = warp_sum(g1) * scale; g2 = warp_sum(g2) * scale;
+  for (int d = lane; d < p.F; d += 32) {
+    p.gtea[0][(size_t)b * p.ldt + d] = g0;
+    p.gtea[1][(size_t)b * p.ldt + d] = g1;
+    p.gtea[2][(size_t)b * p.ldt + d] = g2;
+  }
+}
+
 int launch_bce(const BceDev& p, int cap_rows, cudaStream_t stream) {
   const long rows = cap_rows > 0 ? cap_rows : p.nrows;
   long b = (rows + 7) / 8;
@@ -338,4 +413,30 @@ extern "C" int tcn_sgd_step_dev(float* params, const float* grads, long long n, 
   TCN_REQUIRE(params && grads && hyper && n > 0, "tcn_sgd_step_dev: bad arguments");
   sgd_dev_kernel<<<grid_for(n, 1024, num_sms() * 4), 256, 0, (cudaStream_t)stream>>>(params, grads, (long)n, hyper);
   return check_launch("sgd_dev_kernel");
+}
+
+static int kd_attn_common(const tcn_kd_attn_args* a, KdAttnDev* p) {
+  TCN_REQUIRE(a && a->s && a->tsum && a->n_rows > 0 && a->feat_dim > 0, "tcn_kd_attn: bad arguments");
+  for (int n = 0; n < 3; ++n) TCN_REQUIRE(a->tea[n] && a->z[n], "tcn_kd_attn: null teacher / output pointer");
+  TCN_REQUIRE(a->lds >= a->feat_dim && a->ldt >= a->feat_dim && a->ldz >= a->feat_dim, "tcn_kd_attn: bad pitch");
+  p->s = a->s; p->lds = a->lds; p->ldt = a->ldt; p->ldz = a->ldz; p->tsum = a->tsum; p->gs = a->gs; p->ldgs = a->ldgs;
+  for (int n = 0; n < 3; ++n) { p->tea[n] = a->tea[n]; p->z[n] = a->z[n]; p->gz[n] = a->gz[n]; p->gtea[n] = a->gtea[n]; }
+  p->N = a->n_rows; p->F = a->feat_dim;
+  return TCN_OK;
+}
+
+extern "C" int tcn_kd_attn_fwd(const tcn_kd_attn_args* a, tcn_stream_t stream) {
+  KdAttnDev p;
+  TCN_CHECK(kd_attn_common(a, &p));
+  kd_attn_fwd_kernel<<<(a->n_rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("kd_attn_fwd_kernel");
+}
+
+extern "C" int tcn_kd_attn_bwd(const tcn_kd_attn_args* a, tcn_stream_t stream) {
+  KdAttnDev p;
+  TCN_CHECK(kd_attn_common(a, &p));
+  TCN_REQUIRE(a->gs && a->ldgs >= a->feat_dim, "tcn_kd_attn_bwd: null gradient pointer");
+  for (int n = 0; n < 3; ++n) TCN_REQUIRE(a->gz[n] && a->gtea[n], "tcn_kd_attn_bwd: null gradient pointer");
+  kd_attn_bwd_kernel<<<(a->n_rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("kd_attn_bwd_kernel");
 }

@@ -259,3 +259,85 @@ class MultiTeacherKDLoss(nn.Module):
             kd = sum(mse_loss(feats[k], teacher_feats[k]) for k in range(3)) / 3
         loss = self.rates[0] * hard + self.rates[1] * soft + self.rates[2] * kd
         return loss, hard, soft, kd
+
+
+# ---------------------------------------------------------------------------------------------- feature KD (row f3)
+class _KdAttnFn(torch.autograd.Function):
+    """(s, m_i(t_i), m_v(t_v), m_t(t_t)) -> (s * attn_i, s * attn_v, s * attn_t); all (N, F)."""
+
+    @staticmethod
+    def forward(ctx, s, tea_i, tea_v, tea_t):
+        lib = _lib.load()
+        s = s.contiguous().float()
+        teas = [t.contiguous().float() for t in (tea_i, tea_v, tea_t)]
+        N, Fd = s.shape
+        assert all(t.shape == s.shape for t in teas), "projected teacher features must be (N, student_dim)"
+        zs = [torch.empty_like(s) for _ in range(3)]
+        tsum = torch.empty(N, 3, device=s.device, dtype=torch.float32)
+        a = _lib.KdAttnArgs()
+        a.s, a.lds, a.ldt, a.ldz, a.tsum = _lib.ptr(s), Fd, Fd, Fd, _lib.ptr(tsum)
+        for n in range(3):
+            a.tea[n], a.z[n] = _lib.ptr(teas[n]), _lib.ptr(zs[n])
+        a.n_rows, a.feat_dim = N, Fd
+        _lib.check(lib.tcn_kd_attn_fwd(C.byref(a), _lib.stream_ptr()), "tcn_kd_attn_fwd")
+        ctx.save_for_backward(s, tsum, *teas)
+        return tuple(zs)
+
+    @staticmethod
+    def backward(ctx, g_i, g_v, g_t):
+        lib = _lib.load()
+        s, tsum, *teas = ctx.saved_tensors
+        N, Fd = s.shape
+        gz = [g.contiguous().float() for g in (g_i, g_v, g_t)]
+        gs = torch.empty_like(s)
+        gteas = [torch.empty_like(s) for _ in range(3)]
+        a = _lib.KdAttnArgs()
+        a.s, a.lds, a.ldt, a.ldz, a.tsum = _lib.ptr(s), Fd, Fd, Fd, _lib.ptr(tsum)
+        a.gs, a.ldgs = _lib.ptr(gs), Fd
+        for n in range(3):
+            a.tea[n], a.z[n] = _lib.ptr(teas[n]), _lib.ptr(gz[n])   # z is not written by the backward
+            a.gz[n], a.gtea[n] = _lib.ptr(gz[n]), _lib.ptr(gteas[n])
+        a.n_rows, a.feat_dim = N, Fd
+        _lib.check(lib.tcn_kd_attn_bwd(C.byref(a), _lib.stream_ptr()), "tcn_kd_attn_bwd")
+        return gs, gteas[0], gteas[1], gteas[2]
+
+
+class MultiTeacherFeatureAttention(nn.Module):
+    """The feature-KD head of the spatial student, ``MT4MTLKD/Spatial_cnn/network.py:26-32`` (parameters) and
+    ``:47-71`` (forward); identical block in ``Spatial_transformer/network.py:102-124``.
+
+    Parameters keep the reference's names, shapes and creation order -- ``wi, wv, wt: Conv1d(student_dim,
+    teacher_dim, 1)``, ``mi, mv, mt: Conv1d(teacher_dim, student_dim, 1)`` -- so a reference ``state_dict`` loads with
+    ``strict=False`` and equal seeds give equal initial weights.  ``forward(s, tool, verb, target)``: s (N, student_dim)
+    pooled student feature, the three teacher features (N, teacher_dim); returns (stus_fi, stus_fv, stus_ft), each
+    (N, teacher_dim), which ``MultiTeacherKDLoss(feats=..., teacher_feats=...)`` compares with the teachers by MSE
+    (``Spatial_cnn/run.py:187-191``).  The 1x1 projections run on the tap-GEMM kernels, the re-weighting on
+    ``tcn_kd_attn_{fwd,bwd}``."""
+
+    def __init__(self, student_dim=512, teacher_dim=1536):
+        super().__init__()
+        self.feat_dim, self.num_f_mstct = student_dim, teacher_dim
+        self.wi = nn.Conv1d(student_dim, teacher_dim, kernel_size=1, stride=1, padding=0)
+        self.wv = nn.Conv1d(student_dim, teacher_dim, kernel_size=1, stride=1, padding=0)
+        self.wt = nn.Conv1d(student_dim, teacher_dim, kernel_size=1, stride=1, padding=0)
+        self.mi = nn.Conv1d(teacher_dim, student_dim, kernel_size=1, stride=1, padding=0)
+        self.mv = nn.Conv1d(teacher_dim, student_dim, kernel_size=1, stride=1, padding=0)
+        self.mt = nn.Conv1d(teacher_dim, student_dim, kernel_size=1, stride=1, padding=0)
+
+    def forward(self, s, tool, verb, target):
+        from . import ops
+
+        if not s.is_cuda:
+            raise RuntimeError("MultiTeacherFeatureAttention runs on the CUDA kernels only (no CPU path)")
+        N = s.shape[0]
+        lay = SeqLayout.get([N], s.device)
+        pad = lay.rows - N
+
+        def rows(t):
+            return torch.nn.functional.pad(t.float(), (0, 0, 0, pad)) if pad else t.float().contiguous()
+
+        teas = [ops.tap_linear(rows(t), m.weight, m.bias, lay)[:N, :self.feat_dim]
+                for t, m in zip((tool, verb, target), (self.mi, self.mv, self.mt))]
+        zs = _KdAttnFn.apply(s, *teas)
+        return tuple(ops.tap_linear(rows(z), w.weight, w.bias, lay)[:N, :self.num_f_mstct]
+                     for z, w in zip(zs, (self.wi, self.wv, self.wt)))

@@ -224,6 +224,24 @@ int tcn_kd_kl_rows(const float* ys, int lds, const float* yt, int ldt, int teach
 int tcn_mse(const float* a, const float* b, long long n, float* loss, float loss_scale, float* ga, float grad_scale,
             tcn_stream_t stream);
 
+/* Multi-teacher attention re-weighting of the student feature (MT4MTLKD/Spatial_cnn/network.py:47-71; same block
+ * Spatial_transformer/network.py:102-124): with tea[n] = m_n(teacher_n) (N, F), S[b, n] = sum_d tea[n][b, d],
+ * attn[b, c, :] = softmax_n(s[b, c] * S[b, n] / sqrt(F)) and z[n] = s * attn[:, :, n], the inputs of w_i / w_v / w_t.
+ * Backward: gs (N, F) and gtea[n] (N, F; every column of row b carries dL/dS[b, n]).  tsum: (N, 3) scratch saved by
+ * the forward. */
+typedef struct {
+  const float* s; int lds;
+  const float* tea[3]; int ldt;
+  float* z[3]; int ldz;
+  float* tsum;
+  const float* gz[3];
+  float* gs; int ldgs;
+  float* gtea[3];
+  int n_rows; int feat_dim;
+} tcn_kd_attn_args;
+int tcn_kd_attn_fwd(const tcn_kd_attn_args* args, tcn_stream_t stream);
+int tcn_kd_attn_bwd(const tcn_kd_attn_args* args, tcn_stream_t stream);
+
 /* Softmax cross-entropy (7-way phase head; no reference counterpart). */
 int tcn_ce_rows(const float* x, int ldx, const int* target, const int* meta, int tgt_unpadded, int nrows, int K,
                 float row_scale, float* loss, float* gx, int ldg, float grad_scale, tcn_stream_t stream);

@@ -105,3 +105,18 @@ def mstct_classifier_class():
     ns = {"torch": torch, "nn": nn}
     exec("\n".join(lines[start:end]), ns)
     return ns["Classifier"]
+
+
+def spatial_cnn_network():
+    """MT4MTLKD/Spatial_cnn/network.py (the student of the multi-teacher KD stage; row f3 uses lines 47-71).
+
+    Its constructor asks torchvision for *pretrained* ResNet weights (a download) and its forward calls ``.cuda()``;
+    callers patch ``basemodels.resnet18`` to the un-initialised architecture and swap ``model.basemodel`` for a stub
+    that returns a given feature tensor, so that only the attention / projection lines of the reference run."""
+    import torchvision.models as basemodels
+
+    mod = _load(os.path.join(REF_ROOT, "MT4MTLKD/Spatial_cnn/network.py"), "_ref_spatial_cnn_network")
+    orig = basemodels.resnet18
+    mod.basemodels = types.SimpleNamespace(resnet18=lambda pretrained=True: orig(weights=None),
+                                           resnet50=basemodels.resnet50)
+    return mod

@@ -331,6 +331,29 @@ def multi_teacher_kd_loss(logits, labels, teacher_logits, feats=None, teacher_fe
     return loss, hard, soft, kd
 
 
+def feature_kd_attention(s, teachers, params):
+    """Multi-teacher attention re-weighting of the student feature, MT4MTLKD/Spatial_cnn/network.py:47-71
+    (same block: Spatial_transformer/network.py:102-124).
+
+    s (B, F) student feature; teachers = (t_i, t_v, t_t), each (B, M); params: '{wi,wv,wt}.weight' (M, F, 1),
+    '{mi,mv,mt}.weight' (F, M, 1) and biases.  The reference stacks F copies of s into stus[b, c, d] = s[b, c] and the
+    three projected teachers into teas[b, d, n] = m_n(t_n)[b, d] (:56-59), so that
+    attn[b, c, :] = softmax_n( sum_d stus[b, c, d] / sqrt(F) * teas[b, d, n] ) (:61-62) and
+    stus_f_n = w_n(s * attn[:, :, n]) (:63-65).  Returns (stus_fi, stus_fv, stus_ft), each (B, M)."""
+    F = s.shape[1]
+    teas = torch.stack([conv1x1(t.unsqueeze(-1), params[f"{m}.weight"], params[f"{m}.bias"]).squeeze(-1)
+                        for t, m in zip(teachers, ("mi", "mv", "mt"))], dim=-1)          # (B, F, 3)
+    stus = s.unsqueeze(-1).expand(-1, -1, F)                                               # (B, F, F)
+    attn = torch.einsum("bcd,bdn->bcn", stus / (F ** 0.5), teas).softmax(dim=-1)
+    return tuple(conv1x1((s * attn[:, :, n]).unsqueeze(-1), params[f"{w}.weight"], params[f"{w}.bias"]).squeeze(-1)
+                 for n, w in enumerate(("wi", "wv", "wt")))
+
+
+def feature_kd_loss(stus_f, teachers):
+    """Spatial_cnn/run.py:187-191: mean of the three MSE losses."""
+    return sum(mse(a, b) for a, b in zip(stus_f, teachers)) / 3
+
+
 def phase_ce(logits, target):
     """7-way 'phase' head: mean softmax cross-entropy over frames.  logits (N, K), target (N,) int.
 

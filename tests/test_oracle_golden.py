@@ -142,6 +142,27 @@ def test_kd_losses(golden_dir):
         assert torch.allclose(feats[k].grad, _t(z[f"comp.gfeat{k}"]), atol=1e-7, rtol=1e-4)
 
 
+@pytest.mark.parametrize("tag", ["small", "wide"])
+def test_feature_kd_attention_block(golden_dir, tag):
+    """Row f3 against the reference's own forward/backward (oracle/gen_golden_kdattn.py)."""
+    z = _load(golden_dir, "kd_attn.npz")
+    params = {k: v.double().requires_grad_(True) for k, v in _sd(z, f"{tag}.sd.").items()}
+    s = _t(z[f"{tag}.s"]).double().requires_grad_(True)
+    teachers = [_t(z[f"{tag}.teacher_{n}"]).double() for n in "ivt"]
+    outs = O.feature_kd_attention(s, teachers, params)
+    for n, y in zip("ivt", outs):
+        ref = z[f"{tag}.stus_f{n}"]
+        assert np.abs(y.detach().numpy() - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
+    loss = O.feature_kd_loss(outs, teachers)
+    assert abs(float(loss) - float(z[f"{tag}.kd_loss"])) <= 1e-6 * float(z[f"{tag}.kd_loss"])
+    loss.backward()
+    ref = z[f"{tag}.grad.s"]
+    assert np.abs(s.grad.numpy() - ref).max() <= 1e-5 * np.abs(ref).max() + 1e-9
+    for k, v in params.items():
+        ref = z[f"{tag}.grad.{k}"]
+        assert np.abs(v.grad.numpy() - ref).max() <= 1e-5 * np.abs(ref).max() + 1e-9, k
+
+
 def test_phase_ce_matches_textbook():
     torch.manual_seed(3)
     x = torch.randn(50, 7)

@@ -339,3 +339,35 @@ def test_drop_in_training_loop_matches_cpu_port_for_two_sgd_steps():
         assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
     for k, v in m.state_dict().items():
         assert _maxabs(v, ref[k]) <= 2e-5, (k, _maxabs(v, ref[k]))
+
+
+@pytest.mark.parametrize("tag", ["small", "wide"])
+def test_multi_teacher_feature_attention_matches_reference_golden(golden_dir, tag):
+    """Row f3: the drop-in block loads the reference's weights by name and reproduces its outputs, the KD term of
+    Spatial_cnn/run.py:187-191 and every gradient (fixtures: oracle/gen_golden_kdattn.py)."""
+    import numpy as np
+
+    from computervision_codes_b200.losses import MultiTeacherFeatureAttention, mse_loss
+
+    z = np.load(os.path.join(golden_dir, "kd_attn.npz"))
+    s = torch.from_numpy(z[f"{tag}.s"]).to(DEV).requires_grad_(True)
+    teachers = [torch.from_numpy(z[f"{tag}.teacher_{n}"]).to(DEV) for n in "ivt"]
+    blk = MultiTeacherFeatureAttention(s.shape[1], teachers[0].shape[1])
+    sd = {k[len(tag) + 4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(f"{tag}.sd.")}
+    assert set(sd) == set(blk.state_dict())
+    blk.load_state_dict(sd)
+    blk = blk.to(DEV)
+    outs = blk(s, *teachers)
+    for n, y in zip("ivt", outs):
+        ref = z[f"{tag}.stus_f{n}"]
+        assert y.shape == ref.shape
+        assert np.abs(y.detach().cpu().numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+    kd = sum(mse_loss(a, b) for a, b in zip(outs, teachers)) / 3
+    assert abs(float(kd.detach()) - float(z[f"{tag}.kd_loss"])) <= 1e-5 * float(z[f"{tag}.kd_loss"])
+    kd.backward()
+    ref = z[f"{tag}.grad.s"]
+    assert np.abs(s.grad.cpu().numpy() - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-8
+    for name, prm in blk.named_parameters():
+        ref = z[f"{tag}.grad.{name}"]
+        got = prm.grad.cpu().numpy()
+        assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-8, name

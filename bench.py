@@ -347,7 +347,7 @@ def _graph_time(fn, n=24):
 
 def measure_layer_roofline(model, lengths, batch, dev):
     """Dominant kernel by time share (profiles/): the residual layers' tensor-core kernels.  Reported here: the
-    input-gradient tap GEMM `gemm_tc_persist_kernel` (3 taps; gx = gy + sum_k W1_k^T gu[t - s_k]) timed live on this
+    input-gradient tap GEMM `gemm_tc_slab_kernel` (3 taps; gx = gy + sum_k W1_k^T gu[t - s_k]) timed live on this
     step's batch shape, and the same kernel on the TERL stress shape (64 x 8000 frames) where the HBM roofline is
     the binding limit.  Algorithmic bytes per frame: 12*C (read gu, read gy, write gx)."""
     from computervision_codes_b200 import ops
@@ -380,8 +380,12 @@ def measure_layer_roofline(model, lengths, batch, dev):
 
     frames, ms, gbs = run([lengths[v] for v in batch], 8)
     sframes, sms, sgbs = run([8000] * 64, 6)
-    return {"bound": "hbm", "kernel": "gemm_tc_persist_kernel (tcgen05 tap GEMM, input gradient of the dilated conv)",
-            "achieved": gbs, "peak": peak, "peak_source": src, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, from the committed ncu capture
+    tpath = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
+    return {"bound": "hbm", "kernel": "gemm_tc_slab_kernel (tcgen05 tap GEMM, input gradient of the dilated conv)",
+            "achieved": gbs, "peak": peak, "peak_source": src, "unit": "GB/s", "frac": gbs / peak, "traffic": traffic,
             "frames_per_launch": frames, "ms_per_launch": ms,
             "stress_shape": {"frames_per_launch": sframes, "ms_per_launch": sms, "achieved": sgbs, "frac": sgbs / peak},
             "note": "at this step's batch (a few MB per activation, L2-resident, one wave of CTAs) the kernel is "

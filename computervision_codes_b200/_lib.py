@@ -56,6 +56,17 @@ class LayerFwdArgs(C.Structure):
     ]
 
 
+class LayerFwdTcArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("x_rows", C.c_longlong), ("y", C.c_void_p), ("h", C.c_void_p),
+        ("w1_hi", C.c_void_p), ("w1_lo", C.c_void_p), ("w2_hi", C.c_void_p), ("w2_lo", C.c_void_p),
+        ("b1", C.c_void_p), ("b2", C.c_void_p),
+        ("meta", C.c_void_p), ("nblk", C.c_int), ("channels", C.c_int),
+        ("shift", C.c_int * 3),
+        ("drop_p", C.c_float), ("drop_seed", C.c_uint), ("drop_stream", C.c_uint),
+    ]
+
+
 class GemmTcArgs(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("ldx", C.c_int), ("x_rows", C.c_longlong), ("x_unpadded", C.c_int),
@@ -140,6 +151,7 @@ SIGNATURES = {
     "tcn_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     "tcn_wgrad_tc": (C.c_int, [C.POINTER(WgradTcArgs), C.c_void_p]),
     "tcn_layer_fwd": (C.c_int, [C.POINTER(LayerFwdArgs), C.c_void_p]),
+    "tcn_layer_fwd_tc": (C.c_int, [C.POINTER(LayerFwdTcArgs), C.c_void_p]),
     "tcn_gemm_tc_supported": (C.c_int, [C.c_int, C.c_int]),
     "tcn_gemm_tc": (C.c_int, [C.POINTER(GemmTcArgs), C.c_void_p]),
     "tcn_split_weight_floats": (C.c_longlong, [C.c_int] * 4),

@@ -201,6 +201,49 @@ __device__ __forceinline__ void epilogue_block_coalesced(const float (&v0)[32], 
   __syncwarp();
 }
 
+// Coalesced epilogue of a warp's 32 x 32 accumulator block (one row per lane in `v`) through a private 4 KB staging
+// buffer (XOR-swizzled 16-byte chunks: conflict-free both ways); every global access covers four full 128-byte row
+// segments per warp instruction.  Compile-time feature set, bias always on.  Used by the fused layer kernel, whose
+// epilogue warps each own 32 columns.
+template <bool RELU, bool RES, bool DROP>
+__device__ __forceinline__ void epilogue_block32(const float (&v)[32], float4* st, int lane, int row_base, int row_hi,
+                                                 int n_base, const GemmTcDev& p, uint32_t out_seed) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    st[lane * 8 + (c ^ (lane & 7))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+  __syncwarp();
+  const int c = lane & 7, n = n_base + c * 4;
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+  float4 rr[8];
+  if (RES) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rowc = min(row_base + i * 4 + (lane >> 3), row_hi - 1);  // clamp: loads stay in bounds
+      rr[i] = *reinterpret_cast<const float4*>(p.R + (size_t)rowc * p.ldr + n);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3), row = row_base + r;
+    const float4 a = st[r * 8 + (c ^ (r & 7))];
+    float o[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
+    if (RELU) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+    }
+    if (DROP) {
+      if (p.drop_thresh != 0u) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          o[e] *= drop_factor(out_seed, p.drop_stream, p.drop_thresh, p.drop_scale, row, n + e);
+      }
+    }
+    if (RES) { o[0] += rr[i].x; o[1] += rr[i].y; o[2] += rr[i].z; o[3] += rr[i].w; }
+    if (row < row_hi) *reinterpret_cast<float4*>(p.Y + (size_t)row * p.ldy + n) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  __syncwarp();
+}
+
 template <int BN>
 struct TcSmem {
   static constexpr int kStages = BN > 64 ? 3 : 4;
@@ -761,6 +804,308 @@ static int wide_bn(const GemmTcDev& p, int nb) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused residual layer forward (network.py:186-198), 64 channels, one kernel:
+//     u = b1 + sum_k W1_k x[t + s_k];  h = relu(u);  v = b2 + W2 h;  y = x + dropout(v)
+// Both GEMMs take their A operand from TENSOR MEMORY (tcgen05.mma with A in TMEM, tools/exp/exp_tmem_a.cu):
+//   * GEMM 1 (dilated conv): TMA drops the raw 128 x 32 fp32 tiles of x (one per tap and 32-channel block) into a
+//     4-deep shared-memory ring; each operand-split thread owns one frame (= one TMEM lane), un-swizzles its 128-byte
+//     row, zeroes it when the tap leaves the sequence, and stores the TF32 hi / lo halves straight into a
+//     double-buffered TMEM operand slot.  Shared memory holds only raw tiles (16 KB per stage instead of 32 KB for
+//     hi + lo), is written once and read once, and the tensor pipe reads A from TMEM instead of shared memory.
+//   * GEMM 2 (1x1 conv): the epilogue warps read u from TMEM, apply bias + ReLU, store the hi / lo halves of h back to
+//     TMEM (and h once to HBM for the backward pass); h never touches shared memory.
+// W1 / W2 (hi and lo) stay resident in shared memory; the MMA warp issues GEMM 1 of tile i + 1 before GEMM 2 of tile i.
+//   TMEM (512 columns): u[2] @ 0 / 64, v[2] @ 128 / 192, h_hi @ 256, h_lo @ 320, x operand slots @ 384 / 448 (hi | lo)
+//   warp 0: TMA | warp 1: MMA + TMEM owner | warps 2-5: operand split of x | warps 6-9: u -> h (TMEM + HBM) |
+//   warps 10-13: v -> y.  The two epilogue groups work on different tiles at the same time.
+constexpr int LFT_STAGES = 4;
+constexpr int LFT_THREADS = 448;
+constexpr int LFT_EPI = 8 * 4096;   // eight epilogue warps x (32 x 32 fp32) staging
+static inline int lft_smem_bytes() { return 8 * 2 * TP_KB + LFT_STAGES * TP_KA + LFT_EPI + 1024 + 256; }
+
+__global__ void __launch_bounds__(LFT_THREADS, 1)
+layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1hi,
+                    const __grid_constant__ CUtensorMap map_w1lo, const __grid_constant__ CUtensorMap map_w2hi,
+                    const __grid_constant__ CUtensorMap map_w2lo, const LayerTcDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nblk = p.y.dyn ? p.y.dyn->nblk : p.y.nblk;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* wt = smem_raw + (base - smem_u32(smem_raw));   // slots 0..5: W1 (tap * 2 + kc), 6..7: W2 (kc); [hi | lo]
+  uint8_t* at = wt + 8 * 2 * TP_KB;                       // raw x tiles, LFT_STAGES x 16 KB
+  const uint32_t wt_addr = base;
+  float4* epi = reinterpret_cast<float4*>(at + LFT_STAGES * TP_KA);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(at + LFT_STAGES * TP_KA + LFT_EPI);
+  uint64_t* wfull = bars;
+  uint64_t* full_bar = bars + 1;                  // [4] TMA bytes landed
+  uint64_t* empty_bar = full_bar + LFT_STAGES;    // [4] raw tile read by the 128 split threads
+  uint64_t* aready = empty_bar + LFT_STAGES;      // [2] x operand slot written to TMEM (128 split threads)
+  uint64_t* aempty = aready + 2;                  // [2] ... consumed by the tensor pipe (tcgen05.commit)
+  uint64_t* ufull = aempty + 2;                   // [2] GEMM 1 accumulator complete
+  uint64_t* uempty = ufull + 2;                   // [2] ... drained by the epilogue warps
+  uint64_t* vfull = uempty + 2;                   // [2] GEMM 2 accumulator complete (also: h in TMEM is free again)
+  uint64_t* vempty = vfull + 2;                   // [2]
+  uint64_t* hready = vempty + 2;                  // h_hi / h_lo written to TMEM (128 epilogue threads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hready + 1);
+
+  if (threadIdx.x == 0) {
+    mbar_init(wfull, 1);
+    for (int s = 0; s < LFT_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 128);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&aready[s], 128);
+      mbar_init(&aempty[s], 1);
+      mbar_init(&ufull[s], 1);
+      mbar_init(&uempty[s], 128);
+      mbar_init(&vfull[s], 1);
+      mbar_init(&vempty[s], 128);
+    }
+    mbar_init(hready, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t dseed = p.y.dyn ? p.y.dyn->seed : 0u;
+  constexpr uint32_t kU = 0, kV = 128, kHhi = 256, kHlo = 320, kA = 384;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wfull, 8 * 2 * TP_KB);
+      for (int kb = 0; kb < 6; ++kb) {
+        tma_load_2d(wt + kb * 2 * TP_KB, &map_w1hi, wfull, kb * TC_BK, 0);
+        tma_load_2d(wt + kb * 2 * TP_KB + TP_KB, &map_w1lo, wfull, kb * TC_BK, 0);
+      }
+      for (int kc = 0; kc < 2; ++kc) {
+        tma_load_2d(wt + (6 + kc) * 2 * TP_KB, &map_w2hi, wfull, kc * TC_BK, 0);
+        tma_load_2d(wt + (6 + kc) * 2 * TP_KB + TP_KB, &map_w2lo, wfull, kc * TC_BK, 0);
+      }
+      int it = 0;
+      for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const BlkMeta m = p.y.meta[blk];
+        const int row0 = blk * kBlkRows;
+        if (row0 >= m.hi) continue;
+        for (int j = 0; j < 6; ++j, ++it) {
+          const int tap = j >> 1, kc = j & 1;
+          const int s = it % LFT_STAGES;
+          const uint32_t ph = (it / LFT_STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], TP_KA);
+          const int sh = tap == 0 ? p.y.shift[0] : (tap == 1 ? p.y.shift[1] : p.y.shift[2]);
+          tma_load_2d(at + s * TP_KA, &map_x, &full_bar[s], kc * TC_BK, row0 + sh);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, 64);
+    mbar_wait(wfull, 0);
+    auto gemm2 = [&](int t) {  // v[t & 1] = h W2^T, h taken from TMEM
+      const int a = t & 1;
+      mbar_wait(hready, (uint32_t)(t & 1));
+      mbar_wait(&vempty[a], (((uint32_t)t >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t tacc = tmem_base + kV + a * 64;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t b_hi = wt_addr + (6 + (k >> 2)) * 2 * TP_KB + (k & 3) * 32, b_lo = b_hi + TP_KB;
+          const uint64_t dbh = umma_desc_sw128(b_hi), dbl = umma_desc_sw128(b_lo);
+          umma_tf32_ts(tacc, tmem_base + kHlo + k * 8, dbh, idesc, k != 0);
+          umma_tf32_ts(tacc, tmem_base + kHhi + k * 8, dbl, idesc, 1u);
+          umma_tf32_ts(tacc, tmem_base + kHhi + k * 8, dbh, idesc, 1u);
+        }
+        umma_commit(&vfull[a]);
+      }
+      __syncwarp();
+    };
+    int it = 0, tcount = 0;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      const BlkMeta m = p.y.meta[blk];
+      if (blk * kBlkRows >= m.hi) continue;
+      const int a = tcount & 1;
+      mbar_wait(&uempty[a], (((uint32_t)tcount >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + kU + a * 64;
+      for (int j = 0; j < 6; ++j, ++it) {
+        const int ta = it & 1;
+        mbar_wait(&aready[ta], ((uint32_t)it >> 1) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = tmem_base + kA + ta * 64, a_lo = a_hi + 32;
+          const uint32_t b_hi = wt_addr + j * 2 * TP_KB, b_lo = b_hi + TP_KB;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint64_t dbh = umma_desc_sw128(b_hi + k * 32), dbl = umma_desc_sw128(b_lo + k * 32);
+            umma_tf32_ts(tacc, a_lo + k * 8, dbh, idesc, (j | k) != 0);
+            umma_tf32_ts(tacc, a_hi + k * 8, dbl, idesc, 1u);
+            umma_tf32_ts(tacc, a_hi + k * 8, dbh, idesc, 1u);
+          }
+          umma_commit(&aempty[ta]);
+          if (j == 5) umma_commit(&ufull[a]);
+        }
+        __syncwarp();
+      }
+      if (tcount > 0) gemm2(tcount - 1);
+      ++tcount;
+    }
+    if (tcount > 0) gemm2(tcount - 1);
+  } else if (warp < 6) {
+    // ===================== operand split of x (warps 2..5): one frame = one thread = one TMEM lane ================
+    const int r = (warp & 3) * 32 + lane;                      // frame inside the tile == TMEM lane
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    int it = 0;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      const BlkMeta m = p.y.meta[blk];
+      const int row0 = blk * kBlkRows;
+      if (row0 >= m.hi) continue;
+      for (int j = 0; j < 6; ++j, ++it) {
+        const int tap = j >> 1;
+        const int s = it % LFT_STAGES, ta = it & 1;
+        const int sh = tap == 0 ? p.y.shift[0] : (tap == 1 ? p.y.shift[1] : p.y.shift[2]);
+        mbar_wait(&full_bar[s], (it / LFT_STAGES) & 1);
+        const float4* row = reinterpret_cast<const float4*>(at + s * TP_KA) + r * 8;
+        const int src = row0 + r + sh;
+        const float keep = (src >= m.lo && src < m.hi) ? 1.f : 0.f;
+        float hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = row[c ^ (r & 7)];                   // undo the 128B swizzle: logical 16-byte chunk c
+          const float x0 = v.x * keep, x1 = v.y * keep, x2 = v.z * keep, x3 = v.w * keep;
+          hi[4 * c + 0] = __uint_as_float(__float_as_uint(x0) & 0xffffe000u); lo[4 * c + 0] = x0 - hi[4 * c + 0];
+          hi[4 * c + 1] = __uint_as_float(__float_as_uint(x1) & 0xffffe000u); lo[4 * c + 1] = x1 - hi[4 * c + 1];
+          hi[4 * c + 2] = __uint_as_float(__float_as_uint(x2) & 0xffffe000u); lo[4 * c + 2] = x2 - hi[4 * c + 2];
+          hi[4 * c + 3] = __uint_as_float(__float_as_uint(x3) & 0xffffe000u); lo[4 * c + 3] = x3 - hi[4 * c + 3];
+        }
+        mbar_arrive(&empty_bar[s]);                            // the raw tile is in registers: TMA may refill the slot
+        mbar_wait(&aempty[ta], (((uint32_t)it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        tmem_st32(lane_base + kA + ta * 64, hi);
+        tmem_st32(lane_base + kA + ta * 64 + 32, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&aready[ta]);
+      }
+    }
+  } else if (warp < 10) {
+    // ===================== u -> h (warps 6..9; TMEM lane quadrant = warp % 4) =====================
+    const int q = warp & 3;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    float4* st = epi + (warp - 6) * 256;
+    int tcount = 0;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      const BlkMeta m = p.y.meta[blk];
+      const int row0 = blk * kBlkRows;
+      if (row0 >= m.hi) continue;
+      const int a = tcount & 1;
+      mbar_wait(&ufull[a], ((uint32_t)tcount >> 1) & 1);
+      tc_fence_after();
+      if (tcount > 0) mbar_wait(&vfull[(tcount - 1) & 1], ((uint32_t)(tcount - 1) >> 1) & 1);  // h of the previous tile consumed
+      tc_fence_after();
+      // bias + ReLU, hi / lo halves of h into TMEM (32 columns at a time)
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        float u[32], lo[32];
+        tmem_ld32(lane_base + kU + a * 64 + c0, u);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.h.bias + c0 + j));
+          const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float hv = fmaxf(u[j + e] + bb[e], 0.f);
+            u[j + e] = __uint_as_float(__float_as_uint(hv) & 0xffffe000u);
+            lo[j + e] = hv - u[j + e];
+          }
+        }
+        tmem_st32(lane_base + kHhi + c0, u);
+        tmem_st32(lane_base + kHlo + c0, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(hready);   // GEMM 2 can start; the copy of h to HBM below overlaps it
+      if (p.h.Y != nullptr) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          float u[32];
+          tmem_ld32(lane_base + kU + a * 64 + c0, u);
+          if (c0 == 32) {
+            tc_fence_before();
+            mbar_arrive(&uempty[a]);
+          }
+          epilogue_block32<true, false, false>(u, st, lane, row0 + q * 32, m.hi, c0, p.h, 0u);
+        }
+      } else {
+        mbar_arrive(&uempty[a]);
+      }
+      ++tcount;
+    }
+  } else {
+    // ===================== v -> y: bias, dropout, + x (warps 10..13) =====================
+    const int q = warp & 3;
+    const uint32_t out_seed = p.y.drop_seed ^ dseed;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    float4* st = epi + (warp - 6) * 256;
+    int tcount = 0;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      const BlkMeta m = p.y.meta[blk];
+      const int row0 = blk * kBlkRows;
+      if (row0 >= m.hi) continue;
+      const int a = tcount & 1;
+      mbar_wait(&vfull[a], ((uint32_t)tcount >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        float v[32];
+        tmem_ld32(lane_base + kV + a * 64 + c0, v);
+        if (c0 == 32) {
+          tc_fence_before();
+          mbar_arrive(&vempty[a]);
+        }
+        epilogue_block32<false, true, true>(v, st, lane, row0 + q * 32, m.hi, c0, p.y, out_seed);
+      }
+      ++tcount;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u));
+}
+
+int launch_layer_fwd_tc(const CUtensorMap& mx, const CUtensorMap& w1hi, const CUtensorMap& w1lo, const CUtensorMap& w2hi,
+                        const CUtensorMap& w2lo, const LayerTcDev& p, int cap_nblk, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e =
+        cudaFuncSetAttribute(layer_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lft_smem_bytes());
+    if (e != cudaSuccess) {
+      set_error("layer_fwd_tc: smem attribute: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return TCN_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int nb = cap_nblk > 0 ? cap_nblk : p.y.nblk;
+  int gx = num_sms();
+  if (gx > nb) gx = nb;
+  launch_kernel(layer_fwd_tc_kernel, dim3(gx), dim3(LFT_THREADS), lft_smem_bytes(), stream, true, mx, w1hi, w1lo, w2hi, w2lo,
+                p);
+  return check_launch("layer_fwd_tc_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
 // Slab variant of the persistent kernel for the k = 3 dilated convolutions with a small dilation
 // (max shift - min shift <= 64 frames, 64 input channels).  tcgen05 shared-memory descriptors may start at ANY row
 // of a TMA-swizzled tile (the 128B swizzle is a function of the absolute shared-memory address; verified on
@@ -1187,4 +1532,32 @@ extern "C" int tcn_gemm_tc(const tcn_gemm_tc_args* a, tcn_stream_t stream) {
   const bool slab = gemm_tc_wants_slab(p);
   if (slab) TCN_CHECK(make_tensor_map_2d(&mx32, a->x, a->x_rows, a->c_in, a->ldx, 32));
   return launch_gemm_tc(mx, mh, ml, p, 0, (cudaStream_t)stream, slab ? &mx32 : nullptr);
+}
+
+extern "C" int tcn_layer_fwd_tc(const tcn_layer_fwd_tc_args* a, tcn_stream_t stream) {
+  TCN_REQUIRE(a && a->x && a->y && a->w1_hi && a->w1_lo && a->w2_hi && a->w2_lo && a->b1 && a->b2 && a->meta,
+              "tcn_layer_fwd_tc: null pointer");
+  if (a->channels != 64) {
+    set_error("tcn_layer_fwd_tc: the fused kernel is built for 64 channels (got %d); use tcn_gemm_tc", a->channels);
+    return TCN_ERR_UNSUPPORTED;
+  }
+  TCN_REQUIRE(a->nblk > 0 && a->x_rows > 0, "tcn_layer_fwd_tc: empty problem");
+  TCN_REQUIRE(a->drop_p >= 0.f && a->drop_p < 1.f, "tcn_layer_fwd_tc: drop_p must be in [0, 1)");
+  CUtensorMap mx, w1h, w1l, w2h, w2l;
+  TCN_CHECK(make_tensor_map_2d(&mx, a->x, a->x_rows, 64, 64, TC_BM));
+  TCN_CHECK(make_tensor_map_2d(&w1h, a->w1_hi, 64, 192, 192, 64));
+  TCN_CHECK(make_tensor_map_2d(&w1l, a->w1_lo, 64, 192, 192, 64));
+  TCN_CHECK(make_tensor_map_2d(&w2h, a->w2_hi, 64, 64, 64, 64));
+  TCN_CHECK(make_tensor_map_2d(&w2l, a->w2_lo, 64, 64, 64, 64));
+  LayerTcDev p;
+  memset(&p, 0, sizeof(p));
+  p.h.Y = a->h; p.h.ldy = 64; p.h.N = 64; p.h.bias = a->b1; p.h.relu = 1; p.h.drop_scale = 1.f; p.h.in_drop_scale = 1.f;
+  p.y.Y = a->y; p.y.ldy = 64; p.y.N = 64; p.y.bias = a->b2; p.y.R = a->x; p.y.ldr = 64;
+  p.y.meta = reinterpret_cast<const BlkMeta*>(a->meta); p.y.nblk = a->nblk; p.y.ntaps = 3; p.y.kbp = 2; p.y.c_in = 64;
+  for (int i = 0; i < 3; ++i) p.y.shift[i] = a->shift[i];
+  p.y.in_drop_scale = 1.f;
+  p.y.drop_thresh = a->drop_p > 0.f ? drop_thresh(a->drop_p) : 0u;
+  p.y.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
+  p.y.drop_seed = a->drop_seed; p.y.drop_stream = a->drop_stream;
+  return launch_layer_fwd_tc(mx, w1h, w1l, w2h, w2l, p, 0, (cudaStream_t)stream);
 }

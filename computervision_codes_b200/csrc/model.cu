@@ -71,6 +71,7 @@ struct tcn_model {
     CUtensorMap mh, ml;
   };
   bool use_tc = false;
+  bool fused_tc = true;   // TCN_NO_FUSED_TC=1: previous forward schedule (A/B)
   std::map<long, TcW> tcw;
   std::map<std::pair<const float*, int>, CUtensorMap> xmaps;
   std::map<std::pair<const float*, int>, CUtensorMap> xmaps32;  // same tensors, 32-row boxes (slab kernel)
@@ -428,6 +429,7 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
     e = cudaMemcpy(m->sjobs_dev, sjobs.data(), sjobs.size() * sizeof(SplitJob), cudaMemcpyHostToDevice);
   // tcgen05 path available? (needs the driver's tensor-map encoder; TCN_NO_TCGEN05=1 forces the mma.sync kernels)
   m->use_tc = (std::getenv("TCN_NO_TCGEN05") == nullptr) && (C % 4 == 0);
+  m->fused_tc = std::getenv("TCN_NO_FUSED_TC") == nullptr;
   if (m->use_tc) {
     for (auto& kv : m->tcw) {
       tcn_model::TcW& w = kv.second;
@@ -589,7 +591,34 @@ static int model_forward(tcn_model* m, const float* x, long x_rows, int training
     layer_shifts(m, l, s);
     // one wave of tiles or less: the fused mma.sync kernel has the shorter latency; beyond that two tcgen05 launches
     // (conv3 + ReLU -> h, 1x1 + dropout + residual -> y) move more frames per second
-    if (C == 64 && !(m->use_tc && m->max_blk > 2 * num_sms())) {
+    if (C == 64 && m->use_tc && m->fused_tc) {
+      // one tcgen05 launch: conv3 accumulates in TMEM, bias + ReLU on the accumulator, h re-enters the 1x1 conv as a
+      // TMEM A operand (gemm_tc.cu: layer_fwd_tc_kernel)
+      const long k1 = reinterpret_cast<const float*>(m->wf_(m->wf_w1[l])) - m->wf;
+      const long k2 = reinterpret_cast<const float*>(m->wf_(m->wf_w2[l])) - m->wf;
+      auto w1 = m->tcw.find(k1), w2 = m->tcw.find(k2);
+      TCN_REQUIRE(w1 != m->tcw.end() && w2 != m->tcw.end(), "tcn_model forward: missing split weights for the fused layer");
+      const auto xkey = std::make_pair((const float*)m->act[l], C);
+      auto xm = m->xmaps.find(xkey);
+      if (xm == m->xmaps.end()) {
+        CUtensorMap map;
+        TCN_CHECK(make_tensor_map_2d(&map, m->act[l], m->cfg.max_rows, C, C, TC_BM));
+        xm = m->xmaps.emplace(xkey, map).first;
+      }
+      LayerTcDev p;
+      memset(&p, 0, sizeof(p));
+      p.h.Y = save_h ? m->H[l] : nullptr; p.h.ldy = C; p.h.N = C; p.h.bias = m->p_(m->off_b1[l]); p.h.relu = 1;
+      p.h.drop_scale = 1.f; p.h.in_drop_scale = 1.f;
+      p.y.Y = m->act[l + 1]; p.y.ldy = C; p.y.N = C; p.y.bias = m->p_(m->off_b2[l]); p.y.R = m->act[l]; p.y.ldr = C;
+      p.y.meta = m->meta; p.y.nblk = m->max_blk; p.y.dyn = m->desc; p.y.ntaps = 3; p.y.kbp = 2; p.y.c_in = C;
+      for (int i = 0; i < 3; ++i) p.y.shift[i] = s[i];
+      p.y.in_drop_scale = 1.f;
+      p.y.drop_thresh = pl > 0.f ? drop_thresh(pl) : 0u;
+      p.y.drop_scale = pl > 0.f ? 1.f / (1.f - pl) : 1.f;
+      p.y.drop_seed = 0u; p.y.drop_stream = (uint32_t)l;
+      TCN_CHECK(launch_layer_fwd_tc(xm->second, w1->second.mh, w1->second.ml, w2->second.mh, w2->second.ml, p, m->max_blk,
+                                    st));
+    } else if (C == 64 && !(m->use_tc && m->max_blk > 2 * num_sms())) {
       LayerFwdDev p;
       p.X = m->act[l]; p.Y = m->act[l + 1]; p.H = save_h ? m->H[l] : nullptr;
       p.W1f = m->wf_(m->wf_w1[l]); p.W2f = m->wf_(m->wf_w2[l]);

@@ -3,6 +3,7 @@ built from them.  All tensors are fp32 CUDA tensors in the packed time-major lay
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -107,6 +108,27 @@ def layer_fwd(x, w1f, w2f, b1, b2, lay: SeqLayout, shifts, save_h=True, drop_p=0
         a.shift[i] = int(s)
     a.drop_p, a.drop_seed, a.drop_stream = float(drop_p), int(seed) & 0xFFFFFFFF, int(stream_id) & 0xFFFFFFFF
     _lib.check(lib.tcn_layer_fwd(C.byref(a), _lib.stream_ptr()), "tcn_layer_fwd")
+    return y, h
+
+
+def layer_fwd_tc(x, w1, w2, b1, b2, lay: SeqLayout, shifts, save_h=True, drop_p=0.0, seed=0, stream_id=0):
+    """Fused residual layer forward on tcgen05 / TMEM (64 channels): returns (y, h).  w1 (64, 64, 3), w2 (64, 64, 1)
+    are the torch weights (split into TF32 hi / lo halves here)."""
+    lib = _lib.load()
+    assert x.is_contiguous() and x.shape[1] == 64
+    y = torch.zeros_like(x)
+    h = torch.zeros_like(x) if save_h else None
+    w1h, w1l = split_weight(w1)
+    w2h, w2l = split_weight(w2)
+    a = _lib.LayerFwdTcArgs()
+    a.x, a.x_rows, a.y, a.h = _lib.ptr(x), x.shape[0], _lib.ptr(y), _lib.ptr(h)
+    a.w1_hi, a.w1_lo, a.w2_hi, a.w2_lo = _lib.ptr(w1h), _lib.ptr(w1l), _lib.ptr(w2h), _lib.ptr(w2l)
+    a.b1, a.b2 = _lib.ptr(b1), _lib.ptr(b2)
+    a.meta, a.nblk, a.channels = _lib.ptr(lay.meta), lay.nblk, x.shape[1]
+    for i, s in enumerate(shifts):
+        a.shift[i] = int(s)
+    a.drop_p, a.drop_seed, a.drop_stream = float(drop_p), int(seed) & 0xFFFFFFFF, int(stream_id) & 0xFFFFFFFF
+    _lib.check(lib.tcn_layer_fwd_tc(C.byref(a), _lib.stream_ptr()), "tcn_layer_fwd_tc")
     return y, h
 
 
@@ -277,7 +299,9 @@ class DilatedResidualFn(torch.autograd.Function):
         x = _f32c(x)
         Cc = w1.shape[0]
         shifts = tap_shifts(dilation, causal)
-        if Cc == 64:  # one fused launch
+        if Cc == 64 and os.environ.get("TCN_NO_TCGEN05") is None:  # one fused launch, tcgen05 / TMEM
+            y, h = layer_fwd_tc(x, w1, w2, _f32c(b1.detach()), _f32c(b2.detach()), lay, shifts, True, p, seed, stream_id)
+        elif Cc == 64:  # one fused launch, mma.sync
             y, h = layer_fwd(x, prep_weight(w1), prep_weight(w2), _f32c(b1.detach()), _f32c(b2.detach()), lay, shifts,
                              True, p, seed, stream_id)
         else:

@@ -147,6 +147,18 @@ typedef struct {
   float drop_p; unsigned drop_seed; unsigned drop_stream;
 } tcn_layer_fwd_args;
 int tcn_layer_fwd(const tcn_layer_fwd_args* args, tcn_stream_t stream);
+/* The same layer on tcgen05 / TMA / TMEM (csrc/gemm_tc.cu: layer_fwd_tc_kernel): the dilated conv accumulates in
+ * tensor memory, bias + ReLU run on the accumulator, and h re-enters the 1x1 conv as a TMEM A operand.  Weights as
+ * written by tcn_split_weight (transpose = 0) for (64, 64, 3) and (64, 64, 1); x_rows = rows of the x buffer. */
+typedef struct {
+  const float* x; long long x_rows; float* y; float* h;
+  const float* w1_hi; const float* w1_lo; const float* w2_hi; const float* w2_lo;
+  const float* b1; const float* b2;
+  const int* meta; int nblk; int channels;
+  int shift[3];
+  float drop_p; unsigned drop_seed; unsigned drop_stream;
+} tcn_layer_fwd_tc_args;
+int tcn_layer_fwd_tc(const tcn_layer_fwd_tc_args* args, tcn_stream_t stream);
 
 /* ---- whole-model executor -------------------------------------------------------------------------
  * VideoNas(fpn) of network.py:14-68 (BaseCausalTCN -> num_r x Refinement -> FPN -> 4 heads x 4 levels)

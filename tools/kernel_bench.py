@@ -78,6 +78,28 @@ def main():
             print(json.dumps({"kernel": "layer_fwd64", "shape": name, "dilation": d, "ms": round(ms, 4),
                               "alg_GBps": round(gbs, 1), "frac_hbm": round(gbs / PEAK, 4),
                               "executed_TFLOPs_3xtf32": round(tf, 1)}))
+            w1h, w1l = ops.split_weight(w1)
+            w2h, w2l = ops.split_weight(w2)
+
+            def fused_tc():
+                i = it[0] % nbuf
+                it[0] += 1
+                a = _lib.LayerFwdTcArgs()
+                a.x, a.x_rows, a.y, a.h = xs[i].data_ptr(), xs[i].shape[0], ys[i].data_ptr(), hs[i].data_ptr()
+                a.w1_hi, a.w1_lo, a.w2_hi, a.w2_lo = w1h.data_ptr(), w1l.data_ptr(), w2h.data_ptr(), w2l.data_ptr()
+                a.b1, a.b2 = b.data_ptr(), b.data_ptr()
+                a.meta, a.nblk, a.channels = lay.meta.data_ptr(), lay.nblk, C
+                for k, s in enumerate(shifts):
+                    a.shift[k] = s
+                a.drop_p, a.drop_seed, a.drop_stream = 0.5, 1, 2
+                _lib.check(lib.tcn_layer_fwd_tc(Ct.byref(a), _lib.stream_ptr()))
+
+            ms = timeit(fused_tc)
+            gbs = 12 * C * frames / ms / 1e6   # read x, write h, write y
+            tf = 8 * C * C * frames * 3 / ms / 1e9
+            print(json.dumps({"kernel": "layer_fwd_tc (tcgen05, h via TMEM)", "shape": name, "dilation": d,
+                              "ms": round(ms, 4), "alg_GBps": round(gbs, 1), "frac_hbm": round(gbs / PEAK, 4),
+                              "executed_TFLOPs_3xtf32": round(tf, 1)}))
         # backward pieces of one layer (d = 16)
         shifts = (-16, 0, 16)
         it = [0]

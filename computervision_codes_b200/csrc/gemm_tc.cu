@@ -244,6 +244,64 @@ __device__ __forceinline__ void epilogue_block32(const float (&v)[32], float4* s
   __syncwarp();
 }
 
+// Same 32 x 32 block epilogue with the feature set read from `p` at run time (bias / ReLU / ReLU-mask / dropout /
+// residual), plus the scalar path for ragged column counts.  Used by the persistent kernels, whose eight epilogue warps
+// each own one TMEM lane quadrant x 32 columns.
+__device__ __forceinline__ void epilogue_block32_rt(const float (&v)[32], float4* st, int lane, int row_base, int row_hi,
+                                                    int n_base, const GemmTcDev& p, uint32_t out_seed, bool vec_ok) {
+  if (n_base >= p.N) return;  // warp-uniform
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    st[lane * 8 + (c ^ (lane & 7))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+  __syncwarp();
+  const int c = lane & 7, n = n_base + c * 4;
+  if (vec_ok && n_base + 32 <= p.N) {
+    float4 mk[8], rr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rowc = min(row_base + i * 4 + (lane >> 3), row_hi - 1);  // clamp: loads stay in bounds
+      if (p.M != nullptr) mk[i] = *reinterpret_cast<const float4*>(p.M + (size_t)rowc * p.ldm + n);
+      if (p.R != nullptr) rr[i] = *reinterpret_cast<const float4*>(p.R + (size_t)rowc * p.ldr + n);
+    }
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    const uint32_t th = p.drop_thresh;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3), row = row_base + r;
+      const float4 a = st[r * 8 + (c ^ (r & 7))];
+      float o[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
+      if (p.relu) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+      }
+      if (p.M != nullptr) {
+        if (!(mk[i].x > 0.f)) o[0] = 0.f;
+        if (!(mk[i].y > 0.f)) o[1] = 0.f;
+        if (!(mk[i].z > 0.f)) o[2] = 0.f;
+        if (!(mk[i].w > 0.f)) o[3] = 0.f;
+      }
+      if (th != 0u) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] *= drop_factor(out_seed, p.drop_stream, th, p.drop_scale, row, n + e);
+      }
+      if (p.R != nullptr) { o[0] += rr[i].x; o[1] += rr[i].y; o[2] += rr[i].z; o[3] += rr[i].w; }
+      if (row < row_hi) *reinterpret_cast<float4*>(p.Y + (size_t)row * p.ldy + n) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  } else {
+#pragma unroll 2
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3), row = row_base + r;
+      const float4 a = st[r * 8 + (c ^ (r & 7))];
+      if (row < row_hi) {
+        float o[4] = {a.x, a.y, a.z, a.w};
+        epilogue_vec4(o, row, n, p, out_seed, vec_ok);
+      }
+    }
+  }
+  __syncwarp();
+}
+
 template <int BN>
 struct TcSmem {
   static constexpr int kStages = BN > 64 ? 3 : 4;
@@ -395,8 +453,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 // 128-frame tiles; the split weights stay resident in shared memory, the accumulator is double-buffered in
 // TMEM, and four dedicated epilogue warps drain tile i while the producer / split / MMA warps are already
 // working on tile i + 1.
-//   warp 0: TMA producer | warp 1: MMA issuer + TMEM owner | warps 2-5: operand split | warps 6-9: epilogue
-constexpr int TP_THREADS = 320;
+//   warp 0: TMA producer | warp 1: MMA issuer + TMEM owner | warps 2-5: operand split | warps 6-13: epilogue
+constexpr int TP_THREADS = 448;   // TMA, MMA, 4 x operand split, 8 x epilogue (lane quadrant x 32-column half)
 constexpr int TP_STAGES = 3;
 constexpr int TP_MAX_KB = 6;
 constexpr int TP_KA = TC_BM * TC_BK * 4;  // 16384: one A tile
@@ -436,7 +494,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 128);
+      mbar_init(&tempty[a], 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -540,8 +598,8 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       }
     }
   } else {
-    // ===================== epilogue (warps 6..9; TMEM lane quadrant = warp % 4) =====================
-    const int q = warp & 3;
+    // ===================== epilogue (warps 6..13; TMEM lane quadrant = warp % 4, 32-column half) ================
+    const int q = warp & 3, half = (warp - 6) >> 2;
     const uint32_t out_seed = p.drop_seed ^ dseed;
     const bool vec_ok = ((p.ldy & 3) == 0) && (p.R == nullptr || (p.ldr & 3) == 0) && (p.M == nullptr || (p.ldm & 3) == 0);
     int tcount = 0;
@@ -553,14 +611,13 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       const uint32_t tph = (tcount >> 1) & 1;
       mbar_wait(&tfull[a], tph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * 64;
-      float v0[32], v1[32];
-      tmem_ld32(taddr, v0);
-      tmem_ld32(taddr + 32, v1);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * 64 + half * 32;
+      float v[32];
+      tmem_ld32(taddr, v);
       tc_fence_before();
       mbar_arrive(&tempty[a]);  // the MMA warp may overwrite this accumulator
-      epilogue_block_coalesced(v0, v1, epi + (warp - 6) * 512, lane, row0 + q * 32, m.hi, ntile * 64, p, out_seed,
-                               vec_ok);
+      epilogue_block32_rt(v, epi + (warp - 6) * 256, lane, row0 + q * 32, m.hi, ntile * 64 + half * 32, p, out_seed,
+                          vec_ok);
       ++tcount;
     }
   }
@@ -587,8 +644,10 @@ struct TwSmem {
   static constexpr int kBytes = kStages * kStage + TP_EPI + 1024 + 256;
 };
 
+constexpr int TW_THREADS = 320;   // TMA, MMA, 4 x operand split, 4 x epilogue
+
 template <int BN>
-__global__ void __launch_bounds__(TP_THREADS, 1)
+__global__ void __launch_bounds__(TW_THREADS, 1)
 gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                     const __grid_constant__ CUtensorMap map_wlo, const GemmTcDev p) {
   extern __shared__ uint8_t smem_raw[];
@@ -778,7 +837,7 @@ static int launch_wide(const CUtensorMap& mx, const CUtensorMap& mwhi, const CUt
   }
   const long tiles = (long)nb * ((p.N + BN - 1) / BN);
   const int gx = (int)(tiles < num_sms() ? tiles : num_sms());
-  launch_kernel(gemm_tc_wide_kernel<BN>, dim3(gx), dim3(TP_THREADS), TwSmem<BN>::kBytes, stream, true, mx, mwhi, mwlo, p);
+  launch_kernel(gemm_tc_wide_kernel<BN>, dim3(gx), dim3(TW_THREADS), TwSmem<BN>::kBytes, stream, true, mx, mwhi, mwlo, p);
   return check_launch("gemm_tc_wide_kernel");
 }
 
@@ -1149,7 +1208,7 @@ gemm_tc_slab_kernel(const __grid_constant__ CUtensorMap map_x32, const __grid_co
       mbar_init(&ready_bar[s], 128);
       mbar_init(&empty_bar[s], 1);
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 128);
+      mbar_init(&tempty[s], 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -1271,8 +1330,8 @@ gemm_tc_slab_kernel(const __grid_constant__ CUtensorMap map_x32, const __grid_co
       }
     }
   } else {
-    // ===================== epilogue (warps 6..9) =====================
-    const int q = warp & 3;
+    // ===================== epilogue (warps 6..13: TMEM lane quadrant x 32-column half) =====================
+    const int q = warp & 3, half = (warp - 6) >> 2;
     const uint32_t out_seed = p.drop_seed ^ dseed;
     const bool vec_ok = ((p.ldy & 3) == 0) && (p.R == nullptr || (p.ldr & 3) == 0) && (p.M == nullptr || (p.ldm & 3) == 0);
     int tcount = 0;
@@ -1284,14 +1343,13 @@ gemm_tc_slab_kernel(const __grid_constant__ CUtensorMap map_x32, const __grid_co
       const uint32_t tph = (tcount >> 1) & 1;
       mbar_wait(&tfull[a], tph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * 64;
-      float v0[32], v1[32];
-      tmem_ld32(taddr, v0);
-      tmem_ld32(taddr + 32, v1);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * 64 + half * 32;
+      float v[32];
+      tmem_ld32(taddr, v);
       tc_fence_before();
       mbar_arrive(&tempty[a]);
-      epilogue_block_coalesced(v0, v1, epi + (warp - 6) * 512, lane, row0 + q * 32, m.hi, ntile * 64, p, out_seed,
-                               vec_ok);
+      epilogue_block32_rt(v, epi + (warp - 6) * 256, lane, row0 + q * 32, m.hi, ntile * 64 + half * 32, p, out_seed,
+                          vec_ok);
       ++tcount;
     }
   }

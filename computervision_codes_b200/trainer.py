@@ -112,6 +112,8 @@ class TemporalTrainer:
         self.lab_slots = [torch.zeros(max_frames, self.ex.ld_logits, device=dev, dtype=torch.uint8) for _ in range(2)]
         self.slot = 0
         self.copy_stream = torch.cuda.Stream(device=dev)
+        self.copy_stream2 = torch.cuda.Stream(device=dev)
+        self.slot_ready2 = [torch.cuda.Event(), torch.cuda.Event()]
         self.slot_free = [torch.cuda.Event(), torch.cuda.Event()]   # compute finished reading the slot
         self.slot_ready = [torch.cuda.Event(), torch.cuda.Event()]  # copy into the slot finished
         self._prefetched = None
@@ -172,13 +174,31 @@ class TemporalTrainer:
         return lay
 
     def prefetch(self, x_rows, labels_u8, lengths):
-        """Stage the NEXT step's batch into the idle input slot on the copy stream; the following step() call
-        (without arguments) consumes it.  Lets the H2D copy of step i + 1 overlap the kernels of step i."""
+        """Stage the NEXT step's batch into the idle input slot on the copy streams; the following step() call
+        (without arguments) consumes it.  Lets the H2D copy of step i + 1 overlap the kernels of step i.  The
+        per-video copies alternate between two copy streams so that the set-up latency of one transfer hides behind
+        the payload of the other (a single stream reaches ~42 GB/s on 16 MB transfers, the link does ~54 GB/s)."""
         nxt = self.slot ^ 1
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(self.slot_free[nxt])
-            lay = self._stage(nxt, x_rows, labels_u8, lengths)
-            self.slot_ready[nxt].record(self.copy_stream)
+        lay = SeqLayout.get(lengths, self.ex.device)
+        assert lay.frames <= self.max_frames
+        xs = x_rows if isinstance(x_rows, (list, tuple)) else [x_rows]
+        ls = labels_u8 if isinstance(labels_u8, (list, tuple)) else [labels_u8]
+        streams = (self.copy_stream, self.copy_stream2)
+        for st in streams:
+            st.wait_event(self.slot_free[nxt])
+        off = 0
+        for i, x in enumerate(xs):
+            with torch.cuda.stream(streams[i & 1]):
+                self.x_slots[nxt][off:off + x.shape[0]].copy_(x, non_blocking=True)
+            off += x.shape[0]
+        assert off == lay.frames
+        off = 0
+        for i, lab in enumerate(ls):
+            with torch.cuda.stream(streams[(i + 1) & 1]):
+                self.lab_slots[nxt][off:off + lab.shape[0], :lab.shape[1]].copy_(lab, non_blocking=True)
+            off += lab.shape[0]
+        self.slot_ready[nxt].record(self.copy_stream)
+        self.slot_ready2[nxt].record(self.copy_stream2)
         self._prefetched = (nxt, lay)
 
     def step(self, x_rows=None, labels_u8=None, lengths=None):
@@ -191,6 +211,7 @@ class TemporalTrainer:
             slot, lay = self._prefetched
             self._prefetched = None
             cur.wait_event(self.slot_ready[slot])
+            cur.wait_event(self.slot_ready2[slot])
         else:
             slot = self.slot ^ 1 if self._prefetched is None else self.slot  # never the slot a prefetch is filling
             if self._prefetched is not None and self._prefetched[0] == slot:

@@ -183,7 +183,7 @@ def main():
     config = {"workload": "cfg2: 5-fold epoch schedule over 45 synthetic CholecT45-shaped videos "
                           "(ragged 900..3600 frames, seed 45), VideoNas(fpn, 11/10/3, C=64, D=2048, heads 100/6/10/15), "
                           "tenco BCE loss, SGD(lr 1e-2, wd 1e-5)",
-              "videos_per_rank_per_step": a.videos_per_step, "parallelism": f"dp{world}-by-video",
+              "videos_per_rank_per_step": a.videos_per_step, "parallelism": f"dp{world}-by-video, videos of a global step assigned longest-first (LPT), equal count per rank",
               "l2": "inputs cycle through the 0.8 GB feature set (>> 126 MB L2); no explicit flush"}
 
     if a.impl == "reference":
@@ -219,10 +219,15 @@ def main():
                               max_frames=max_frames, max_seqs=max(V, 1), use_graph=not a.no_graph,
                               input_mask_p=0.25)  # --mask of Scripts/train_fold1.sh:28
 
-    mine = passes[rank::world]
     nsteps_total = a.warmup + a.steps
-    # batches this rank will run (cycled over its shard of the schedule)
-    batches = [[mine[(s * V + j) % len(mine)] for j in range(V)] for s in range(nsteps_total)]
+    # Global step s takes the next V * world passes of the schedule (cycled) and assigns them to the ranks
+    # longest-first, V videos each (length-balanced DP by video).  Every rank computes the same table.
+    from computervision_codes_b200.trainer import lpt_assign
+    batches = []
+    for s in range(nsteps_total):
+        vids = [passes[(s * V * world + j) % len(passes)] for j in range(V * world)]
+        shard = lpt_assign([lengths[v] for v in vids], world, cap=V)[rank]
+        batches.append([vids[i] for i in shard])
     needed = sorted({v for b in batches for v in b})
     host = {v: make_video(v, lengths[v], pinned=True) for v in needed}
     resident = {v: (x.to(dev), lab.to(dev)) for v, (x, lab) in host.items()}

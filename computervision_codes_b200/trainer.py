@@ -67,13 +67,16 @@ class TemporalTrainerEager:
         return out
 
 
-def lpt_assign(lengths, world):
-    """Longest-processing-time-first assignment of videos to ranks (balances frames per rank)."""
+def lpt_assign(lengths, world, cap=None):
+    """Longest-processing-time-first assignment of videos to ranks (balances frames per rank).
+    cap: at most this many videos per rank (equal counts keep "mean over ranks of the per-rank mean" == mean over all
+    videos)."""
     order = sorted(range(len(lengths)), key=lambda i: -lengths[i])
     loads = [0] * world
     shards = [[] for _ in range(world)]
     for i in order:
-        r = min(range(world), key=lambda k: loads[k])
+        open_ranks = [k for k in range(world) if cap is None or len(shards[k]) < cap]
+        r = min(open_ranks, key=lambda k: loads[k])
         shards[r].append(i)
         loads[r] += lengths[i]
     return shards

@@ -209,6 +209,14 @@ struct WgradTcDev {
 };
 // mx / mg: maps built with make_tensor_map_2d(..., WG_BOX_ROWS, /*atom32=*/true)
 int launch_wgrad_tc(const CUtensorMap& mx, const CUtensorMap& mg, WgradTcDev& p, int cap_nblk, cudaStream_t stream);
+// Many independent weight-gradient problems in ONE launch (all residual layers of a stage): descriptors (tensor maps +
+// parameters, row_splits / cbn filled in by the caller) and the (problem, m-tile) table live in device memory.
+struct alignas(64) WgradMultiDesc {
+  CUtensorMap mx, mg;
+  WgradTcDev p;
+};
+int launch_wgrad_tc_multi(const WgradMultiDesc* descs_dev, const int2* tiles_dev, int ntiles, int row_splits,
+                          cudaStream_t stream);
 int launch_wgrad_tc_pair(const CUtensorMap& mx0, const CUtensorMap& mg0, WgradTcDev& p0, const CUtensorMap& mx1,
                          const CUtensorMap& mg1, WgradTcDev& p1, int cap_nblk, cudaStream_t stream);
 

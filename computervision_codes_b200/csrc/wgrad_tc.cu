@@ -380,6 +380,32 @@ int launch_wgrad_tc(const CUtensorMap& mx, const CUtensorMap& mg, WgradTcDev& p,
   return launch_wgrad_tc_n<2>(mx, mg, p, nb, stream);
 }
 
+// blockIdx.y -> (problem, m-tile) through a device table; tensor maps are read from global memory
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_multi_kernel(const WgradMultiDesc* __restrict__ descs, const int2* __restrict__ tiles) {
+  const int2 t = tiles[blockIdx.y];
+  const WgradMultiDesc& d = descs[t.x];
+  wgrad_tc_body<2>(&d.mx, &d.mg, d.p, blockIdx.x, t.y, 0);
+}
+
+int launch_wgrad_tc_multi(const WgradMultiDesc* descs_dev, const int2* tiles_dev, int ntiles, int row_splits,
+                          cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e =
+        cudaFuncSetAttribute(wgrad_tc_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<2>::kBytes);
+    if (e != cudaSuccess) {
+      set_error("wgrad_tc_multi: smem attribute: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return TCN_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  launch_kernel(wgrad_tc_multi_kernel, dim3(row_splits, ntiles, 1), dim3(TC_THREADS), WgSmem<2>::kBytes, stream, true,
+                descs_dev, tiles_dev);
+  return check_launch("wgrad_tc_multi_kernel");
+}
+
 int launch_wgrad_tc_pair(const CUtensorMap& mx0, const CUtensorMap& mg0, WgradTcDev& p0, const CUtensorMap& mx1,
                          const CUtensorMap& mg1, WgradTcDev& p1, int cap_nblk, cudaStream_t stream) {
   static bool attr_set = false;

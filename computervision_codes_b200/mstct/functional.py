@@ -9,6 +9,12 @@ from .. import _lib
 from ..layout import SeqLayout
 
 
+def _like(x, lay):
+    """Output buffer shaped like x: the kernels write every frame of every sequence, so zero-filling is needed only
+    when the layout has padding rows."""
+    return torch.empty_like(x) if lay.frames == lay.rows else torch.zeros_like(x)
+
+
 def _c(t):
     t = t if t.dtype == torch.float32 else t.float()
     return t if t.is_contiguous() else t.contiguous()
@@ -20,7 +26,7 @@ class LayerNormFn(torch.autograd.Function):
         lib = _lib.load()
         x = _c(x)
         rows, Cc = x.shape
-        y = torch.zeros_like(x)
+        y = _like(x, lay)
         mean = torch.empty(rows, device=x.device, dtype=torch.float32)
         rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
         w, b = _c(weight.detach()), _c(bias.detach())
@@ -37,7 +43,7 @@ class LayerNormFn(torch.autograd.Function):
         x, w, mean, rstd = ctx.saved_tensors
         gy = _c(gy)
         rows, Cc = x.shape
-        dx = torch.zeros_like(x)
+        dx = _like(x, ctx.lay)
         dg = torch.zeros(Cc, device=x.device, dtype=torch.float32)
         db = torch.zeros(Cc, device=x.device, dtype=torch.float32)
         _lib.check(lib.tcn_layernorm_bwd(_lib.ptr(x), Cc, _lib.ptr(gy), Cc, _lib.ptr(dx), Cc, _lib.ptr(w),
@@ -76,7 +82,7 @@ class AttentionFn(torch.autograd.Function):
     def forward(ctx, q, kv, lay, heads):
         lib = _lib.load()
         q, kv = _c(q), _c(kv)
-        o = torch.zeros_like(q)
+        o = _like(q, lay)
         lse = torch.zeros(q.shape[0], heads, device=q.device, dtype=torch.float32)
         a = _attn_args(q, kv, o, lse, lay, heads)
         _lib.check(lib.tcn_attn_fwd(C.byref(a), _lib.stream_ptr()), "tcn_attn_fwd")
@@ -89,7 +95,7 @@ class AttentionFn(torch.autograd.Function):
         lib = _lib.load()
         q, kv, o, lse = ctx.saved_tensors
         go = _c(go)
-        dq, dkv = torch.zeros_like(q), torch.zeros_like(kv)
+        dq, dkv = _like(q, ctx.lay), _like(kv, ctx.lay)
         delta = torch.empty_like(lse)
         a = _attn_args(q, kv, o, lse, ctx.lay, ctx.heads, go, dq, dkv, delta)
         _lib.check(lib.tcn_attn_bwd(C.byref(a), _lib.stream_ptr()), "tcn_attn_bwd")
@@ -109,7 +115,7 @@ class DwConvGeluFn(torch.autograd.Function):
         x = _c(x)
         rows, Cc = x.shape
         w, b = _c(weight.detach()).view(Cc, 3), _c(bias.detach())
-        y = torch.zeros_like(x)
+        y = _like(x, lay)
         _lib.check(lib.tcn_dwconv_gelu_fwd(_lib.ptr(x), _lib.ptr(y), _lib.ptr(w), _lib.ptr(b), _lib.ptr(lay.meta), rows,
                                            Cc, _lib.stream_ptr()), "tcn_dwconv_gelu_fwd")
         ctx.save_for_backward(x, w, b)
@@ -122,7 +128,7 @@ class DwConvGeluFn(torch.autograd.Function):
         x, w, b = ctx.saved_tensors
         gy = _c(gy)
         rows, Cc = x.shape
-        du, dx = torch.zeros_like(x), torch.zeros_like(x)
+        du, dx = _like(x, ctx.lay), _like(x, ctx.lay)
         dw = torch.zeros(Cc, 3, device=x.device, dtype=torch.float32)
         db = torch.zeros(Cc, device=x.device, dtype=torch.float32)
         _lib.check(lib.tcn_dwconv_gelu_bwd(_lib.ptr(x), _lib.ptr(gy), _lib.ptr(du), _lib.ptr(dx), _lib.ptr(w),

@@ -18,6 +18,14 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------ raw launches
+def _rows_out(lay: SeqLayout, cols: int, device, written_cols=None) -> torch.Tensor:
+    """Output buffer (lay.rows, cols).  The kernels write the frames of every sequence and nothing else, so the
+    buffer is zero-filled only when the layout has padding rows or the kernel leaves pad columns untouched."""
+    if lay.frames == lay.rows and (written_cols is None or written_cols == cols):
+        return torch.empty(lay.rows, cols, device=device, dtype=torch.float32)
+    return torch.zeros(lay.rows, cols, device=device, dtype=torch.float32)
+
+
 def prep_weight(w: torch.Tensor, transpose: bool = False) -> torch.Tensor:
     """torch Conv1d / Linear weight (n_out, c_in[, ntaps]) -> fragment-ordered hi/lo buffer."""
     lib = _lib.load()
@@ -39,7 +47,7 @@ def tapgemm(x, wf, lay: SeqLayout, c_in, n_out, shifts=(0,), bias=None, out=None
     if ldy is None:
         ldy = round_up(n_out, 4)
     if out is None:
-        out = torch.zeros(lay.rows, ldy, device=x.device, dtype=torch.float32)
+        out = _rows_out(lay, ldy, x.device, written_cols=n_out)
     a = _lib.TapGemmArgs()
     a.x, a.ldx, a.x_unpadded = _lib.ptr(x), x.shape[1], int(x_unpadded)
     a.colscale, a.colscale_ld = _lib.ptr(colscale), (colscale.shape[1] if colscale is not None else 0)
@@ -158,7 +166,7 @@ def gemm_tc(x, w_hi, w_lo, lay: SeqLayout, c_in, n_out, shifts=(0,), bias=None, 
     if ldy is None:
         ldy = round_up(n_out, 4)
     if out is None:
-        out = torch.zeros(lay.rows, ldy, device=x.device, dtype=torch.float32)
+        out = _rows_out(lay, ldy, x.device, written_cols=n_out)
     a = _lib.GemmTcArgs()
     a.x, a.ldx, a.x_rows, a.x_unpadded = _lib.ptr(x), x.shape[1], x.shape[0], int(x_unpadded)
     a.w_hi, a.w_lo, a.bias = _lib.ptr(w_hi), _lib.ptr(w_lo), _lib.ptr(bias)

@@ -224,3 +224,45 @@ def test_step_cached_reads_clips_from_the_gpu_resident_feature_cache():
         out.append((loss.clone(), tr.flat_p.clone()))
     # same frames, same seeds; fp32 atomics in the weight-gradient kernels make runs differ in the last bits only
     assert _maxabs(out[0][0], out[1][0]) <= 1e-5 and _maxabs(out[0][1], out[1][1]) <= 1e-5
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_executor_edge_lengths_one_frame_to_block_boundaries(causal):
+    """Ragged edge cases of the reference's zero padding: sequences of 1, 2 and 7 frames (every dilation tap of the
+    deeper layers falls outside the video), exactly one 128-frame block, one frame more, and a sequence shorter than
+    the largest dilation (d = 512 in an 11-layer stage).  Loss and every gradient against the fp64 oracle."""
+    from computervision_codes_b200.executor import ModelExecutor
+    from computervision_codes_b200.layout import SeqLayout
+    from computervision_codes_b200.tcn import VideoNas
+
+    torch.manual_seed(13)
+    D, heads = 32, (100, 6, 10, 15)
+    m = VideoNas(ARGS, 11, 3, 3, 64, D, 100, causal=causal).to(DEV)
+    sd64 = {k: v.detach().double().cpu() for k, v in m.state_dict().items()}
+    lengths = [1, 2, 7, 128, 129, 300]
+    g = torch.Generator().manual_seed(2)
+    xs = [torch.randn(T, D, generator=g) for T in lengths]
+    labs = [(torch.rand(T, 132, generator=g) < 0.1).to(torch.uint8) for T in lengths]
+    for lab in labs:
+        lab[:, 131] = 0
+    ref_total, ref_terms, ref_grads = _oracle_step(sd64, xs, labs, heads, causal=causal)
+    ex = ModelExecutor(m, max_rows=1280, max_seqs=8)
+    lay = SeqLayout.get(lengths, DEV)
+    ex.set_batch(lay, seed=1)
+    loss = ex.train_step(torch.cat(xs).to(DEV), torch.cat(labs).to(DEV), training=False).cpu()
+    assert abs(float(loss[4]) - ref_total) <= 1e-4 * abs(ref_total)
+    for name, p in m.named_parameters():
+        r = ref_grads[name]
+        if r is None:
+            continue
+        assert _maxabs(p.grad, r) <= 3e-5 * max(1.0, float(r.abs().max())) + 1e-6, (name, _maxabs(p.grad, r))
+    feats, logits = ex.forward(torch.cat(xs).to(DEV), training=False)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        for s, T in enumerate(lengths):
+            outs = O.videonas_forward(xs[s].double().unsqueeze(0), sd64, causal=causal)
+            r0 = lay.starts[s]
+            for lv in range(4):
+                got, ref = logits[lv][r0:r0 + T, :100].cpu(), outs[0][lv][0].t()
+                assert _maxabs(got, ref) <= 1e-3
+                assert torch.equal(got.argmax(1), ref.float().argmax(1))

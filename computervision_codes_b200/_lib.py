@@ -194,6 +194,8 @@ SIGNATURES = {
                           C.c_void_p]),
     "tcn_ce_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
                               C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
+    "tcn_ap_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                              C.c_void_p]),
     "tcn_dropout_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
                                     C.c_uint, C.c_uint, C.c_void_p]),
     "tcn_dropout_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_uint, C.c_uint, C.c_void_p]),

@@ -300,6 +300,67 @@ __global__ void __launch_bounds__(128) kd_attn_bwd_kernel(const KdAttnDev p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Per-class average precision of one video (the quantity ivtmetrics.Recognition.compute_video_AP takes from
+// sklearn.metrics.average_precision_score; call sites Temporal_tenco/run.py:257-269,428-450):
+//     AP_c = (1 / P_c) * sum over positives i of  #{j : y_j = 1, s_j >= s_i} / #{j : s_j >= s_i}
+// which is sklearn's step-wise sum over distinct thresholds, ties included.  s = sigmoid(logit) in fp32 when
+// apply_sigmoid (the reference ranks the fp32 sigmoid outputs, saturation ties included).  One CTA per class; scores
+// and labels of the class staged in shared memory in chunks; classes without a positive frame give NaN.
+constexpr int AP_THREADS = 256, AP_CHUNK = 4096;
+
+__global__ void __launch_bounds__(AP_THREADS) ap_rows_kernel(const float* __restrict__ logits, int ldl,
+                                                             const unsigned char* __restrict__ labels, int ldlab,
+                                                             int nrows, int apply_sigmoid, float* __restrict__ ap) {
+  __shared__ float ss[AP_CHUNK];
+  __shared__ unsigned char sy[AP_CHUNK];
+  __shared__ float red[AP_THREADS / 32];
+  __shared__ int redp[AP_THREADS / 32];
+  const int c = blockIdx.x;
+  auto score = [&](int r) {
+    const float x = logits[(size_t)r * ldl + c];
+    return apply_sigmoid ? 1.f / (1.f + expf(-x)) : x;
+  };
+  float acc = 0.f;   // sum of the precisions at this thread's positives
+  int npos = 0;
+  for (int i0 = 0; i0 < nrows; i0 += AP_THREADS) {     // every thread owns one candidate frame per sweep
+    const int i = i0 + threadIdx.x;
+    const bool mine = i < nrows && labels[(size_t)i * ldlab + c] != 0;
+    const float si = mine ? score(i) : 0.f;
+    int cnt = 0, pos = 0;
+    for (int j0 = 0; j0 < nrows; j0 += AP_CHUNK) {
+      __syncthreads();
+      for (int j = threadIdx.x; j < AP_CHUNK && j0 + j < nrows; j += AP_THREADS) {
+        ss[j] = score(j0 + j);
+        sy[j] = labels[(size_t)(j0 + j) * ldlab + c];
+      }
+      __syncthreads();
+      if (mine) {
+        const int n = min(AP_CHUNK, nrows - j0);
+        for (int j = 0; j < n; ++j) {
+          const bool ge = ss[j] >= si;
+          cnt += ge;
+          pos += ge && sy[j] != 0;
+        }
+      }
+    }
+    if (mine) {
+      acc += (float)pos / (float)cnt;
+      ++npos;
+    }
+  }
+  acc = warp_sum(acc);
+  for (int o = 16; o > 0; o >>= 1) npos += __shfl_xor_sync(0xffffffffu, npos, o);
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = acc; redp[threadIdx.x >> 5] = npos; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    int n = 0;
+    for (int w = 0; w < AP_THREADS / 32; ++w) { a += red[w]; n += redp[w]; }
+    ap[c] = n > 0 ? a / (float)n : __int_as_float(0x7fc00000);
+  }
+}
+
 int launch_bce(const BceDev& p, int cap_rows, cudaStream_t stream) {
   const long rows = cap_rows > 0 ? cap_rows : p.nrows;
   long b = (rows + 7) / 8;
@@ -439,4 +500,12 @@ extern "C" int tcn_kd_attn_bwd(const tcn_kd_attn_args* a, tcn_stream_t stream) {
   for (int n = 0; n < 3; ++n) TCN_REQUIRE(a->gz[n] && a->gtea[n], "tcn_kd_attn_bwd: null gradient pointer");
   kd_attn_bwd_kernel<<<(a->n_rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>(p);
   return check_launch("kd_attn_bwd_kernel");
+}
+
+extern "C" int tcn_ap_rows(const float* logits, int ldl, const unsigned char* labels, int ldlab, int nrows, int ncols,
+                           int apply_sigmoid, float* ap, tcn_stream_t stream) {
+  TCN_REQUIRE(logits && labels && ap && nrows > 0 && ncols > 0 && ldl >= ncols && ldlab >= ncols,
+              "tcn_ap_rows: bad arguments");
+  ap_rows_kernel<<<ncols, AP_THREADS, 0, (cudaStream_t)stream>>>(logits, ldl, labels, ldlab, nrows, apply_sigmoid, ap);
+  return check_launch("ap_rows_kernel");
 }

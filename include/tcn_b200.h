@@ -289,6 +289,16 @@ int tcn_dwconv_gelu_bwd(const float* x, const float* dy, float* du, float* dx, c
 /* y = a * x + b * y (residual sums of the Temporal_Mixer, TS_Mixer.py:66-76) */
 int tcn_axpby(float* y, const float* x, float a, float b, long long n, tcn_stream_t stream);
 
+/* ---- evaluation ------------------------------------------------------------------------------------
+ * Per-class average precision of ONE video on the device: what ivtmetrics.Recognition.compute_video_AP obtains from
+ * sklearn.metrics.average_precision_score for the frames logged by mAP.update / video_end
+ * (MT4MTLKD/Temporal_tenco/run.py:257-269, read at :428-450).  logits (nrows, ldl) fp32, labels (nrows, ldlab) uint8;
+ * apply_sigmoid != 0 ranks sigmoid(logit) in fp32 like the reference's `activation`; ap: ncols floats, NaN for a
+ * class without a positive frame.  ivtmetrics == 0.0.6 is not available here: parity with it is unpinned, the
+ * arithmetic is checked against sklearn's average_precision_score. */
+int tcn_ap_rows(const float* logits, int ldl, const unsigned char* labels, int ldlab, int nrows, int ncols,
+                int apply_sigmoid, float* ap, tcn_stream_t stream);
+
 /* ---- dropout / optimizer -----------------------------------------------------------------------
  * Counter-based dropout keyed by (seed, stream id, row, column): nn.Dropout() of the residual layers
  * (network.py:175,191) and Dropout2d over input channels (network.py:117,125-127). */

@@ -89,3 +89,27 @@ def test_feature_cache_views_and_label_packing():
     assert lens2 == [40, 75] and xs2[1].data_ptr() == cache.feats["02"].data_ptr()   # views, not copies
     with pytest.raises(AssertionError):
         cache.batch([("01", 30, 20)])
+
+
+def test_artefact_pickles_round_trip(tmp_path):
+    """f4: the k{fold}[_{task}]_{feats,pred}.pkl tables (dict video id -> float32 (T, D)) written here load with plain
+    pickle exactly like the reference's readers do (Spatial_cnn/dataloader.py:216-238), and back."""
+    import pickle
+
+    from computervision_codes_b200.evaluation import artefact_name, read_artefact, write_artefact
+
+    assert artefact_name(3, "feats") == "k3_feats.pkl" and artefact_name(1, "pred", "v") == "k1_v_pred.pkl"
+    g = np.random.default_rng(0)
+    table = {"01": torch.from_numpy(g.standard_normal((7, 5))), "12": g.standard_normal((3, 5))}
+    path = tmp_path / artefact_name(2, "feats", "i")
+    write_artefact(str(path), table)
+    with open(path, "rb") as fh:
+        raw = pickle.load(fh)
+    assert set(raw) == {"01", "12"} and raw["01"].dtype == np.float32 and raw["01"].shape == (7, 5)
+    assert np.allclose(raw["12"], table["12"].astype(np.float32))
+    back = read_artefact(str(path), device="cpu")
+    assert torch.equal(back["01"], table["01"].float())
+    cache = FeatureCache("cpu")
+    zeros = [np.zeros((7, k), dtype=np.int64) for k in (6, 10, 15, 100)]
+    cache.add_pickle(str(path), {"01": zeros}, drop_id_column=False)
+    assert len(cache) == 1 and cache.frames("01") == 7

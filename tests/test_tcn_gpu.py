@@ -371,3 +371,42 @@ def test_multi_teacher_feature_attention_matches_reference_golden(golden_dir, ta
         ref = z[f"{tag}.grad.{name}"]
         got = prm.grad.cpu().numpy()
         assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-8, name
+
+
+def test_video_ap_matches_sklearn_average_precision():
+    """f4: device per-video AP == sklearn.metrics.average_precision_score (the routine ivtmetrics calls) per class,
+    ties from a saturating fp32 sigmoid included; classes without positives are NaN and drop out of the means."""
+    import warnings
+
+    from sklearn.metrics import average_precision_score
+
+    from computervision_codes_b200.evaluation import VideoAP, video_ap
+
+    g = torch.Generator().manual_seed(5)
+    ap_meter = VideoAP(20)
+    per_video = []
+    for T in (1, 37, 5000):
+        logits = torch.randn(T, 20, generator=g) * 6
+        logits[:, 3] = torch.round(logits[:, 3])            # many exact ties
+        logits[:, 4] = logits[:, 4].abs() + 18.0            # sigmoid saturates to 1.0f: everything ties
+        y = (torch.rand(T, 20, generator=g) < 0.2).to(torch.uint8)
+        y[:, 7] = 0                                         # class absent from this video
+        got = video_ap(y.to(DEV), logits.to(DEV)).cpu().numpy()
+        s = torch.sigmoid(logits).numpy()
+        want = np.full(20, np.nan)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for c in range(20):
+                if y[:, c].any():
+                    want[c] = average_precision_score(y[:, c].numpy(), s[:, c])
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        assert np.nanmax(np.abs(got - want)) <= 2e-6, (T, np.nanmax(np.abs(got - want)))
+        per_video.append(want)
+        ap_meter.update(y.to(DEV), logits.to(DEV))
+        ap_meter.video_end()
+    res = ap_meter.compute_video_AP()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        classwise = np.nanmean(np.stack(per_video), axis=0)
+    assert np.allclose(res["AP"], classwise, atol=2e-6, equal_nan=True)
+    assert abs(res["mAP"] - np.nanmean(classwise)) <= 2e-6

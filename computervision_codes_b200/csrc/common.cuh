@@ -151,10 +151,13 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// Counter-based dropout RNG: one 32-bit hash per element, keyed by (seed, stream, row, col).
+// Counter-based dropout RNG keyed by (seed, stream, row, col).  ONE 32-bit hash serves a group of four consecutive
+// columns (col >> 2); column k of the group compares the hash rotated left by 8 k bits against the threshold, so each
+// column's decision is led by its own byte of the hash while the full 32-bit threshold resolution is kept.  The
+// epilogues and operand-split loops, which own four consecutive columns per thread, pay one hash per float4.
 // Forward and backward regenerate the same keep-mask from the same key; no mask tensor is stored.
-__host__ __device__ __forceinline__ uint32_t drop_hash(uint32_t seed, uint32_t stream, uint32_t row, uint32_t col) {
-  uint32_t h = seed ^ (stream * 0xC2B2AE3Du) ^ (row * 0x9E3779B1u) ^ (col * 0x85EBCA77u);
+__host__ __device__ __forceinline__ uint32_t drop_hash4(uint32_t seed, uint32_t stream, uint32_t row, uint32_t col4) {
+  uint32_t h = seed ^ (stream * 0xC2B2AE3Du) ^ (row * 0x9E3779B1u) ^ (col4 * 0x85EBCA77u);
   h ^= h >> 16;
   h *= 0x85EBCA6Bu;
   h ^= h >> 13;
@@ -165,6 +168,13 @@ __host__ __device__ __forceinline__ uint32_t drop_hash(uint32_t seed, uint32_t s
   h *= 0x2C1B3C6Du;
   h ^= h >> 12;
   return h;
+}
+__host__ __device__ __forceinline__ uint32_t drop_rotl(uint32_t h, uint32_t k) {  // rotate left by 8 k bits, k = 0..3
+  const uint32_t s = 8u * k;
+  return s ? ((h << s) | (h >> (32u - s))) : h;
+}
+__host__ __device__ __forceinline__ uint32_t drop_hash(uint32_t seed, uint32_t stream, uint32_t row, uint32_t col) {
+  return drop_rotl(drop_hash4(seed, stream, row, col >> 2), col & 3u);
 }
 // keep iff hash >= thresh, thresh = p * 2^32 (p = 0.5 -> 0x80000000)
 __host__ __device__ __forceinline__ uint32_t drop_thresh(float p) {
@@ -177,6 +187,16 @@ __host__ __device__ __forceinline__ uint32_t drop_thresh(float p) {
 __device__ __forceinline__ float drop_factor(uint32_t seed, uint32_t stream, uint32_t thresh, float scale, int row,
                                              int col) {
   return (drop_hash(seed, stream, (uint32_t)row, (uint32_t)col) >= thresh) ? scale : 0.f;
+}
+
+// the factors of four consecutive columns col .. col + 3, col a multiple of 4: one hash
+__device__ __forceinline__ void drop_factor4(uint32_t seed, uint32_t stream, uint32_t thresh, float scale, int row,
+                                             int col, float (&f)[4]) {
+  const uint32_t h = drop_hash4(seed, stream, (uint32_t)row, (uint32_t)col >> 2);
+  f[0] = h >= thresh ? scale : 0.f;
+  f[1] = drop_rotl(h, 1) >= thresh ? scale : 0.f;
+  f[2] = drop_rotl(h, 2) >= thresh ? scale : 0.f;
+  f[3] = drop_rotl(h, 3) >= thresh ? scale : 0.f;
 }
 
 // ----------------------------------------------------------------------------------------------

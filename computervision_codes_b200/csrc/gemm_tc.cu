@@ -53,10 +53,9 @@ __device__ __forceinline__ void split_tile(float4* __restrict__ xa, float4* __re
         v[i].x *= sc.x; v[i].y *= sc.y; v[i].z *= sc.z; v[i].w *= sc.w;
       }
       if (p.in_drop_thresh != 0u) {
-        v[i].x *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col);
-        v[i].y *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col + 1);
-        v[i].z *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col + 2);
-        v[i].w *= drop_factor(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col + 3);
+        float f[4];
+        drop_factor4(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col, f);
+        v[i].x *= f[0]; v[i].y *= f[1]; v[i].z *= f[2]; v[i].w *= f[3];
       }
     }
   }
@@ -94,8 +93,9 @@ __device__ __forceinline__ void epilogue_vec4(float (&o)[4], int row, int n, con
       if (!(mk.w > 0.f)) o[3] = 0.f;
     }
     if (p.drop_thresh != 0u) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] *= drop_factor(out_seed, p.drop_stream, p.drop_thresh, p.drop_scale, row, n + e);
+      float f[4];
+      drop_factor4(out_seed, p.drop_stream, p.drop_thresh, p.drop_scale, row, n, f);
+      o[0] *= f[0]; o[1] *= f[1]; o[2] *= f[2]; o[3] *= f[3];
     }
     if (p.R != nullptr) {
       const float4 rr = *reinterpret_cast<const float4*>(p.R + (size_t)row * p.ldr + n);
@@ -177,8 +177,9 @@ __device__ __forceinline__ void epilogue_block_coalesced(const float (&v0)[32], 
           if (!(mk[i].w > 0.f)) o[3] = 0.f;
         }
         if (th != 0u) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] *= drop_factor(out_seed, p.drop_stream, th, p.drop_scale, row, n + e);
+          float f[4];
+          drop_factor4(out_seed, p.drop_stream, th, p.drop_scale, row, n, f);
+          o[0] *= f[0]; o[1] *= f[1]; o[2] *= f[2]; o[3] *= f[3];
         }
         if (p.R != nullptr) { o[0] += rr[i].x; o[1] += rr[i].y; o[2] += rr[i].z; o[3] += rr[i].w; }
         if (row < row_hi)
@@ -233,9 +234,9 @@ __device__ __forceinline__ void epilogue_block32(const float (&v)[32], float4* s
     }
     if (DROP) {
       if (p.drop_thresh != 0u) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          o[e] *= drop_factor(out_seed, p.drop_stream, p.drop_thresh, p.drop_scale, row, n + e);
+        float f[4];
+        drop_factor4(out_seed, p.drop_stream, p.drop_thresh, p.drop_scale, row, n, f);
+        o[0] *= f[0]; o[1] *= f[1]; o[2] *= f[2]; o[3] *= f[3];
       }
     }
     if (RES) { o[0] += rr[i].x; o[1] += rr[i].y; o[2] += rr[i].z; o[3] += rr[i].w; }
@@ -282,8 +283,9 @@ __device__ __forceinline__ void epilogue_block32_rt(const float (&v)[32], float4
         if (!(mk[i].w > 0.f)) o[3] = 0.f;
       }
       if (th != 0u) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] *= drop_factor(out_seed, p.drop_stream, th, p.drop_scale, row, n + e);
+        float f[4];
+        drop_factor4(out_seed, p.drop_stream, th, p.drop_scale, row, n, f);
+        o[0] *= f[0]; o[1] *= f[1]; o[2] *= f[2]; o[3] *= f[3];
       }
       if (p.R != nullptr) { o[0] += rr[i].x; o[1] += rr[i].y; o[2] += rr[i].z; o[3] += rr[i].w; }
       if (row < row_hi) *reinterpret_cast<float4*>(p.Y + (size_t)row * p.ldy + n) = make_float4(o[0], o[1], o[2], o[3]);

@@ -231,17 +231,15 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
                   v[i].x *= sc.x; v[i].y *= sc.y; v[i].z *= sc.z; v[i].w *= sc.w;
                 }
                 if (p.x_drop_thresh != 0u) {
-                  v[i].x *= drop_factor(x_seed, p.x_drop_stream, p.x_drop_thresh, p.x_drop_scale, src, col);
-                  v[i].y *= drop_factor(x_seed, p.x_drop_stream, p.x_drop_thresh, p.x_drop_scale, src, col + 1);
-                  v[i].z *= drop_factor(x_seed, p.x_drop_stream, p.x_drop_thresh, p.x_drop_scale, src, col + 2);
-                  v[i].w *= drop_factor(x_seed, p.x_drop_stream, p.x_drop_thresh, p.x_drop_scale, src, col + 3);
+                  float f[4];
+                  drop_factor4(x_seed, p.x_drop_stream, p.x_drop_thresh, p.x_drop_scale, src, col, f);
+                  v[i].x *= f[0]; v[i].y *= f[1]; v[i].z *= f[2]; v[i].w *= f[3];
                 }
               } else if (p.g_drop_thresh != 0u) {
                 const int col = (ntile * NGA + (atom - 4)) * 32 + lc * 4;
-                v[i].x *= drop_factor(g_seed, p.g_drop_stream, p.g_drop_thresh, p.g_drop_scale, src, col);
-                v[i].y *= drop_factor(g_seed, p.g_drop_stream, p.g_drop_thresh, p.g_drop_scale, src, col + 1);
-                v[i].z *= drop_factor(g_seed, p.g_drop_stream, p.g_drop_thresh, p.g_drop_scale, src, col + 2);
-                v[i].w *= drop_factor(g_seed, p.g_drop_stream, p.g_drop_thresh, p.g_drop_scale, src, col + 3);
+                float f[4];
+                drop_factor4(g_seed, p.g_drop_stream, p.g_drop_thresh, p.g_drop_scale, src, col, f);
+                v[i].x *= f[0]; v[i].y *= f[1]; v[i].z *= f[2]; v[i].w *= f[3];
               }
             }
           }

@@ -206,23 +206,27 @@ __device__ __forceinline__ void epilogue_block_coalesced(const float (&v0)[32], 
 // buffer (XOR-swizzled 16-byte chunks: conflict-free both ways); every global access covers four full 128-byte row
 // segments per warp instruction.  Compile-time feature set, bias always on.  Used by the fused layer kernel, whose
 // epilogue warps each own 32 columns.
+// residual rows of a 32 x 32 block, loaded ahead of the accumulator (the L2 round trip overlaps the MMAs)
+__device__ __forceinline__ void epi32_load_residual(float4 (&rr)[8], int lane, int row_base, int row_hi, int n_base,
+                                                    const GemmTcDev& p) {
+  const int n = n_base + (lane & 7) * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rowc = min(row_base + i * 4 + (lane >> 3), row_hi - 1);  // clamp: loads stay in bounds
+    rr[i] = *reinterpret_cast<const float4*>(p.R + (size_t)rowc * p.ldr + n);
+  }
+}
+
 template <bool RELU, bool RES, bool DROP>
 __device__ __forceinline__ void epilogue_block32(const float (&v)[32], float4* st, int lane, int row_base, int row_hi,
-                                                 int n_base, const GemmTcDev& p, uint32_t out_seed) {
+                                                 int n_base, const GemmTcDev& p, uint32_t out_seed,
+                                                 const float4 (&rr)[8]) {
 #pragma unroll
   for (int c = 0; c < 8; ++c)
     st[lane * 8 + (c ^ (lane & 7))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
   __syncwarp();
   const int c = lane & 7, n = n_base + c * 4;
   const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-  float4 rr[8];
-  if (RES) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rowc = min(row_base + i * 4 + (lane >> 3), row_hi - 1);  // clamp: loads stay in bounds
-      rr[i] = *reinterpret_cast<const float4*>(p.R + (size_t)rowc * p.ldr + n);
-    }
-  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + (lane >> 3), row = row_base + r;
@@ -248,22 +252,34 @@ __device__ __forceinline__ void epilogue_block32(const float (&v)[32], float4* s
 // Same 32 x 32 block epilogue with the feature set read from `p` at run time (bias / ReLU / ReLU-mask / dropout /
 // residual), plus the scalar path for ragged column counts.  Used by the persistent kernels, whose eight epilogue warps
 // each own one TMEM lane quadrant x 32 columns.
+struct Epi32Pre {
+  float4 mk[8], rr[8];
+  bool fast;
+};
+// ReLU-mask / residual rows of the block, loaded BEFORE the accumulator is waited for
+__device__ __forceinline__ void epi32_prefetch(Epi32Pre& pre, int lane, int row_base, int row_hi, int n_base,
+                                               const GemmTcDev& p, bool vec_ok) {
+  pre.fast = vec_ok && n_base + 32 <= p.N;
+  if (!pre.fast) return;
+  const int n = n_base + (lane & 7) * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rowc = min(row_base + i * 4 + (lane >> 3), row_hi - 1);  // clamp: loads stay in bounds
+    if (p.M != nullptr) pre.mk[i] = *reinterpret_cast<const float4*>(p.M + (size_t)rowc * p.ldm + n);
+    if (p.R != nullptr) pre.rr[i] = *reinterpret_cast<const float4*>(p.R + (size_t)rowc * p.ldr + n);
+  }
+}
+
 __device__ __forceinline__ void epilogue_block32_rt(const float (&v)[32], float4* st, int lane, int row_base, int row_hi,
-                                                    int n_base, const GemmTcDev& p, uint32_t out_seed, bool vec_ok) {
+                                                    int n_base, const GemmTcDev& p, uint32_t out_seed, bool vec_ok,
+                                                    const Epi32Pre& pre) {
   if (n_base >= p.N) return;  // warp-uniform
 #pragma unroll
   for (int c = 0; c < 8; ++c)
     st[lane * 8 + (c ^ (lane & 7))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
   __syncwarp();
   const int c = lane & 7, n = n_base + c * 4;
-  if (vec_ok && n_base + 32 <= p.N) {
-    float4 mk[8], rr[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rowc = min(row_base + i * 4 + (lane >> 3), row_hi - 1);  // clamp: loads stay in bounds
-      if (p.M != nullptr) mk[i] = *reinterpret_cast<const float4*>(p.M + (size_t)rowc * p.ldm + n);
-      if (p.R != nullptr) rr[i] = *reinterpret_cast<const float4*>(p.R + (size_t)rowc * p.ldr + n);
-    }
+  if (pre.fast) {
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
     const uint32_t th = p.drop_thresh;
@@ -277,17 +293,17 @@ __device__ __forceinline__ void epilogue_block32_rt(const float (&v)[32], float4
         for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
       }
       if (p.M != nullptr) {
-        if (!(mk[i].x > 0.f)) o[0] = 0.f;
-        if (!(mk[i].y > 0.f)) o[1] = 0.f;
-        if (!(mk[i].z > 0.f)) o[2] = 0.f;
-        if (!(mk[i].w > 0.f)) o[3] = 0.f;
+        if (!(pre.mk[i].x > 0.f)) o[0] = 0.f;
+        if (!(pre.mk[i].y > 0.f)) o[1] = 0.f;
+        if (!(pre.mk[i].z > 0.f)) o[2] = 0.f;
+        if (!(pre.mk[i].w > 0.f)) o[3] = 0.f;
       }
       if (th != 0u) {
         float f[4];
         drop_factor4(out_seed, p.drop_stream, th, p.drop_scale, row, n, f);
         o[0] *= f[0]; o[1] *= f[1]; o[2] *= f[2]; o[3] *= f[3];
       }
-      if (p.R != nullptr) { o[0] += rr[i].x; o[1] += rr[i].y; o[2] += rr[i].z; o[3] += rr[i].w; }
+      if (p.R != nullptr) { o[0] += pre.rr[i].x; o[1] += pre.rr[i].y; o[2] += pre.rr[i].z; o[3] += pre.rr[i].w; }
       if (row < row_hi) *reinterpret_cast<float4*>(p.Y + (size_t)row * p.ldy + n) = make_float4(o[0], o[1], o[2], o[3]);
     }
   } else {
@@ -611,6 +627,8 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       if (row0 >= m.hi) continue;
       const int a = tcount & 1;
       const uint32_t tph = (tcount >> 1) & 1;
+      Epi32Pre pre;
+      epi32_prefetch(pre, lane, row0 + q * 32, m.hi, ntile * 64 + half * 32, p, vec_ok);
       mbar_wait(&tfull[a], tph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * 64 + half * 32;
@@ -619,7 +637,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       tc_fence_before();
       mbar_arrive(&tempty[a]);  // the MMA warp may overwrite this accumulator
       epilogue_block32_rt(v, epi + (warp - 6) * 256, lane, row0 + q * 32, m.hi, ntile * 64 + half * 32, p, out_seed,
-                          vec_ok);
+                          vec_ok, pre);
       ++tcount;
     }
   }
@@ -1106,7 +1124,8 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             tc_fence_before();
             mbar_arrive(&uempty[a]);
           }
-          epilogue_block32<true, false, false>(u, st, lane, row0 + q * 32, m.hi, c0, p.h, 0u);
+          float4 none[8];
+          epilogue_block32<true, false, false>(u, st, lane, row0 + q * 32, m.hi, c0, p.h, 0u, none);
         }
       } else {
         mbar_arrive(&uempty[a]);
@@ -1129,13 +1148,17 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 32) {
+        // (fetching the residual before the wait, as the persistent kernels do, measured slower here: the same rows
+        // are in flight through the TMA ring at that time)
+        float4 rr[8];
+        epi32_load_residual(rr, lane, row0 + q * 32, m.hi, c0, p.y);
         float v[32];
         tmem_ld32(lane_base + kV + a * 64 + c0, v);
         if (c0 == 32) {
           tc_fence_before();
           mbar_arrive(&vempty[a]);
         }
-        epilogue_block32<false, true, true>(v, st, lane, row0 + q * 32, m.hi, c0, p.y, out_seed);
+        epilogue_block32<false, true, true>(v, st, lane, row0 + q * 32, m.hi, c0, p.y, out_seed, rr);
       }
       ++tcount;
     }
@@ -1343,6 +1366,8 @@ gemm_tc_slab_kernel(const __grid_constant__ CUtensorMap map_x32, const __grid_co
       if (row0 >= m.hi) continue;
       const int a = tcount & 1;
       const uint32_t tph = (tcount >> 1) & 1;
+      Epi32Pre pre;
+      epi32_prefetch(pre, lane, row0 + q * 32, m.hi, ntile * 64 + half * 32, p, vec_ok);
       mbar_wait(&tfull[a], tph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * 64 + half * 32;
@@ -1351,7 +1376,7 @@ gemm_tc_slab_kernel(const __grid_constant__ CUtensorMap map_x32, const __grid_co
       tc_fence_before();
       mbar_arrive(&tempty[a]);
       epilogue_block32_rt(v, epi + (warp - 6) * 256, lane, row0 + q * 32, m.hi, ntile * 64 + half * 32, p, out_seed,
-                          vec_ok);
+                          vec_ok, pre);
       ++tcount;
     }
   }

@@ -664,7 +664,7 @@ struct TwSmem {
   static constexpr int kBytes = kStages * kStage + TP_EPI + 1024 + 256;
 };
 
-constexpr int TW_THREADS = 320;   // TMA, MMA, 4 x operand split, 4 x epilogue
+constexpr int TW_THREADS = 448;   // TMA, MMA, 4 x operand split, 8 x epilogue
 
 template <int BN>
 __global__ void __launch_bounds__(TW_THREADS, 1)
@@ -698,7 +698,7 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 128);
+      mbar_init(&tempty[a], 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -804,10 +804,11 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       }
     }
   } else {
-    // ===================== epilogue (warps 6..9; TMEM lane quadrant = warp % 4) =====================
-    const int q = warp & 3;
+    // ===================== epilogue (warps 6..13: TMEM lane quadrant x half of the BN columns) =====================
+    const int q = warp & 3, half = (warp - 6) >> 2;
     const uint32_t out_seed = p.drop_seed ^ dseed;
     const bool vec_ok = ((p.ldy & 3) == 0) && (p.R == nullptr || (p.ldr & 3) == 0) && (p.M == nullptr || (p.ldm & 3) == 0);
+    float4* st = epi + (warp - 6) * 256;
     int tcount = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int blk = tile % nblk, ntile = tile / nblk;
@@ -816,21 +817,22 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       if (row0 >= m.hi) continue;
       const int a = tcount & 1;
       const uint32_t tph = (tcount >> 1) & 1;
+      const int cbase = half * (BN / 2);
+      Epi32Pre pre;
+      epi32_prefetch(pre, lane, row0 + q * 32, m.hi, ntile * BN + cbase, p, vec_ok);
       mbar_wait(&tfull[a], tph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + cbase;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 64) {
-        float v0[32], v1[32];
-        tmem_ld32(taddr + c0, v0);
-        tmem_ld32(taddr + c0 + 32, v1);
-        if (c0 + 64 >= BN) {  // last read of this accumulator: hand it back before the stores
+      for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        if (c0 + 32 >= BN / 2) {  // last read of this accumulator: hand it back before the stores
           tc_fence_before();
           mbar_arrive(&tempty[a]);
         }
-        if (ntile * BN + c0 < p.N)
-          epilogue_block_coalesced(v0, v1, epi + (warp - 6) * 512, lane, row0 + q * 32, m.hi, ntile * BN + c0, p,
-                                   out_seed, vec_ok);
+        epilogue_block32_rt(v, st, lane, row0 + q * 32, m.hi, ntile * BN + cbase + c0, p, out_seed, vec_ok, pre);
+        if (c0 + 32 < BN / 2) epi32_prefetch(pre, lane, row0 + q * 32, m.hi, ntile * BN + cbase + c0 + 32, p, vec_ok);
       }
       ++tcount;
     }

@@ -14,13 +14,16 @@
 // One CTA owns one (m-tile, n-tile) of dW and a slice of the rows; it accumulates over all its rows in TMEM
 // and adds its partial to dW once, at the end (fp32 atomics).  The dropout mask of the layer (gv = keep * gy /
 // (1 - p)), Dropout2d's channel scale and the input mask of the projection are folded into the operand split.
-//   warp 0: TMA producer | warp 1: MMA issuer + TMEM owner | warps 2-5: operand split, bias sums, epilogue
+//   warp 0: TMA producer | warp 1: MMA issuer + TMEM owner | warps 2-9: operand split, bias sums, epilogue
+//   (eight split warps: the per-chunk split is instruction-bound, 4 + NGA 16-byte chunks per thread)
 #include <cstdlib>
 
 #include "gemm_tc.cuh"
 
 namespace tcn {
 
+constexpr int WG_THREADS = 320;                // TMA, MMA, 8 x operand split / epilogue
+constexpr int WG_SPLIT = 256;                  // operand-split threads
 constexpr int WG_RC = 32;                      // frames per pipeline stage
 constexpr int WG_ATOM = WG_RC * 128;           // 4096 B: 32 frames x 32 fp32 columns
 // NGA = 32-column G blocks per tile (output-channel tile = 32 NGA): 2 for the 64-channel layers of the TCN, 4 for the
@@ -80,7 +83,7 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
                                               const int split, const int mtile, const int ntile) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int WG_RAW = WgSmem<NGA>::kRaw, WG_STAGE = WgSmem<NGA>::kStage, WG_STAGES = WgSmem<NGA>::kStages;
-  constexpr int NCH = (4 + NGA) * 2;   // 16-byte chunks per split thread and stage
+  constexpr int NCH = 4 + NGA;         // 16-byte chunks per split thread and stage (one per 32 x 32 block)
   constexpr int NCOL = NGA * 32;       // output channels per tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = p.dyn ? p.dyn->nblk : p.nblk;
@@ -102,7 +105,7 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
   if (threadIdx.x == 0) {
     for (int s = 0; s < WG_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&ready_bar[s], 128);
+      mbar_init(&ready_bar[s], WG_SPLIT);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(accum_bar, 1);
@@ -192,8 +195,8 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
         __syncwarp();
       }
     } else {
-      // ===================== operand split + bias sums (warps 2..5) =====================
-      const int ct = threadIdx.x - 64;  // 0..127
+      // ===================== operand split + bias sums (warps 2..9) =====================
+      const int ct = threadIdx.x - 64;  // 0..255: chunk ct of every 32 x 32 block (frame ct / 8, 16-byte chunk ct % 8)
       const uint32_t g_seed = p.g_drop_seed ^ dseed, x_seed = p.x_drop_seed ^ dseed;
       // every 16-byte chunk this thread touches has the same position inside its 32 x 32 block up to a row offset:
       const int lc = ((((ct & 7) >> 1) ^ ((ct >> 3) & 3)) << 1) | (ct & 1);  // logical 16-byte column chunk (swizzle undone)
@@ -214,11 +217,11 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
           float4* lo = reinterpret_cast<float4*>(tiles + s * WG_STAGE + WG_RAW);
           float4 v[NCH];
 #pragma unroll
-          for (int i = 0; i < NCH; ++i) v[i] = raw[ct + i * 128];
+          for (int i = 0; i < NCH; ++i) v[i] = raw[ct + i * WG_SPLIT];
 #pragma unroll
           for (int i = 0; i < NCH; ++i) {
-            const int atom = i >> 1;                    // chunk ct + i*128 lies in block i/2 ...
-            const int r = (ct >> 3) + (i & 1) * 16;     // ... at frame r of the chunk
+            const int atom = i;                         // chunk ct + 256 i lies in block i ...
+            const int r = ct >> 3;                      // ... at frame r of the chunk
             int src = r0 + r;
             if (atom < 4) src += a_tap[atom] == 0 ? p.shift[0] : (a_tap[atom] == 1 ? p.shift[1] : p.shift[2]);
             const float keep = (src >= m.lo && src < m.hi) ? 1.f : 0.f;
@@ -244,9 +247,9 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
             }
           }
 #pragma unroll
-          for (int i = 8; i < NCH; ++i) {  // G blocks: column sums for the bias gradient
-            bsum[(i - 8) >> 1].x += v[i].x; bsum[(i - 8) >> 1].y += v[i].y;
-            bsum[(i - 8) >> 1].z += v[i].z; bsum[(i - 8) >> 1].w += v[i].w;
+          for (int i = 4; i < NCH; ++i) {  // G blocks: column sums for the bias gradient
+            bsum[i - 4].x += v[i].x; bsum[i - 4].y += v[i].y;
+            bsum[i - 4].z += v[i].z; bsum[i - 4].w += v[i].w;
           }
 #pragma unroll
           for (int i = 0; i < NCH; ++i) {
@@ -255,8 +258,8 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
             h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u); l.y = v[i].y - h.y;
             h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u); l.z = v[i].z - h.z;
             h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u); l.w = v[i].w - h.w;
-            raw[ct + i * 128] = h;
-            lo[ct + i * 128] = l;
+            raw[ct + i * WG_SPLIT] = h;
+            lo[ct + i * WG_SPLIT] = l;
           }
           fence_proxy_async();
           mbar_arrive(&ready_bar[s]);
@@ -272,8 +275,8 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
           atomicAdd(&bias_red[a * 32 + lc * 4 + 2], bsum[a].z);
           atomicAdd(&bias_red[a * 32 + lc * 4 + 3], bsum[a].w);
         }
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");  // the four split warps only
-        for (int i = ct; i < NCOL; i += 128) {
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");  // the eight split warps only
+        for (int i = ct; i < NCOL; i += WG_SPLIT) {
           const int n = ntile * NCOL + i;
           if (n < p.n_out) atomicAdd(p.db + n, bias_red[i]);
         }
@@ -281,13 +284,14 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
       // ===================== epilogue: add the partial into dW =====================
       mbar_wait(accum_bar, 0);
       tc_fence_after();
-      const int q = warp & 3;  // TMEM lane quadrant == X block of this m-tile
+      const int q = warp & 3;  // TMEM lane quadrant == X block of this m-tile; two warps per quadrant split the columns
+      const int half = (warp - 2) >> 2;
       const int vblk = mtile * 4 + q;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
       const int c = a_cb[q] * 32 + lane;
       const bool row_ok = (vblk < nv) && (c < p.c_in);
 #pragma unroll 1
-      for (int c0 = 0; c0 < NCOL; c0 += 32) {
+      for (int c0 = half * (NCOL / 2); c0 < (half + 1) * (NCOL / 2); c0 += 32) {
         if (ntile * NCOL + c0 >= p.n_out) break;  // warp-uniform
         float v[32];
         tmem_ld32(taddr + c0, v);
@@ -308,14 +312,14 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
 }
 
 template <int NGA>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
                 const WgradTcDev p) {
   wgrad_tc_body<NGA>(&map_x, &map_g, p, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 // two independent problems in one launch (the two weight gradients of a residual layer): blockIdx.y < mt0 -> problem 0
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_g0,
                      const WgradTcDev p0, const __grid_constant__ CUtensorMap map_x1,
                      const __grid_constant__ CUtensorMap map_g1, const WgradTcDev p1, int mt0) {
@@ -355,7 +359,7 @@ static int launch_wgrad_tc_n(const CUtensorMap& mx, const CUtensorMap& mg, Wgrad
   if (rs < 1) rs = 1;
   if (rs > nb) rs = nb;
   p.row_splits = rs;
-  launch_kernel(wgrad_tc_kernel<NGA>, dim3(rs, mt, nt), dim3(TC_THREADS), WgSmem<NGA>::kBytes, stream, true, mx, mg, p);
+  launch_kernel(wgrad_tc_kernel<NGA>, dim3(rs, mt, nt), dim3(WG_THREADS), WgSmem<NGA>::kBytes, stream, true, mx, mg, p);
   return check_launch("wgrad_tc_kernel");
 }
 
@@ -379,7 +383,7 @@ int launch_wgrad_tc(const CUtensorMap& mx, const CUtensorMap& mg, WgradTcDev& p,
 }
 
 // blockIdx.y -> (problem, m-tile) through a device table; tensor maps are read from global memory
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_multi_kernel(const WgradMultiDesc* __restrict__ descs, const int2* __restrict__ tiles) {
   const int2 t = tiles[blockIdx.y];
   const WgradMultiDesc& d = descs[t.x];
@@ -399,7 +403,7 @@ int launch_wgrad_tc_multi(const WgradMultiDesc* descs_dev, const int2* tiles_dev
     }
     attr_set = true;
   }
-  launch_kernel(wgrad_tc_multi_kernel, dim3(row_splits, ntiles, 1), dim3(TC_THREADS), WgSmem<2>::kBytes, stream, true,
+  launch_kernel(wgrad_tc_multi_kernel, dim3(row_splits, ntiles, 1), dim3(WG_THREADS), WgSmem<2>::kBytes, stream, true,
                 descs_dev, tiles_dev);
   return check_launch("wgrad_tc_multi_kernel");
 }
@@ -430,7 +434,7 @@ int launch_wgrad_tc_pair(const CUtensorMap& mx0, const CUtensorMap& mg0, WgradTc
   if (rs > nb) rs = nb;
   p0.row_splits = rs;
   p1.row_splits = rs;
-  launch_kernel(wgrad_tc_pair_kernel, dim3(rs, mt0 + mt1, 1), dim3(TC_THREADS), WgSmem<2>::kBytes, stream, true, mx0, mg0, p0, mx1,
+  launch_kernel(wgrad_tc_pair_kernel, dim3(rs, mt0 + mt1, 1), dim3(WG_THREADS), WgSmem<2>::kBytes, stream, true, mx0, mg0, p0, mx1,
                 mg1, p1, mt0);
   return check_launch("wgrad_tc_pair_kernel");
 }

@@ -28,24 +28,26 @@
 namespace tcn {
 
 
-// Operand split of one 128 x 32 fp32 tile (TMA layout, 128B swizzle) by 128 threads: X -> (X_hi in place, X_lo).
+// Operand split of one 128 x 32 fp32 tile (TMA layout, 128B swizzle) by NT = 128 / 256 threads: X -> (X_hi in place, X_lo).
 // All eight 16-byte chunks of a thread are loaded before any is processed; rows whose tap source leaves the
 // sequence are zeroed with selects (no divergent control flow on the fast path).
+template <int NT>
 __device__ __forceinline__ void split_tile(float4* __restrict__ xa, float4* __restrict__ xl, int ct, int row0, int sh,
                                            const BlkMeta& m, int kc, const GemmTcDev& p, uint32_t in_seed) {
-  float4 v[8];
+  constexpr int NV = 1024 / NT;   // 16-byte chunks per thread (128 rows x 8 chunks, NT threads)
+  float4 v[NV];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = xa[ct + i * 128];
+  for (int i = 0; i < NV; ++i) v[i] = xa[ct + i * NT];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int src = row0 + ((ct + i * 128) >> 3) + sh;
+  for (int i = 0; i < NV; ++i) {
+    const int src = row0 + ((ct + i * NT) >> 3) + sh;
     const float keep = (src >= m.lo && src < m.hi) ? 1.f : 0.f;
     v[i].x *= keep; v[i].y *= keep; v[i].z *= keep; v[i].w *= keep;
   }
   if (p.colscale != nullptr || p.in_drop_thresh != 0u) {  // CTA-uniform, rare (projection in training)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = ct + i * 128, r = c >> 3;
+    for (int i = 0; i < NV; ++i) {
+      const int c = ct + i * NT, r = c >> 3;
       const int src = row0 + r + sh;
       const int col = kc * TC_BK + (((c & 7) ^ (r & 7)) << 2);  // undo the 128B swizzle
       if (p.colscale != nullptr && col < p.c_in) {
@@ -60,14 +62,14 @@ __device__ __forceinline__ void split_tile(float4* __restrict__ xa, float4* __re
     }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < NV; ++i) {
     float4 h, l;
     h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xffffe000u); l.x = v[i].x - h.x;
     h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u); l.y = v[i].y - h.y;
     h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u); l.z = v[i].z - h.z;
     h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u); l.w = v[i].w - h.w;
-    xa[ct + i * 128] = h;
-    xl[ct + i * 128] = l;
+    xa[ct + i * NT] = h;
+    xl[ct + i * NT] = l;
   }
 }
 
@@ -329,8 +331,10 @@ struct TcSmem {
   static constexpr int kBytes = kStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+constexpr int TS_THREADS = 320;   // TMA, MMA, 8 x operand split / epilogue
+
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TS_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                const __grid_constant__ CUtensorMap map_wlo, const GemmTcDev p) {
   extern __shared__ uint8_t smem_raw[];
@@ -353,7 +357,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&ready_bar[s], 128);
+      mbar_init(&ready_bar[s], 256);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(accum_bar, 1);
@@ -424,8 +428,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         __syncwarp();
       }
     } else {
-      // ===================== operand split (warps 2..5) =====================
-      const int ct = threadIdx.x - 64;  // 0..127
+      // ===================== operand split (warps 2..9) =====================
+      const int ct = threadIdx.x - 64;  // 0..255
       const uint32_t dseed = p.dyn ? p.dyn->seed : 0u;
       const uint32_t in_seed = p.in_drop_seed ^ dseed;
       int tap = 0, kc = 0;
@@ -434,22 +438,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const uint32_t ph = (kb / TC_STAGES) & 1;
         const int sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
         mbar_wait(&full_bar[s], ph);
-        split_tile(reinterpret_cast<float4*>(tiles + s * S::kStage),
-                   reinterpret_cast<float4*>(tiles + s * S::kStage + S::kA), ct, row0, sh, m, kc, p, in_seed);
+        split_tile<256>(reinterpret_cast<float4*>(tiles + s * S::kStage),
+                        reinterpret_cast<float4*>(tiles + s * S::kStage + S::kA), ct, row0, sh, m, kc, p, in_seed);
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(&ready_bar[s]);
         if (++kc == p.kbp) { kc = 0; ++tap; }
       }
-      // ===================== epilogue (same warps; TMEM lane quadrant = warp % 4) =====================
+      // ===================== epilogue (same warps; TMEM lane quadrant = warp % 4, two warps share the columns) ======
       mbar_wait(accum_bar, 0);
       tc_fence_after();
-      const int q = warp & 3;
+      const int q = warp & 3, half = (warp - 2) >> 2;
       const int row = row0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
       const uint32_t out_seed = p.drop_seed ^ dseed;
       const bool vec_ok = ((p.ldy & 3) == 0) && (p.R == nullptr || (p.ldr & 3) == 0) && (p.M == nullptr || (p.ldm & 3) == 0);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * 32; c0 < BN; c0 += 64) {
         float v[32];
         tmem_ld32(taddr + c0, v);  // warp-collective: every lane takes part, stores are predicated below
         if (row < m.hi) epilogue_cols(v, row, ntile * BN + c0, p, out_seed, vec_ok);
@@ -608,7 +612,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         const uint32_t ph = (it / TP_STAGES) & 1;
         const int sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
         mbar_wait(&full_bar[s], ph);
-        split_tile(reinterpret_cast<float4*>(at + s * 2 * TP_KA), reinterpret_cast<float4*>(at + s * 2 * TP_KA + TP_KA),
+        split_tile<128>(reinterpret_cast<float4*>(at + s * 2 * TP_KA), reinterpret_cast<float4*>(at + s * 2 * TP_KA + TP_KA),
                    ct, row0, sh, m, kc, p, in_seed);
         fence_proxy_async();
         mbar_arrive(&ready_bar[s]);
@@ -796,8 +800,8 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const uint32_t ph = (it / NST) & 1;
         const int sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
         mbar_wait(&full_bar[s], ph);
-        split_tile(reinterpret_cast<float4*>(tiles + s * S::kStage),
-                   reinterpret_cast<float4*>(tiles + s * S::kStage + S::kA), ct, row0, sh, m, kc, p, in_seed);
+        split_tile<128>(reinterpret_cast<float4*>(tiles + s * S::kStage),
+                        reinterpret_cast<float4*>(tiles + s * S::kStage + S::kA), ct, row0, sh, m, kc, p, in_seed);
         fence_proxy_async();
         mbar_arrive(&ready_bar[s]);
         if (++kc == p.kbp) { kc = 0; ++tap; }
@@ -1558,7 +1562,7 @@ int launch_gemm_tc(const CUtensorMap& mx, const CUtensorMap& mwhi, const CUtenso
     }
     attr_set = true;
   }
-  launch_kernel(gemm_tc_kernel<64>, grid, dim3(TC_THREADS), TcSmem<64>::kBytes, stream, true, mx, mwhi, mwlo, p);
+  launch_kernel(gemm_tc_kernel<64>, grid, dim3(TS_THREADS), TcSmem<64>::kBytes, stream, true, mx, mwhi, mwlo, p);
   return check_launch("gemm_tc_kernel");
 }
 

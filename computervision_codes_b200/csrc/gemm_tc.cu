@@ -322,16 +322,53 @@ __device__ __forceinline__ void epilogue_block32_rt(const float (&v)[32], float4
   __syncwarp();
 }
 
+// one frame (= one thread = one TMEM lane) of a raw 128 x 32 TMA tile -> TF32 hi / lo halves in a TMEM operand slot
+// (hi: 32 columns at taddr, lo: the next 32).  Same masking / scaling rules as split_tile.
+__device__ __forceinline__ void split_row_to_tmem(const float4* __restrict__ tile, int r, int src, const BlkMeta& m,
+                                                  int kc, const GemmTcDev& p, uint32_t in_seed, uint32_t taddr) {
+  const float4* row = tile + r * 8;
+  const bool inside = src >= m.lo && src < m.hi;
+  float hi[32], lo[32];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float4 v = row[c ^ (r & 7)];                   // undo the 128B swizzle: logical 16-byte chunk c
+    if (!inside) v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.colscale != nullptr || p.in_drop_thresh != 0u) {  // CTA-uniform, rare (projection in training)
+      const int col = kc * TC_BK + c * 4;
+      if (p.colscale != nullptr && col < p.c_in) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.colscale + (size_t)m.seq * p.colscale_ld + col));
+        v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+      }
+      if (p.in_drop_thresh != 0u) {
+        float f[4];
+        drop_factor4(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col, f);
+        v.x *= f[0]; v.y *= f[1]; v.z *= f[2]; v.w *= f[3];
+      }
+    }
+    hi[4 * c + 0] = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); lo[4 * c + 0] = v.x - hi[4 * c + 0];
+    hi[4 * c + 1] = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); lo[4 * c + 1] = v.y - hi[4 * c + 1];
+    hi[4 * c + 2] = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); lo[4 * c + 2] = v.z - hi[4 * c + 2];
+    hi[4 * c + 3] = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); lo[4 * c + 3] = v.w - hi[4 * c + 3];
+  }
+  tmem_st32(taddr, hi);
+  tmem_st32(taddr + 32, lo);
+}
+
+// Streaming kernel (long contractions: the stage-input projection, K = D): one (frame tile, 64-column tile) per CTA.
+// The raw X tile and the pre-split weight tiles of a k-block travel through a 6-deep TMA ring (32 KB per stage: the
+// ring only holds RAW activations, so 96 KB of X are in flight per SM -- the projection is bound by HBM latency x
+// bandwidth); one split thread per frame moves the hi / lo halves into a double-buffered TMEM operand slot and the
+// MMAs take A from tensor memory.
 template <int BN>
 struct TcSmem {
-  static constexpr int kStages = BN > 64 ? 3 : 4;
-  static constexpr int kA = TC_BM * TC_BK * 4;  // 16384
-  static constexpr int kB = BN * TC_BK * 4;
-  static constexpr int kStage = 2 * kA + 2 * kB;
+  static constexpr int kStages = 6;
+  static constexpr int kA = TC_BM * TC_BK * 4;  // 16384: raw X tile
+  static constexpr int kB = BN * TC_BK * 4;     // one weight half
+  static constexpr int kStage = kA + 2 * kB;
   static constexpr int kBytes = kStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-constexpr int TS_THREADS = 320;   // TMA, MMA, 8 x operand split / epilogue
+constexpr int TS_THREADS = 320;   // TMA, MMA, 4 x operand split (+ epilogue), 4 x epilogue
 
 template <int BN>
 __global__ void __launch_bounds__(TS_THREADS, 1)
@@ -340,6 +377,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   using S = TcSmem<BN>;
   constexpr int TC_STAGES = S::kStages;
+  static_assert(BN == 64, "TMEM layout below: D @ 0..63, operand slots @ 64 / 128");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int blk = blockIdx.x, ntile = blockIdx.y;
   const int nblk = p.dyn ? p.dyn->nblk : p.nblk;
@@ -349,30 +387,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * S::kStage);
   uint64_t* full_bar = bars;                    // TMA bytes landed          (count 1 + tx)
-  uint64_t* ready_bar = bars + TC_STAGES;       // operands split            (count 128)
-  uint64_t* empty_bar = bars + 2 * TC_STAGES;   // MMAs that read the stage retired (count 1, tcgen05.commit)
-  uint64_t* accum_bar = bars + 3 * TC_STAGES;   // accumulator complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 1);
+  uint64_t* empty_bar = bars + TC_STAGES;       // MMAs that read the stage retired (count 1, tcgen05.commit)
+  uint64_t* aready = bars + 2 * TC_STAGES;      // [2] X halves written to the TMEM operand slot (128 split threads)
+  uint64_t* aempty = aready + 2;                // [2] ... consumed (tcgen05.commit)
+  uint64_t* accum_bar = aempty + 2;             // accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&ready_bar[s], 256);
       mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&aready[s], 128);
+      mbar_init(&aempty[s], 1);
     }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: BN fp32 accumulator columns (power of two >= 32)
-    constexpr uint32_t kCols = BN < 32 ? 32 : BN;
+  if (warp == 1) {  // TMEM: 64 accumulator columns + two (hi | lo) operand slots of 64 columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
-                 "r"(kCols));
+                 "r"(256u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kAslot = 64;
   pdl_launch_dependents();
   pdl_wait();
 
@@ -382,6 +424,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   const int row0 = blk * kBlkRows;
   const bool has_rows = active && row0 < m.hi;
   const int kblocks = p.ntaps * p.kbp;
+  const uint32_t dseed = p.dyn ? p.dyn->seed : 0u;
 
   if (has_rows) {
     if (warp == 0) {
@@ -397,8 +440,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           mbar_arrive_expect_tx(&full_bar[s], S::kA + 2 * S::kB);
           const int sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
           tma_load_2d(st, &map_x, &full_bar[s], kc * TC_BK, xrow + sh);  // rows < 0 or past the end: zero fill
-          tma_load_2d(st + 2 * S::kA, &map_whi, &full_bar[s], kb * TC_BK, ntile * BN);
-          tma_load_2d(st + 2 * S::kA + S::kB, &map_wlo, &full_bar[s], kb * TC_BK, ntile * BN);
+          tma_load_2d(st + S::kA, &map_whi, &full_bar[s], kb * TC_BK, ntile * BN);
+          tma_load_2d(st + S::kA + S::kB, &map_wlo, &full_bar[s], kb * TC_BK, ntile * BN);
           if (++kc == p.kbp) { kc = 0; ++tap; }
         }
       }
@@ -406,45 +449,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
       for (int kb = 0; kb < kblocks; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (kb / TC_STAGES) & 1;
-        mbar_wait(&ready_bar[s], ph);
+        const int s = kb % TC_STAGES, ta = kb & 1;
+        mbar_wait(&aready[ta], ((uint32_t)kb >> 1) & 1);   // implies full_bar[s]: the split threads waited for it
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a_hi = base + s * S::kStage, a_lo = a_hi + S::kA;
-          const uint32_t b_hi = a_hi + 2 * S::kA, b_lo = b_hi + S::kB;
+          const uint32_t a_hi = tmem_base + kAslot + ta * 64, a_lo = a_hi + 32;
+          const uint32_t b_hi = base + s * S::kStage + S::kA, b_lo = b_hi + S::kB;
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {
-            const uint32_t ko = k * 32;  // 8 tf32 = 32 bytes inside the 128-byte swizzle row
-            const uint64_t dah = umma_desc_sw128(a_hi + ko), dal = umma_desc_sw128(a_lo + ko);
-            const uint64_t dbh = umma_desc_sw128(b_hi + ko), dbl = umma_desc_sw128(b_lo + ko);
-            umma_tf32(tmem_base, dal, dbh, idesc, (kb | k) != 0);
-            umma_tf32(tmem_base, dah, dbl, idesc, 1u);
-            umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+            const uint64_t dbh = umma_desc_sw128(b_hi + k * 32), dbl = umma_desc_sw128(b_lo + k * 32);
+            umma_tf32_ts(tmem_base, a_lo + k * 8, dbh, idesc, (kb | k) != 0);
+            umma_tf32_ts(tmem_base, a_hi + k * 8, dbl, idesc, 1u);
+            umma_tf32_ts(tmem_base, a_hi + k * 8, dbh, idesc, 1u);
           }
           umma_commit(&empty_bar[s]);                       // stage reusable once these MMAs retire
+          umma_commit(&aempty[ta]);
           if (kb == kblocks - 1) umma_commit(accum_bar);    // accumulator complete
         }
         __syncwarp();
       }
     } else {
-      // ===================== operand split (warps 2..9) =====================
-      const int ct = threadIdx.x - 64;  // 0..255
-      const uint32_t dseed = p.dyn ? p.dyn->seed : 0u;
-      const uint32_t in_seed = p.in_drop_seed ^ dseed;
-      int tap = 0, kc = 0;
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (kb / TC_STAGES) & 1;
-        const int sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
-        mbar_wait(&full_bar[s], ph);
-        split_tile<256>(reinterpret_cast<float4*>(tiles + s * S::kStage),
-                        reinterpret_cast<float4*>(tiles + s * S::kStage + S::kA), ct, row0, sh, m, kc, p, in_seed);
-        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
-        mbar_arrive(&ready_bar[s]);
-        if (++kc == p.kbp) { kc = 0; ++tap; }
+      if (warp < 6) {
+        // ===================== operand split (warps 2..5): one frame = one thread = one TMEM lane ================
+        const int r = (warp & 3) * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t in_seed = p.in_drop_seed ^ dseed;
+        int tap = 0, kc = 0;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int s = kb % TC_STAGES, ta = kb & 1;
+          const int sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
+          mbar_wait(&full_bar[s], (kb / TC_STAGES) & 1);
+          mbar_wait(&aempty[ta], (((uint32_t)kb >> 1) & 1) ^ 1);
+          tc_fence_after();
+          split_row_to_tmem(reinterpret_cast<const float4*>(tiles + s * S::kStage), r, row0 + r + sh, m, kc, p, in_seed,
+                            lane_base + kAslot + ta * 64);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&aready[ta]);
+          if (++kc == p.kbp) { kc = 0; ++tap; }
+        }
       }
-      // ===================== epilogue (same warps; TMEM lane quadrant = warp % 4, two warps share the columns) ======
+      // ===================== epilogue (warps 2..9; TMEM lane quadrant = warp % 4, two warps share the columns) ======
       mbar_wait(accum_bar, 0);
       tc_fence_after();
       const int q = warp & 3, half = (warp - 2) >> 2;
@@ -462,10 +507,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
-    constexpr uint32_t kCols = BN < 32 ? 32 : BN;
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(kCols));
-  }
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(256u));
 }
 
 

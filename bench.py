@@ -295,7 +295,7 @@ def main():
     trainer._prefetched = None
     e2e_value = frames_all / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel (fused residual-layer forward), timed live with CUDA events
+    # ---- roofline of the dominant kernel (persistent tcgen05 tap GEMM), timed live with CUDA events
     roof = measure_layer_roofline(model, lengths, batches[a.warmup], dev)
 
     def shutdown():
@@ -351,10 +351,12 @@ def _graph_time(fn, n=24):
 
 
 def measure_layer_roofline(model, lengths, batch, dev):
-    """Dominant kernel by time share (profiles/): the residual layers' tensor-core kernels.  Reported here: the
-    input-gradient tap GEMM `gemm_tc_slab_kernel` (3 taps; gx = gy + sum_k W1_k^T gu[t - s_k]) timed live on this
-    step's batch shape, and the same kernel on the TERL stress shape (64 x 8000 frames) where the HBM roofline is
-    the binding limit.  Algorithmic bytes per frame: 12*C (read gu, read gy, write gx)."""
+    """Dominant kernel by time share (profiles/r1_launches_summary.txt, r1_tcn_step_timeline.txt):
+    `gemm_tc_persist_kernel`, the persistent tcgen05 tap GEMM behind every 1x1 contraction of the step.  Reported here:
+    its most frequent use, the input gradient of a residual layer's 1x1 conv
+    gu = ((keep * gy / (1 - p)) W2) * [h > 0]   (dropout mask regenerated as gy is loaded, ReLU mask in the epilogue),
+    timed live on this step's batch shape and on the TERL stress shape (64 x 8000 frames) where the HBM roofline is the
+    binding limit.  Algorithmic bytes per frame: 12*C (read gy, read h, write gu)."""
     from computervision_codes_b200 import ops
     from computervision_codes_b200.layout import SeqLayout
 
@@ -363,21 +365,20 @@ def measure_layer_roofline(model, lengths, batch, dev):
     if os.path.exists(peaks_path):
         peak, src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
     layer = model.PG.layers[4]
-    w1 = layer.conv_dilated.weight.detach()
-    hi, lo = ops.split_weight(w1, transpose=True)
-    shifts = tuple(-s for s in ops.tap_shifts(layer.dilation, layer.causal))
+    hi, lo = ops.split_weight(layer.conv_1x1.weight.detach(), transpose=True)
 
     def run(lens, nbuf):
         lay = SeqLayout.get(lens, dev)
-        gu = [torch.randn(lay.rows, C_MAPS, device=dev) for _ in range(nbuf)]
         gy = [torch.randn(lay.rows, C_MAPS, device=dev) for _ in range(nbuf)]
+        h = [torch.randn(lay.rows, C_MAPS, device=dev).relu_() for _ in range(nbuf)]
         out = [torch.zeros(lay.rows, C_MAPS, device=dev) for _ in range(nbuf)]
         it = [0]
 
         def fn():
             i = it[0] % nbuf
             it[0] += 1
-            ops.gemm_tc(gu[i], hi, lo, lay, C_MAPS, C_MAPS, shifts, out=out[i], residual=gy[i])
+            ops.gemm_tc(gy[i], hi, lo, lay, C_MAPS, C_MAPS, (0,), out=out[i], relu_mask=h[i], in_drop_p=0.5,
+                        in_drop_rescale=True, seed=7, stream_id=4)
 
         ms = _graph_time(fn)
         frames = sum(lens)
@@ -389,7 +390,8 @@ def measure_layer_roofline(model, lengths, batch, dev):
     tpath = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
-    return {"bound": "hbm", "kernel": "gemm_tc_slab_kernel (tcgen05 tap GEMM, input gradient of the dilated conv)",
+    return {"bound": "hbm", "kernel": "gemm_tc_persist_kernel (tcgen05 tap GEMM; here: input gradient of the 1x1 conv "
+                                      "with ReLU mask and dropout-on-load)",
             "achieved": gbs, "peak": peak, "peak_source": src, "unit": "GB/s", "frac": gbs / peak, "traffic": traffic,
             "frames_per_launch": frames, "ms_per_launch": ms,
             "stress_shape": {"frames_per_launch": sframes, "ms_per_launch": sms, "achieved": sgbs, "frac": sgbs / peak},

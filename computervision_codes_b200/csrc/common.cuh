@@ -282,6 +282,11 @@ struct BceDev {
   float* dL;
   int lddl;
   float grad_scale;
+  // several problems that differ only in the logits / gradient buffers (the four FPN levels) in ONE launch:
+  // blockIdx.y selects the level when nlev > 0
+  int nlev;
+  const float* logits_lv[4];
+  float* dL_lv[4];
 };
 int launch_bce(const BceDev& p, int cap_rows, cudaStream_t stream);
 int launch_chan_scale(float* out, int ld, int max_seqs, const BatchDesc* dyn, float p, uint32_t seed,

@@ -11,15 +11,17 @@
 //  - the FPN lateral (network.py:98-106), the four heads (:63-67) and their gradients;
 //  - nn.Linear / Conv1d(k=1,3) of the MS-TCT blocks (Temporal_mstct/MSTCT/Temporal_Encoder.py:12,15,57-59,139).
 //
-// Blackwell structure (one CTA = one 128-frame x 64 (or 128) column tile, 6 warps):
-//   warp 0   : TMA producer  -- cp.async.bulk.tensor 2D loads of the X tile (128 x 32 fp32, 128B swizzle) at
-//              row0 + shift[tap] and of the pre-split weight tiles W_hi / W_lo (BN x 32), 4-stage smem ring
-//   warps 2-5: operand split -- X -> (X_hi in place, X_lo): hi = x & 0xffffe000 is exact in TF32, lo = x - hi;
-//              rows whose tap leaves the sequence are zeroed here (Conv1d zero padding / causal F.pad)
-//   warp 1   : MMA issuer    -- one elected lane issues tcgen05.mma.kind::tf32 (M = 128, N = BN, K = 8), three
-//              products per k-slice (lo*hi + hi*lo + hi*hi) accumulating in TMEM (fp32); tcgen05.commit
-//              releases the smem stage back to the producer
-//   warps 2-5: epilogue      -- tcgen05.ld (32 lanes x 32 columns) -> epi -> 128-bit stores of Y
+// Kernels in this file (all: TMA producer warp, one MMA-issuing lane, operand-split warps, epilogue warps, mbarrier
+// rings, accumulators in TMEM, 3 x TF32 products per k-slice: lo*hi + hi*lo + hi*hi):
+//   gemm_tc_kernel          streaming: long contractions (projection, K = D); raw X ring, A operand through TMEM
+//   gemm_tc_persist_kernel  persistent, <= 6 k-blocks of pre-split weights resident in shared memory (1x1 / k=3 convs,
+//                           their input gradients, FPN lateral, heads); double-buffered TMEM accumulator
+//   gemm_tc_slab_kernel     persistent, the three dilation taps read as row-offset views of ONE staged time slab
+//   gemm_tc_wide_kernel     persistent over (frame tile, 128 / 256-column tile): the MS-TCT Linear layers
+//   layer_fwd_tc_kernel     fused residual layer forward: both GEMMs take A from TMEM, h never leaves the SM
+// Operand split: hi = x & 0xffffe000 is exact in TF32, lo = x - hi; rows whose tap leaves the sequence are zeroed
+// there (Conv1d zero padding / causal F.pad).  Epilogues: tcgen05.ld (32 lanes x 32 columns) -> XOR-swizzled
+// shared-memory transpose -> bias / ReLU / ReLU-mask / dropout / residual -> 128-bit coalesced stores.
 // Accuracy: 3xTF32 == fp32 to ~1e-6 relative (see tests), the bar is 1e-3 on logits.
 #include <cstdlib>
 

@@ -8,6 +8,8 @@
 //                       (run.py:180-182): loss and closed-form gradient T*(softmax(s/T) - p_t)/N.
 //   mse_kernel        : nn.MSELoss feature-KD (Spatial_cnn/run.py:187-191,328).
 //   ce_rows_kernel    : softmax cross-entropy for the 7-way phase head (no reference counterpart).
+#include <cstring>
+
 #include "common.cuh"
 
 namespace tcn {
@@ -26,6 +28,8 @@ __global__ void __launch_bounds__(256) bce_rows_kernel(const BceDev p) {
 
   const int nrows = p.dyn ? p.dyn->rows : p.nrows;
   const float rsc = p.dyn ? 1.f / (float)p.dyn->num_seqs : p.row_scale_const;
+  const float* logits = p.nlev > 0 ? p.logits_lv[blockIdx.y] : p.logits;
+  float* dL = p.nlev > 0 ? p.dL_lv[blockIdx.y] : p.dL;
   for (int row = blockIdx.x * 8 + warp; row < nrows; row += gridDim.x * 8) {
     float rs = rsc;
     int lrow = row;
@@ -35,7 +39,7 @@ __global__ void __launch_bounds__(256) bce_rows_kernel(const BceDev p) {
       rs = rsc / (float)(m.hi - m.lo);
       if (p.lab_unpadded) lrow = row + m.in_delta;
     }
-    const float* x = p.logits + (size_t)row * p.ldl;
+    const float* x = logits + (size_t)row * p.ldl;
     const uint8_t* y = p.labels + (size_t)lrow * p.ldlab;
     for (int c = lane; c < p.zero_cols; c += 32) {
       if (c < p.ncols) {
@@ -50,13 +54,13 @@ __global__ void __launch_bounds__(256) bce_rows_kernel(const BceDev p) {
         const float lu = rs * __ldg(p.col_unit + c) * l;
 #pragma unroll
         for (int k = 0; k < kMaxHeads; ++k) part[k] += (k == h) ? lu : 0.f;
-        if (p.dL != nullptr) {
+        if (dL != nullptr) {
           const float sg = 1.f / (1.f + expf(-xv));
           const float gr = sg * (pw * yv + 1.f - yv) - pw * yv;
-          p.dL[(size_t)row * p.lddl + c] = gr * rs * __ldg(p.col_scale + c) * p.grad_scale;
+          dL[(size_t)row * p.lddl + c] = gr * rs * __ldg(p.col_scale + c) * p.grad_scale;
         }
-      } else if (p.dL != nullptr) {
-        p.dL[(size_t)row * p.lddl + c] = 0.f;
+      } else if (dL != nullptr) {
+        dL[(size_t)row * p.lddl + c] = 0.f;
       }
     }
   }
@@ -367,7 +371,9 @@ int launch_bce(const BceDev& p, int cap_rows, cudaStream_t stream) {
   const long cap = (long)num_sms() * 8;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
-  bce_rows_kernel<<<(int)b, 256, 0, stream>>>(p);
+  const int nlev = p.nlev > 0 ? p.nlev : 1;
+  if (nlev > 1 && b > cap / nlev) b = cap / nlev;
+  bce_rows_kernel<<<dim3((int)b, nlev), 256, 0, stream>>>(p);
   return check_launch("bce_rows_kernel");
 }
 
@@ -410,6 +416,7 @@ extern "C" int tcn_bce_rows(const tcn_bce_args* a, tcn_stream_t stream) {
   TCN_REQUIRE(a->zero_cols >= a->ncols && (a->dl == nullptr || a->lddl >= a->zero_cols),
               "tcn_bce_rows: zero_cols must be in [ncols, lddl]");
   BceDev p;
+  memset(&p, 0, sizeof(p));
   p.logits = a->logits; p.ldl = a->ldl; p.labels = a->labels; p.ldlab = a->ldlab; p.lab_unpadded = a->lab_unpadded;
   p.meta = reinterpret_cast<const BlkMeta*>(a->meta); p.nrows = a->nrows; p.ncols = a->ncols;
   p.zero_cols = a->zero_cols; p.pos_w = a->pos_w; p.col_scale = a->col_scale; p.col_head = a->col_head;

@@ -916,14 +916,16 @@ extern "C" int tcn_model_train_step(tcn_model* m, const float* x, long long x_ro
     cudaGetLastError();
     return TCN_ERR_CUDA;
   }
-  for (int lv = 0; lv < 4; ++lv) {
+  {  // the four FPN levels in one launch (same labels, weights and layout; blockIdx.y = level)
     BceDev b;
     memset(&b, 0, sizeof(b));
-    b.logits = m->logits[lv]; b.ldl = m->LDH; b.labels = labels; b.ldlab = ldlab; b.lab_unpadded = 1;
+    b.ldl = m->LDH; b.labels = labels; b.ldlab = ldlab; b.lab_unpadded = 1;
     b.meta = m->meta; b.nrows = m->cfg.max_rows; b.dyn = m->desc; b.ncols = m->NH; b.zero_cols = m->LDH;
     b.pos_w = m->has_pos_w ? m->pos_w : nullptr; b.col_scale = m->col_scale; b.col_unit = m->col_unit;
-    b.col_head = m->col_head; b.row_scale_const = 1.f; b.loss = m->loss8; b.dL = m->dL[lv]; b.lddl = m->LDH;
+    b.col_head = m->col_head; b.row_scale_const = 1.f; b.loss = m->loss8; b.lddl = m->LDH;
     b.grad_scale = 1.f;
+    b.nlev = 4;
+    for (int lv = 0; lv < 4; ++lv) { b.logits_lv[lv] = m->logits[lv]; b.dL_lv[lv] = m->dL[lv]; }
     TCN_CHECK(launch_bce(b, m->cfg.max_rows, st));
   }
   finish_loss_kernel<<<1, 32, 0, st>>>(m->loss8, loss_out, m->head_w[0], m->head_w[1], m->head_w[2], m->head_w[3]);

@@ -38,29 +38,6 @@ struct WgSmem {
   static constexpr int kBytes = kStages * kStage + 1024 + 512 + NGA * 32 * 4;
 };
 
-#if 0
-struct WgradTcDev {
-  const BlkMeta* meta;
-  int nblk;
-  const BatchDesc* dyn;
-  int x_unpadded;
-  int n_out, c_in, ntaps;
-  int shift[3];
-  int cbn;          // 32-column blocks per tap = ceil(c_in / 32)
-  int row_splits;
-  float* dW;
-  float* db;        // nullable
-  const float* colscale;
-  int colscale_ld;
-  uint32_t g_drop_thresh;
-  float g_drop_scale;
-  uint32_t g_drop_seed, g_drop_stream;
-  uint32_t x_drop_thresh;
-  float x_drop_scale;
-  uint32_t x_drop_seed, x_drop_stream;
-};
-#endif
-
 // MN-major TF32 operand.  tcgen05 accepts exactly one shared-memory layout for it: 128-byte rows (one frame each,
 // 32 fp32 columns) swizzled with 32-byte atoms (byte-address bits [5,7) ^= bits [7,9); TMA mode 128B_ATOM_32B),
 // K-atoms of 4 frames 512 bytes apart (SBO), 32-column blocks `lbo` bytes apart (LBO).

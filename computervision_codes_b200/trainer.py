@@ -153,8 +153,8 @@ class TemporalTrainer:
         """Kernels of this library enqueued by one step (static count of the executor's schedule)."""
         L = self.ex.cfg.layers_pg + self.ex.cfg.layers_r * self.ex.cfg.num_r
         fwd_layer = 1 if self.ex.cfg.channels == 64 else 2
-        # 2 weight preps + proj split + chan-scale + proj + layers + 3 lateral + 4 heads + 4 bce + finish
-        fwd = 2 + 1 + 1 + 1 + L * fwd_layer + 3 + 4 + 4 + 1
+        # 2 weight preps + proj split + chan-scale + proj + layers + 3 lateral + 4 heads + bce (4 levels) + finish
+        fwd = 2 + 1 + 1 + 1 + L * fwd_layer + 3 + 4 + 1 + 1
         # 4 x (head wgrad + dgrad) + 3 lateral wgrad + L x (dgrad1, wgrad2, wgrad1, dgrad2) + 3 lateral dgrad + proj wgrad
         bwd = 8 + 3 + 4 * L + 3 + 1
         return fwd + bwd + 1  # + sgd

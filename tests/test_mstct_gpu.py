@@ -99,3 +99,42 @@ def test_mstct_loss_composition_a14():
         (ggot,) = torch.autograd.grad(got, y)
         assert abs(float(got) - float(ref)) <= 1e-5 * abs(float(ref))
         assert _maxabs(ggot, gref) <= 1e-7
+
+
+@pytest.mark.parametrize("heads,hd", [(2, 3), (3, 5), (8, 32), (2, 72), (1, 108), (1, 128)])
+def test_attention_kernels_ragged_windows_and_odd_head_dims(heads, hd):
+    """Global_Relational_Block attention (Temporal_Encoder.py:76-88) on the tensor-core kernels, forward and both
+    backward passes, against fp64 softmax attention per (window, head): windows of 1, 5, 63, 64, 65 and 200 frames
+    packed in one call (chunk boundaries at 32 / 64 frames, a single-frame window), head dims that are not multiples
+    of 4 or 8 (scalar loads, zero-padded k-slices) up to the 128 limit."""
+    from computervision_codes_b200.layout import SeqLayout
+    from computervision_codes_b200.mstct import functional as Fn
+
+    lengths = [1, 5, 63, 64, 65, 200]
+    lay = SeqLayout.get(lengths, DEV)
+    d = heads * hd
+    g = torch.Generator().manual_seed(heads * 1000 + hd)
+    q = torch.zeros(lay.rows, d)
+    kv = torch.zeros(lay.rows, 2 * d)
+    go = torch.zeros(lay.rows, d)
+    for s, T in enumerate(lengths):
+        r0 = lay.starts[s]
+        q[r0:r0 + T] = torch.randn(T, d, generator=g)
+        kv[r0:r0 + T] = torch.randn(T, 2 * d, generator=g)
+        go[r0:r0 + T] = torch.randn(T, d, generator=g)
+    qd, kvd = q.to(DEV).requires_grad_(True), kv.to(DEV).requires_grad_(True)
+    o = Fn.attention(qd, kvd, lay, heads)
+    (o * go.to(DEV)).sum().backward()
+    for s, T in enumerate(lengths):
+        r0 = lay.starts[s]
+        q64 = q[r0:r0 + T].double().requires_grad_(True)
+        kv64 = kv[r0:r0 + T].double().requires_grad_(True)
+        qh = q64.view(T, heads, hd).transpose(0, 1)
+        kh = kv64[:, :d].reshape(T, heads, hd).transpose(0, 1)
+        vh = kv64[:, d:].reshape(T, heads, hd).transpose(0, 1)
+        att = torch.softmax(qh @ kh.transpose(1, 2) * hd ** -0.5, dim=-1)
+        ref = (att @ vh).transpose(0, 1).reshape(T, d)
+        (ref * go[r0:r0 + T].double()).sum().backward()
+        assert _maxabs(o[r0:r0 + T], ref) <= 2e-5 * max(1.0, float(ref.abs().max())), (T, "o")
+        assert _maxabs(qd.grad[r0:r0 + T], q64.grad) <= 5e-5 * max(1.0, float(q64.grad.abs().max())), (T, "dq")
+        assert _maxabs(kvd.grad[r0:r0 + T], kv64.grad) <= 5e-5 * max(1.0, float(kv64.grad.abs().max())), (T, "dkv")

@@ -64,6 +64,18 @@ class LayerFwdTcArgs(C.Structure):
         ("meta", C.c_void_p), ("nblk", C.c_int), ("channels", C.c_int),
         ("shift", C.c_int * 3),
         ("drop_p", C.c_float), ("drop_seed", C.c_uint), ("drop_stream", C.c_uint),
+        ("masks", C.c_void_p),
+    ]
+
+
+class LayerBwdTcArgs(C.Structure):
+    _fields_ = [
+        ("gy", C.c_void_p), ("g_rows", C.c_longlong), ("gu", C.c_void_p), ("gx", C.c_void_p),
+        ("masks", C.c_void_p),
+        ("w2t_hi", C.c_void_p), ("w2t_lo", C.c_void_p), ("w1t_hi", C.c_void_p), ("w1t_lo", C.c_void_p),
+        ("meta", C.c_void_p), ("nblk", C.c_int), ("channels", C.c_int),
+        ("shift", C.c_int * 3),
+        ("drop_p", C.c_float),
     ]
 
 
@@ -152,6 +164,7 @@ SIGNATURES = {
     "tcn_wgrad_tc": (C.c_int, [C.POINTER(WgradTcArgs), C.c_void_p]),
     "tcn_layer_fwd": (C.c_int, [C.POINTER(LayerFwdArgs), C.c_void_p]),
     "tcn_layer_fwd_tc": (C.c_int, [C.POINTER(LayerFwdTcArgs), C.c_void_p]),
+    "tcn_layer_bwd_tc": (C.c_int, [C.POINTER(LayerBwdTcArgs), C.c_void_p]),
     "tcn_gemm_tc_supported": (C.c_int, [C.c_int, C.c_int]),
     "tcn_gemm_tc": (C.c_int, [C.POINTER(GemmTcArgs), C.c_void_p]),
     "tcn_split_weight_floats": (C.c_longlong, [C.c_int] * 4),

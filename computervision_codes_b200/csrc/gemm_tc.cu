@@ -221,7 +221,7 @@ __device__ __forceinline__ void epi32_load_residual(float4 (&rr)[8], int lane, i
   }
 }
 
-template <bool RELU, bool RES, bool DROP>
+template <bool RELU, bool RES, bool DROP, bool BIAS = true>
 __device__ __forceinline__ void epilogue_block32(const float (&v)[32], float4* st, int lane, int row_base, int row_hi,
                                                  int n_base, const GemmTcDev& p, uint32_t out_seed,
                                                  const float4 (&rr)[8]) {
@@ -230,7 +230,8 @@ __device__ __forceinline__ void epilogue_block32(const float (&v)[32], float4* s
     st[lane * 8 + (c ^ (lane & 7))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
   __syncwarp();
   const int c = lane & 7, n = n_base + c * 4;
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (BIAS) b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + (lane >> 3), row = row_base + r;
@@ -1147,6 +1148,7 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 32) {
         float u[32], lo[32];
+        uint32_t pos = 0u;   // bit j: h[row, c0 + j] > 0 (the ReLU mask of the backward pass)
         tmem_ld32(lane_base + kU + a * 64 + c0, u);
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -1155,12 +1157,15 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float hv = fmaxf(u[j + e] + bb[e], 0.f);
+            pos |= (hv > 0.f ? 1u : 0u) << (j + e);
             u[j + e] = __uint_as_float(__float_as_uint(hv) & 0xffffe000u);
             lo[j + e] = hv - u[j + e];
           }
         }
         tmem_st32(lane_base + kHhi + c0, u);
         tmem_st32(lane_base + kHlo + c0, lo);
+        const int row = row0 + q * 32 + lane;
+        if (p.masks != nullptr && row < m.hi) p.masks[(size_t)row * 4 + (c0 >> 5)] = pos;
       }
       tmem_st_wait();
       tc_fence_before();
@@ -1208,7 +1213,31 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           tc_fence_before();
           mbar_arrive(&vempty[a]);
         }
-        epilogue_block32<false, true, true>(v, st, lane, row0 + q * 32, m.hi, c0, p.y, out_seed, rr);
+        if (p.masks == nullptr) {
+          epilogue_block32<false, true, true>(v, st, lane, row0 + q * 32, m.hi, c0, p.y, out_seed, rr);
+        } else {
+          // bias + dropout in the accumulator layout (one frame per thread), so that the keep-mask of the frame can be
+          // saved as a bit word for the fused backward kernel
+          const int row = row0 + q * 32 + lane;
+          uint32_t keep = 0xffffffffu;
+          if (p.y.drop_thresh != 0u) keep = 0u;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.y.bias + c0 + j));
+            float f[4] = {1.f, 1.f, 1.f, 1.f};
+            if (p.y.drop_thresh != 0u) {
+              drop_factor4(out_seed, p.y.drop_stream, p.y.drop_thresh, p.y.drop_scale, row, c0 + j, f);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) keep |= (f[e] != 0.f ? 1u : 0u) << (j + e);
+            }
+            v[j + 0] = (v[j + 0] + b.x) * f[0];
+            v[j + 1] = (v[j + 1] + b.y) * f[1];
+            v[j + 2] = (v[j + 2] + b.z) * f[2];
+            v[j + 3] = (v[j + 3] + b.w) * f[3];
+          }
+          if (row < m.hi) p.masks[(size_t)row * 4 + 2 + (c0 >> 5)] = keep;
+          epilogue_block32<false, true, false, false>(v, st, lane, row0 + q * 32, m.hi, c0, p.y, out_seed, rr);
+        }
       }
       ++tcount;
     }
@@ -1237,6 +1266,308 @@ int launch_layer_fwd_tc(const CUtensorMap& mx, const CUtensorMap& w1hi, const CU
   launch_kernel(layer_fwd_tc_kernel, dim3(gx), dim3(LFT_THREADS), lft_smem_bytes(), stream, true, mx, w1hi, w1lo, w2hi, w2lo,
                 p);
   return check_launch("layer_fwd_tc_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused residual layer INPUT GRADIENT (network.py:186-198 backward), 64 channels, one kernel:
+//     gv = keep * gy / (1 - p);  gu = (gv W2) * [h > 0];  gx[t] = gy[t] + sum_k W1_k^T gu[t - s_k]
+// For each tap k the kernel recomputes gu on the 128 frames t0 - s_k .. (1x1 GEMM, A = gv from a TMEM operand slot
+// fed by the split threads), masks it with the ReLU bit words the forward kernel saved, stores the hi / lo halves back
+// to TMEM and feeds them to the tap's GEMM against W1_k^T -- gu never returns from HBM.  The centre tap (s = 0)
+// also writes gu once for the weight-gradient kernel.  Dropout / ReLU masks come as 32-bit words per (frame, half)
+// written by layer_fwd_tc_kernel, so the backward pass hashes nothing.
+//   TMEM (512 columns): gu accumulators U[2] @ 0 / 64, gx accumulators ACC[2] @ 128 / 192, gv operand slots @ 256 / 320
+//   (hi | lo, one 32-channel block each), gu operand @ 384 (hi) / 448 (lo)
+//   warp 0: TMA | warp 1: MMA + TMEM owner | warps 2-5: gy -> gv split | warps 6-9: U -> gu (TMEM + HBM) |
+//   warps 10-13: ACC + gy -> gx
+__global__ void __launch_bounds__(LFT_THREADS, 1)
+layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constant__ CUtensorMap map_w2thi,
+                    const __grid_constant__ CUtensorMap map_w2tlo, const __grid_constant__ CUtensorMap map_w1thi,
+                    const __grid_constant__ CUtensorMap map_w1tlo, const LayerBwdTcDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nblk = p.gx.dyn ? p.gx.dyn->nblk : p.gx.nblk;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* wt = smem_raw + (base - smem_u32(smem_raw));   // slots 0..1: W2^T (kc), 2..7: W1^T (tap * 2 + kc); [hi | lo]
+  uint8_t* at = wt + 8 * 2 * TP_KB;                       // raw gy tiles, LFT_STAGES x 16 KB
+  const uint32_t wt_addr = base;
+  float4* epi = reinterpret_cast<float4*>(at + LFT_STAGES * TP_KA);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(at + LFT_STAGES * TP_KA + LFT_EPI);
+  uint64_t* wfull = bars;
+  uint64_t* full_bar = bars + 1;                  // [4] TMA bytes landed
+  uint64_t* empty_bar = full_bar + LFT_STAGES;    // [4] raw tile read by the 128 split threads
+  uint64_t* a1ready = empty_bar + LFT_STAGES;     // [2] gv operand slot written (128 split threads)
+  uint64_t* a1empty = a1ready + 2;                // [2] ... consumed (tcgen05.commit)
+  uint64_t* ufull = a1empty + 2;                  // [2] gu accumulator complete
+  uint64_t* uempty = ufull + 2;                   // [2] ... read by the gu warps
+  uint64_t* a2ready = uempty + 2;                 // gu operand written to TMEM (128 threads)
+  uint64_t* a2empty = a2ready + 1;                // ... consumed (tcgen05.commit)
+  uint64_t* accfull = a2empty + 1;                // [2] gx accumulator complete
+  uint64_t* accempty = accfull + 2;               // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
+
+  if (threadIdx.x == 0) {
+    mbar_init(wfull, 1);
+    for (int s = 0; s < LFT_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 128);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a1ready[s], 128);
+      mbar_init(&a1empty[s], 1);
+      mbar_init(&ufull[s], 1);
+      mbar_init(&uempty[s], 128);
+      mbar_init(&accfull[s], 1);
+      mbar_init(&accempty[s], 128);
+    }
+    mbar_init(a2ready, 128);
+    mbar_init(a2empty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kU = 0, kAcc = 128, kA1 = 256, kA2hi = 384, kA2lo = 448;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wfull, 8 * 2 * TP_KB);
+      for (int kc = 0; kc < 2; ++kc) {
+        tma_load_2d(wt + kc * 2 * TP_KB, &map_w2thi, wfull, kc * TC_BK, 0);
+        tma_load_2d(wt + kc * 2 * TP_KB + TP_KB, &map_w2tlo, wfull, kc * TC_BK, 0);
+      }
+      for (int kb = 0; kb < 6; ++kb) {
+        tma_load_2d(wt + (2 + kb) * 2 * TP_KB, &map_w1thi, wfull, kb * TC_BK, 0);
+        tma_load_2d(wt + (2 + kb) * 2 * TP_KB + TP_KB, &map_w1tlo, wfull, kb * TC_BK, 0);
+      }
+      int it = 0;
+      for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const BlkMeta m = p.gx.meta[blk];
+        const int row0 = blk * kBlkRows;
+        if (row0 >= m.hi) continue;
+        for (int j = 0; j < 6; ++j, ++it) {
+          const int tap = j >> 1, kc = j & 1;
+          const int s = it % LFT_STAGES;
+          const uint32_t ph = (it / LFT_STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], TP_KA);
+          const int sh = tap == 0 ? p.gx.shift[0] : (tap == 1 ? p.gx.shift[1] : p.gx.shift[2]);
+          tma_load_2d(at + s * TP_KA, &map_gy, &full_bar[s], kc * TC_BK, row0 + sh);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, 64);
+    mbar_wait(wfull, 0);
+    int it = 0, uc = 0, tcount = 0;
+    auto gemm2 = [&](int u, int tap, int ab) {  // ACC[ab] (+)= gu_tap W1_tap^T, gu taken from TMEM
+      mbar_wait(a2ready, (uint32_t)(u & 1));
+      if (tap == 0) mbar_wait(&accempty[ab], (((uint32_t)tcount >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t tacc = tmem_base + kAcc + ab * 64;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t b_hi = wt_addr + (2 + tap * 2 + (k >> 2)) * 2 * TP_KB + (k & 3) * 32, b_lo = b_hi + TP_KB;
+          const uint64_t dbh = umma_desc_sw128(b_hi), dbl = umma_desc_sw128(b_lo);
+          umma_tf32_ts(tacc, tmem_base + kA2lo + k * 8, dbh, idesc, (tap | k) != 0);
+          umma_tf32_ts(tacc, tmem_base + kA2hi + k * 8, dbl, idesc, 1u);
+          umma_tf32_ts(tacc, tmem_base + kA2hi + k * 8, dbh, idesc, 1u);
+        }
+        umma_commit(a2empty);
+        if (tap == 2) umma_commit(&accfull[ab]);
+      }
+      __syncwarp();
+    };
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      const BlkMeta m = p.gx.meta[blk];
+      if (blk * kBlkRows >= m.hi) continue;
+      const int ab = tcount & 1;
+      for (int tap = 0; tap < 3; ++tap, ++uc) {
+        const int ub = uc & 1;
+        mbar_wait(&uempty[ub], (((uint32_t)uc >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + kU + ub * 64;
+        for (int kc = 0; kc < 2; ++kc, ++it) {
+          const int ta = it & 1;
+          mbar_wait(&a1ready[ta], ((uint32_t)it >> 1) & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_hi = tmem_base + kA1 + ta * 64, a_lo = a_hi + 32;
+            const uint32_t b_hi = wt_addr + kc * 2 * TP_KB, b_lo = b_hi + TP_KB;
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; ++k) {
+              const uint64_t dbh = umma_desc_sw128(b_hi + k * 32), dbl = umma_desc_sw128(b_lo + k * 32);
+              umma_tf32_ts(tacc, a_lo + k * 8, dbh, idesc, (kc | k) != 0);
+              umma_tf32_ts(tacc, a_hi + k * 8, dbl, idesc, 1u);
+              umma_tf32_ts(tacc, a_hi + k * 8, dbh, idesc, 1u);
+            }
+            umma_commit(&a1empty[ta]);
+            if (kc == 1) umma_commit(&ufull[ub]);
+          }
+          __syncwarp();
+        }
+        if (tap > 0) gemm2(uc - 1, tap - 1, ab);
+      }
+      gemm2(uc - 1, 2, ab);
+      ++tcount;
+    }
+  } else if (warp < 6) {
+    // ===================== gy -> gv (warps 2..5): one frame = one thread = one TMEM lane =====================
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    int it = 0;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      const BlkMeta m = p.gx.meta[blk];
+      const int row0 = blk * kBlkRows;
+      if (row0 >= m.hi) continue;
+      for (int j = 0; j < 6; ++j, ++it) {
+        const int tap = j >> 1, kc = j & 1;
+        const int s = it % LFT_STAGES, ta = it & 1;
+        const int sh = tap == 0 ? p.gx.shift[0] : (tap == 1 ? p.gx.shift[1] : p.gx.shift[2]);
+        const int src = row0 + r + sh;
+        const bool inside = src >= m.lo && src < m.hi;
+        uint32_t keep = 0u;
+        if (inside) keep = p.use_drop ? __ldg(p.masks + (size_t)src * 4 + 2 + kc) : 0xffffffffu;
+        mbar_wait(&full_bar[s], (it / LFT_STAGES) & 1);
+        const float4* row = reinterpret_cast<const float4*>(at + s * TP_KA) + r * 8;
+        float hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = row[c ^ (r & 7)];
+          const float x0 = (keep >> (4 * c + 0)) & 1u ? v.x * p.drop_scale : 0.f;
+          const float x1 = (keep >> (4 * c + 1)) & 1u ? v.y * p.drop_scale : 0.f;
+          const float x2 = (keep >> (4 * c + 2)) & 1u ? v.z * p.drop_scale : 0.f;
+          const float x3 = (keep >> (4 * c + 3)) & 1u ? v.w * p.drop_scale : 0.f;
+          hi[4 * c + 0] = __uint_as_float(__float_as_uint(x0) & 0xffffe000u); lo[4 * c + 0] = x0 - hi[4 * c + 0];
+          hi[4 * c + 1] = __uint_as_float(__float_as_uint(x1) & 0xffffe000u); lo[4 * c + 1] = x1 - hi[4 * c + 1];
+          hi[4 * c + 2] = __uint_as_float(__float_as_uint(x2) & 0xffffe000u); lo[4 * c + 2] = x2 - hi[4 * c + 2];
+          hi[4 * c + 3] = __uint_as_float(__float_as_uint(x3) & 0xffffe000u); lo[4 * c + 3] = x3 - hi[4 * c + 3];
+        }
+        mbar_arrive(&empty_bar[s]);
+        mbar_wait(&a1empty[ta], (((uint32_t)it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        tmem_st32(lane_base + kA1 + ta * 64, hi);
+        tmem_st32(lane_base + kA1 + ta * 64 + 32, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&a1ready[ta]);
+      }
+    }
+  } else if (warp < 10) {
+    // ===================== U -> gu (warps 6..9): ReLU mask, hi / lo halves back to TMEM, centre tap to HBM ==========
+    const int q = warp & 3;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    float4* st = epi + (warp - 6) * 256;
+    int uc = 0;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      const BlkMeta m = p.gx.meta[blk];
+      const int row0 = blk * kBlkRows;
+      if (row0 >= m.hi) continue;
+      for (int tap = 0; tap < 3; ++tap, ++uc) {
+        const int ub = uc & 1;
+        const int sh = tap == 0 ? p.gx.shift[0] : (tap == 1 ? p.gx.shift[1] : p.gx.shift[2]);
+        const int src = row0 + q * 32 + lane + sh;
+        const bool inside = src >= m.lo && src < m.hi;
+        uint32_t pos0 = 0u, pos1 = 0u;
+        if (inside) {
+          const uint2 w = __ldg(reinterpret_cast<const uint2*>(p.masks + (size_t)src * 4));
+          pos0 = w.x; pos1 = w.y;
+        }
+        mbar_wait(&ufull[ub], ((uint32_t)uc >> 1) & 1);
+        mbar_wait(a2empty, ((uint32_t)uc & 1) ^ 1);   // the previous tap's GEMM has consumed the gu operand
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          const uint32_t pos = c0 == 0 ? pos0 : pos1;
+          float u[32], hi[32], lo[32];
+          tmem_ld32(lane_base + kU + ub * 64 + c0, u);
+          if (c0 == 32) {
+            tc_fence_before();
+            mbar_arrive(&uempty[ub]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            u[j] = (pos >> j) & 1u ? u[j] : 0.f;
+            hi[j] = __uint_as_float(__float_as_uint(u[j]) & 0xffffe000u);
+            lo[j] = u[j] - hi[j];
+          }
+          tmem_st32(lane_base + kA2hi + c0, hi);
+          tmem_st32(lane_base + kA2lo + c0, lo);
+          if (sh == 0 && p.gu.Y != nullptr) {   // the centre tap is gu of this tile: keep it for the weight gradients
+            float4 none[8];
+            epilogue_block32<false, false, false, false>(u, st, lane, row0 + q * 32, m.hi, c0, p.gu, 0u, none);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(a2ready);
+      }
+    }
+  } else {
+    // ===================== ACC + gy -> gx (warps 10..13) =====================
+    const int q = warp & 3;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    float4* st = epi + (warp - 6) * 256;
+    int tcount = 0;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      const BlkMeta m = p.gx.meta[blk];
+      const int row0 = blk * kBlkRows;
+      if (row0 >= m.hi) continue;
+      const int ab = tcount & 1;
+      float4 rr0[8], rr1[8];   // gy rows of the tile (residual), fetched while the MMAs run
+      epi32_load_residual(rr0, lane, row0 + q * 32, m.hi, 0, p.gx);
+      epi32_load_residual(rr1, lane, row0 + q * 32, m.hi, 32, p.gx);
+      mbar_wait(&accfull[ab], ((uint32_t)tcount >> 1) & 1);
+      tc_fence_after();
+      {
+        float v[32];
+        tmem_ld32(lane_base + kAcc + ab * 64, v);
+        epilogue_block32<false, true, false, false>(v, st, lane, row0 + q * 32, m.hi, 0, p.gx, 0u, rr0);
+        tmem_ld32(lane_base + kAcc + ab * 64 + 32, v);
+        tc_fence_before();
+        mbar_arrive(&accempty[ab]);
+        epilogue_block32<false, true, false, false>(v, st, lane, row0 + q * 32, m.hi, 32, p.gx, 0u, rr1);
+      }
+      ++tcount;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u));
+}
+
+int launch_layer_bwd_tc(const CUtensorMap& mgy, const CUtensorMap& w2thi, const CUtensorMap& w2tlo,
+                        const CUtensorMap& w1thi, const CUtensorMap& w1tlo, const LayerBwdTcDev& p, int cap_nblk,
+                        cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e =
+        cudaFuncSetAttribute(layer_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lft_smem_bytes());
+    if (e != cudaSuccess) {
+      set_error("layer_bwd_tc: smem attribute: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return TCN_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int nb = cap_nblk > 0 ? cap_nblk : p.gx.nblk;
+  int gx = num_sms();
+  if (gx > nb) gx = nb;
+  launch_kernel(layer_bwd_tc_kernel, dim3(gx), dim3(LFT_THREADS), lft_smem_bytes(), stream, true, mgy, w2thi, w2tlo, w1thi,
+                w1tlo, p);
+  return check_launch("layer_bwd_tc_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1694,5 +2025,35 @@ extern "C" int tcn_layer_fwd_tc(const tcn_layer_fwd_tc_args* a, tcn_stream_t str
   p.y.drop_thresh = a->drop_p > 0.f ? drop_thresh(a->drop_p) : 0u;
   p.y.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
   p.y.drop_seed = a->drop_seed; p.y.drop_stream = a->drop_stream;
+  p.masks = a->masks;
   return launch_layer_fwd_tc(mx, w1h, w1l, w2h, w2l, p, 0, (cudaStream_t)stream);
+}
+
+extern "C" int tcn_layer_bwd_tc(const tcn_layer_bwd_tc_args* a, tcn_stream_t stream) {
+  TCN_REQUIRE(a && a->gy && a->gx && a->masks && a->w2t_hi && a->w2t_lo && a->w1t_hi && a->w1t_lo && a->meta,
+              "tcn_layer_bwd_tc: null pointer");
+  if (a->channels != 64) {
+    set_error("tcn_layer_bwd_tc: the fused kernel is built for 64 channels (got %d); use tcn_gemm_tc", a->channels);
+    return TCN_ERR_UNSUPPORTED;
+  }
+  TCN_REQUIRE(a->nblk > 0 && a->g_rows > 0, "tcn_layer_bwd_tc: empty problem");
+  TCN_REQUIRE(a->drop_p >= 0.f && a->drop_p < 1.f, "tcn_layer_bwd_tc: drop_p must be in [0, 1)");
+  TCN_REQUIRE(a->shift[0] == 0 || a->shift[1] == 0 || a->shift[2] == 0, "tcn_layer_bwd_tc: one tap must have shift 0");
+  CUtensorMap mg, w2h, w2l, w1h, w1l;
+  TCN_CHECK(make_tensor_map_2d(&mg, a->gy, a->g_rows, 64, 64, TC_BM));
+  TCN_CHECK(make_tensor_map_2d(&w2h, a->w2t_hi, 64, 64, 64, 64));
+  TCN_CHECK(make_tensor_map_2d(&w2l, a->w2t_lo, 64, 64, 64, 64));
+  TCN_CHECK(make_tensor_map_2d(&w1h, a->w1t_hi, 64, 192, 192, 64));
+  TCN_CHECK(make_tensor_map_2d(&w1l, a->w1t_lo, 64, 192, 192, 64));
+  LayerBwdTcDev p;
+  memset(&p, 0, sizeof(p));
+  p.gu.Y = a->gu; p.gu.ldy = 64; p.gu.N = 64; p.gu.drop_scale = 1.f; p.gu.in_drop_scale = 1.f;
+  p.gx.Y = a->gx; p.gx.ldy = 64; p.gx.N = 64; p.gx.R = a->gy; p.gx.ldr = 64;
+  p.gx.meta = reinterpret_cast<const BlkMeta*>(a->meta); p.gx.nblk = a->nblk; p.gx.ntaps = 3; p.gx.kbp = 2; p.gx.c_in = 64;
+  for (int i = 0; i < 3; ++i) p.gx.shift[i] = -a->shift[i];
+  p.gx.drop_scale = 1.f; p.gx.in_drop_scale = 1.f;
+  p.masks = a->masks;
+  p.use_drop = a->drop_p > 0.f ? 1 : 0;
+  p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
+  return launch_layer_bwd_tc(mg, w2h, w2l, w1h, w1l, p, 0, (cudaStream_t)stream);
 }

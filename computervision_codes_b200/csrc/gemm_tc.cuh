@@ -177,9 +177,25 @@ int launch_split_batched(const SplitJob* jobs_dev, int njobs, const float* param
 struct LayerTcDev {
   GemmTcDev h;
   GemmTcDev y;
+  uint32_t* masks;   // nullable: (rows, 4) bit words per frame {h > 0 [0..31], [32..63], dropout keep [0..31], [32..63]}
 };
 int launch_layer_fwd_tc(const CUtensorMap& mx, const CUtensorMap& w1hi, const CUtensorMap& w1lo, const CUtensorMap& w2hi,
                         const CUtensorMap& w2lo, const LayerTcDev& p, int cap_nblk, cudaStream_t stream);
+
+// Fused residual layer input gradient on tcgen05 (gemm_tc.cu: layer_bwd_tc_kernel):
+//   gu = ((keep * gy / (1 - p)) W2) * [h > 0];   gx[t] = gy[t] + sum_k W1_k^T gu[t - s_k]
+// gu: store of gu (Y, ldy; meta / nblk / dyn; shift[] = the taps of the transposed conv, -s_k); gx: Y = gx, R = gy.
+// masks: the (rows, 4) bit words written by layer_fwd_tc_kernel; drop_scale = 1 / (1 - p) (1 in eval mode).
+struct LayerBwdTcDev {
+  GemmTcDev gu;
+  GemmTcDev gx;
+  const uint32_t* masks;
+  float drop_scale;
+  int use_drop;
+};
+int launch_layer_bwd_tc(const CUtensorMap& mgy, const CUtensorMap& w2thi, const CUtensorMap& w2tlo,
+                        const CUtensorMap& w1thi, const CUtensorMap& w1tlo, const LayerBwdTcDev& p, int cap_nblk,
+                        cudaStream_t stream);
 
 int launch_gemm_tc(const CUtensorMap& mx, const CUtensorMap& mwhi, const CUtensorMap& mwlo, const GemmTcDev& p,
                    int cap_nblk, cudaStream_t stream, const CUtensorMap* mx32 = nullptr);

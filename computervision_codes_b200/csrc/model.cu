@@ -81,6 +81,8 @@ struct tcn_model {
   };
   bool use_tc = false;
   bool fused_tc = true;   // TCN_NO_FUSED_TC=1: previous forward schedule (A/B)
+  bool fused_bwd = true;  // TCN_NO_FUSED_BWD=1: two input-gradient launches per layer (A/B)
+  std::vector<uint32_t*> masks;  // per layer (rows, 4) bit words: ReLU / dropout masks saved by the fused forward
   std::map<long, TcW> tcw;
   std::map<std::pair<const float*, int>, CUtensorMap> xmaps;
   std::map<std::pair<const float*, int>, CUtensorMap> xmaps32;  // same tensors, 32-row boxes (slab kernel)
@@ -430,6 +432,8 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
   std::vector<size_t> o_act(m->L + 1), o_H(m->L);
   for (int i = 0; i <= m->L; ++i) o_act[i] = carve((size_t)rows * C * 4);
   for (int i = 0; i < m->L; ++i) o_H[i] = carve((size_t)rows * C * 4);
+  std::vector<size_t> o_masks(m->L);
+  for (int i = 0; i < m->L; ++i) o_masks[i] = carve((size_t)rows * 16);
   size_t o_P[3], o_log[4], o_dL[4], o_Gp[4];
   std::vector<size_t> o_gpool(m->L + 4), o_gus(m->L);
   for (int i = 0; i < 3; ++i) o_P[i] = carve((size_t)rows * C * 4);
@@ -466,6 +470,7 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
   m->tc_wlo = reinterpret_cast<float*>(m->ws + o_tcwlo);
   for (int i = 0; i <= m->L; ++i) m->act.push_back(reinterpret_cast<float*>(m->ws + o_act[i]));
   for (int i = 0; i < m->L; ++i) m->H.push_back(reinterpret_cast<float*>(m->ws + o_H[i]));
+  for (int i = 0; i < m->L; ++i) m->masks.push_back(reinterpret_cast<uint32_t*>(m->ws + o_masks[i]));
   for (int i = 0; i < 3; ++i) m->P[i] = reinterpret_cast<float*>(m->ws + o_P[i]);
   for (int i = 0; i < 4; ++i) {
     m->logits[i] = reinterpret_cast<float*>(m->ws + o_log[i]);
@@ -502,6 +507,7 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
   // tcgen05 path available? (needs the driver's tensor-map encoder; TCN_NO_TCGEN05=1 forces the mma.sync kernels)
   m->use_tc = (std::getenv("TCN_NO_TCGEN05") == nullptr) && (C % 4 == 0);
   m->fused_tc = std::getenv("TCN_NO_FUSED_TC") == nullptr;
+  m->fused_bwd = m->fused_tc && std::getenv("TCN_NO_FUSED_BWD") == nullptr;
   m->wg_multi = std::getenv("TCN_WGRAD_MULTI") != nullptr;
   if (m->use_tc) {
     for (auto& kv : m->tcw) {
@@ -693,6 +699,7 @@ static int model_forward(tcn_model* m, const float* x, long x_rows, int training
       p.y.drop_thresh = pl > 0.f ? drop_thresh(pl) : 0u;
       p.y.drop_scale = pl > 0.f ? 1.f / (1.f - pl) : 1.f;
       p.y.drop_seed = 0u; p.y.drop_stream = (uint32_t)l;
+      p.masks = (save_h && m->fused_bwd) ? m->masks[l] : nullptr;
       TCN_CHECK(launch_layer_fwd_tc(xm->second, w1->second.mh, w1->second.ml, w2->second.mh, w2->second.ml, p, m->max_blk,
                                     st));
     } else if (C == 64 && !(m->use_tc && m->max_blk > 2 * num_sms())) {
@@ -812,8 +819,35 @@ static int model_backward(tcn_model* m, const float* x, long x_rows, const float
       int sh[3];
       layer_shifts(m, l, sh);
       float* gu = m->gus[l];
-      // gu = (gv W2) * [h > 0],   gv = keep * gy / (1 - p) applied as gy is loaded
-      {
+      const bool fused = m->fused_bwd && m->use_tc && C == 64;
+      if (fused) {
+        // one launch: gu = (gv W2) * [h > 0] recomputed per tap in tensor memory, gx = gy + sum_k W1_k^T gu[t - s_k];
+        // gu of the tile itself is written once for the weight gradients (gemm_tc.cu: layer_bwd_tc_kernel)
+        const long k2 = reinterpret_cast<const float*>(m->wf_(m->wf_w2T[l])) - m->wf;
+        const long k1 = reinterpret_cast<const float*>(m->wf_(m->wf_w1T[l])) - m->wf;
+        auto w2 = m->tcw.find(k2), w1 = m->tcw.find(k1);
+        TCN_REQUIRE(w1 != m->tcw.end() && w2 != m->tcw.end(), "tcn_model backward: missing split weights for the fused layer");
+        const auto gkey = std::make_pair(g, C);
+        auto gm = m->xmaps.find(gkey);
+        if (gm == m->xmaps.end()) {
+          CUtensorMap map;
+          TCN_CHECK(make_tensor_map_2d(&map, g, m->cfg.max_rows, C, C, TC_BM));
+          gm = m->xmaps.emplace(gkey, map).first;
+        }
+        LayerBwdTcDev p;
+        memset(&p, 0, sizeof(p));
+        p.gu.Y = gu; p.gu.ldy = C; p.gu.N = C; p.gu.drop_scale = 1.f; p.gu.in_drop_scale = 1.f;
+        p.gx.Y = m->gpool[gi]; p.gx.ldy = C; p.gx.N = C; p.gx.R = g; p.gx.ldr = C;
+        p.gx.meta = m->meta; p.gx.nblk = m->max_blk; p.gx.dyn = m->desc; p.gx.ntaps = 3; p.gx.kbp = 2; p.gx.c_in = C;
+        for (int i = 0; i < 3; ++i) p.gx.shift[i] = -sh[i];
+        p.gx.drop_scale = 1.f; p.gx.in_drop_scale = 1.f;
+        p.masks = m->masks[l];
+        p.use_drop = pl > 0.f ? 1 : 0;
+        p.drop_scale = pl > 0.f ? 1.f / (1.f - pl) : 1.f;
+        TCN_CHECK(launch_layer_bwd_tc(gm->second, w2->second.mh, w2->second.ml, w1->second.mh, w1->second.ml, p, m->max_blk,
+                                      st));
+      } else {
+        // gu = (gv W2) * [h > 0],   gv = keep * gy / (1 - p) applied as gy is loaded
         TapGemmDev p = base_tapgemm(m);
         p.X = g; p.ldx = C; p.Wf = m->wf_(m->wf_w2T[l]); p.Y = gu; p.ldy = C; p.M = m->H[l]; p.ldm = C;
         if (pl > 0.f) { p.in_drop_thresh = drop_thresh(pl); p.in_drop_scale = 1.f / (1.f - pl); p.in_drop_stream = (uint32_t)l; }
@@ -831,14 +865,14 @@ static int model_backward(tcn_model* m, const float* x, long x_rows, const float
         w1.dW = m->g_(m->off_w1[l]); w1.db = m->g_(m->off_b1[l]);
         TCN_CHECK(wgrad_pair(m, w1, w2, x_rows, ws));
       }
-      {  // gx = gy + sum_k W1_k^T gu[t - s_k]
+      if (!fused) {  // gx = gy + sum_k W1_k^T gu[t - s_k]
         TapGemmDev p = base_tapgemm(m);
         p.X = gu; p.ldx = C; p.Wf = m->wf_(m->wf_w1T[l]); p.Y = m->gpool[gi]; p.ldy = C; p.R = g; p.ldr = C;
         p.ntaps = 3;
         for (int i = 0; i < 3; ++i) p.shift[i] = -sh[i];
         TCN_CHECK(gemm(m, p, C, C, st));
-        g = m->gpool[gi++];
       }
+      g = m->gpool[gi++];
     }
     if (multi) {  // every weight gradient of this stage in one launch, behind the stage's input-gradient chain
       const tcn_model::WgMulti& t = m->wgm[tr];

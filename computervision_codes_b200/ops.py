@@ -119,13 +119,16 @@ def layer_fwd(x, w1f, w2f, b1, b2, lay: SeqLayout, shifts, save_h=True, drop_p=0
     return y, h
 
 
-def layer_fwd_tc(x, w1, w2, b1, b2, lay: SeqLayout, shifts, save_h=True, drop_p=0.0, seed=0, stream_id=0):
-    """Fused residual layer forward on tcgen05 / TMEM (64 channels): returns (y, h).  w1 (64, 64, 3), w2 (64, 64, 1)
-    are the torch weights (split into TF32 hi / lo halves here)."""
+def layer_fwd_tc(x, w1, w2, b1, b2, lay: SeqLayout, shifts, save_h=True, drop_p=0.0, seed=0, stream_id=0,
+                 save_masks=False):
+    """Fused residual layer forward on tcgen05 / TMEM (64 channels): returns (y, h) or (y, h, masks).  w1 (64, 64, 3),
+    w2 (64, 64, 1) are the torch weights (split into TF32 hi / lo halves here); masks: (rows, 4) int32 bit words
+    (ReLU / dropout masks) for layer_bwd_tc."""
     lib = _lib.load()
     assert x.is_contiguous() and x.shape[1] == 64
     y = torch.zeros_like(x)
     h = torch.zeros_like(x) if save_h else None
+    masks = torch.zeros(x.shape[0], 4, device=x.device, dtype=torch.int32) if save_masks else None
     w1h, w1l = split_weight(w1)
     w2h, w2l = split_weight(w2)
     a = _lib.LayerFwdTcArgs()
@@ -136,8 +139,27 @@ def layer_fwd_tc(x, w1, w2, b1, b2, lay: SeqLayout, shifts, save_h=True, drop_p=
     for i, s in enumerate(shifts):
         a.shift[i] = int(s)
     a.drop_p, a.drop_seed, a.drop_stream = float(drop_p), int(seed) & 0xFFFFFFFF, int(stream_id) & 0xFFFFFFFF
+    a.masks = _lib.ptr(masks)
     _lib.check(lib.tcn_layer_fwd_tc(C.byref(a), _lib.stream_ptr()), "tcn_layer_fwd_tc")
-    return y, h
+    return (y, h, masks) if save_masks else (y, h)
+
+
+def layer_bwd_tc(gy, masks, w1, w2, lay: SeqLayout, shifts, drop_p=0.0):
+    """Fused input gradient of a residual layer (64 channels): returns (gu, gx); gu feeds the weight gradients."""
+    lib = _lib.load()
+    assert gy.is_contiguous() and gy.shape[1] == 64 and masks.is_contiguous()
+    gu, gx = torch.zeros_like(gy), torch.zeros_like(gy)
+    w2h, w2l = split_weight(w2, transpose=True)
+    w1h, w1l = split_weight(w1, transpose=True)
+    a = _lib.LayerBwdTcArgs()
+    a.gy, a.g_rows, a.gu, a.gx, a.masks = _lib.ptr(gy), gy.shape[0], _lib.ptr(gu), _lib.ptr(gx), _lib.ptr(masks)
+    a.w2t_hi, a.w2t_lo, a.w1t_hi, a.w1t_lo = _lib.ptr(w2h), _lib.ptr(w2l), _lib.ptr(w1h), _lib.ptr(w1l)
+    a.meta, a.nblk, a.channels = _lib.ptr(lay.meta), lay.nblk, gy.shape[1]
+    for i, s in enumerate(shifts):
+        a.shift[i] = int(s)
+    a.drop_p = float(drop_p)
+    _lib.check(lib.tcn_layer_bwd_tc(C.byref(a), _lib.stream_ptr()), "tcn_layer_bwd_tc")
+    return gu, gx
 
 
 def split_weight(w, transpose: bool = False):
@@ -307,8 +329,10 @@ class DilatedResidualFn(torch.autograd.Function):
         x = _f32c(x)
         Cc = w1.shape[0]
         shifts = tap_shifts(dilation, causal)
+        masks = None
         if Cc == 64 and os.environ.get("TCN_NO_TCGEN05") is None:  # one fused launch, tcgen05 / TMEM
-            y, h = layer_fwd_tc(x, w1, w2, _f32c(b1.detach()), _f32c(b2.detach()), lay, shifts, True, p, seed, stream_id)
+            y, h, masks = layer_fwd_tc(x, w1, w2, _f32c(b1.detach()), _f32c(b2.detach()), lay, shifts, True, p, seed,
+                                       stream_id, save_masks=True)
         elif Cc == 64:  # one fused launch, mma.sync
             y, h = layer_fwd(x, prep_weight(w1), prep_weight(w2), _f32c(b1.detach()), _f32c(b2.detach()), lay, shifts,
                              True, p, seed, stream_id)
@@ -318,6 +342,7 @@ class DilatedResidualFn(torch.autograd.Function):
                         seed=seed, stream_id=stream_id)
         ctx.save_for_backward(x, h, w1, w2)
         ctx.lay, ctx.shifts, ctx.p, ctx.seed, ctx.stream_id = lay, shifts, p, seed, stream_id
+        ctx.masks = masks if os.environ.get("TCN_NO_FUSED_BWD") is None else None
         return y
 
     @staticmethod
@@ -330,13 +355,16 @@ class DilatedResidualFn(torch.autograd.Function):
         gw2 = torch.zeros(Cc, Cc, 1, device=gy.device, dtype=torch.float32)
         gb2 = torch.zeros(Cc, device=gy.device, dtype=torch.float32)
         wgrad(gy, h, lay, Cc, Cc, (0,), gw2, gb2, g_drop_p=p, seed=ctx.seed, stream_id=ctx.stream_id)
-        gu = tapgemm(gy, prep_weight(w2, transpose=True), lay, Cc, Cc, (0,), relu_mask=h, in_drop_p=p, seed=ctx.seed,
-                     stream_id=ctx.stream_id)
+        gx = None
+        if ctx.masks is not None:  # one fused launch for gu and gx (tcgen05 / TMEM)
+            gu, gx = layer_bwd_tc(gy, ctx.masks, w1, w2, lay, shifts, p)
+        else:
+            gu = tapgemm(gy, prep_weight(w2, transpose=True), lay, Cc, Cc, (0,), relu_mask=h, in_drop_p=p,
+                         seed=ctx.seed, stream_id=ctx.stream_id)
         gw1 = torch.zeros(Cc, Cc, 3, device=gy.device, dtype=torch.float32)
         gb1 = torch.zeros(Cc, device=gy.device, dtype=torch.float32)
         wgrad(gu, x, lay, Cc, Cc, shifts, gw1, gb1)
-        gx = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and gx is None:
             gx = tapgemm(gu, prep_weight(w1, transpose=True), lay, Cc, Cc, tuple(-s for s in shifts), residual=gy)
         return gx, gw1, gb1, gw2.view_as(w2), gb2, None, None, None, None, None, None
 

@@ -157,8 +157,23 @@ typedef struct {
   const int* meta; int nblk; int channels;
   int shift[3];
   float drop_p; unsigned drop_seed; unsigned drop_stream;
+  unsigned* masks;   /* optional (rows, 4) bit words per frame for tcn_layer_bwd_tc: h > 0 [0..63], dropout keep [0..63] */
 } tcn_layer_fwd_tc_args;
 int tcn_layer_fwd_tc(const tcn_layer_fwd_tc_args* args, tcn_stream_t stream);
+/* Input gradient of the same layer in one launch (what autograd computes for network.py:193-198 / :178-183):
+ *   gu = ((keep * gy / (1 - p)) W2) * [h > 0]   (written for the weight gradients),
+ *   gx[t] = gy[t] + sum_k W1[:, :, k]^T gu[t - shift[k]].
+ * masks: the bit words written by tcn_layer_fwd_tc; w2t_* / w1t_*: tcn_split_weight with transpose = 1;
+ * shift = the forward taps; drop_p = 0 in eval mode.  The weight gradients run on tcn_wgrad_tc (gy, h) / (gu, x). */
+typedef struct {
+  const float* gy; long long g_rows; float* gu; float* gx;
+  const unsigned* masks;
+  const float* w2t_hi; const float* w2t_lo; const float* w1t_hi; const float* w1t_lo;
+  const int* meta; int nblk; int channels;
+  int shift[3];
+  float drop_p;
+} tcn_layer_bwd_tc_args;
+int tcn_layer_bwd_tc(const tcn_layer_bwd_tc_args* args, tcn_stream_t stream);
 
 /* ---- whole-model executor -------------------------------------------------------------------------
  * VideoNas(fpn) of network.py:14-68 (BaseCausalTCN -> num_r x Refinement -> FPN -> 4 heads x 4 levels)

@@ -164,6 +164,62 @@ def test_layer_train_mode_dropout_matches_oracle_with_same_mask():
     assert float((other != keep_rows).float().mean()) > 0.4
 
 
+@pytest.mark.parametrize("lengths,shifts,p", [([300, 129, 1, 128], (-4, 0, 4), 0.0), ([999, 7], (-2, -1, 0), 0.5),
+                                              ([1800], (-512, 0, 512), 0.5), ([130, 260, 20000], (-1024, -512, 0), 0.3),
+                                              ([40000], (-1, 0, 1), 0.5)])
+def test_fused_layer_backward_matches_unfused_kernels_and_fp64(lengths, shifts, p):
+    """tcn_layer_bwd_tc (one launch: gu recomputed per tap in tensor memory, ReLU / dropout masks as bit words saved by
+    tcn_layer_fwd_tc) against (1) the two tap-GEMM launches it replaces and (2) the fp64 closed form of the layer's
+    backward pass (oracle).  Ragged batches, taps leaving the sequence, more 128-frame tiles than SMs."""
+    from computervision_codes_b200 import ops
+    from computervision_codes_b200.layout import SeqLayout
+
+    torch.manual_seed(len(lengths) + shifts[2])
+    C = 64
+    lay = SeqLayout(lengths, DEV)
+    w1 = (torch.randn(C, C, 3) / (3 * C) ** 0.5).to(DEV)
+    w2 = (torch.randn(C, C, 1) / C ** 0.5).to(DEV)
+    b1, b2 = (torch.randn(C) * 0.1).to(DEV), (torch.randn(C) * 0.1).to(DEV)
+    x = torch.zeros(lay.rows, C, device=DEV)
+    gy = torch.zeros(lay.rows, C, device=DEV)
+    for s, T in enumerate(lengths):
+        x[lay.starts[s]:lay.starts[s] + T] = torch.randn(T, C, device=DEV)
+        gy[lay.starts[s]:lay.starts[s] + T] = torch.randn(T, C, device=DEV)
+    seed, sid = 77, 3
+    y, h, masks = ops.layer_fwd_tc(x, w1, w2, b1, b2, lay, shifts, True, p, seed, sid, save_masks=True)
+    y0, h0 = ops.layer_fwd_tc(x, w1, w2, b1, b2, lay, shifts, True, p, seed, sid)
+    assert torch.equal(y, y0) and torch.equal(h, h0)          # saving the masks does not change the forward result
+    # the bit words are the masks the unfused kernels recompute
+    keep_rows = ops.dropout_keep_mask(lay.rows, C, p, seed, sid, DEV) if p > 0 else torch.ones(lay.rows, C, device=DEV)
+    bits = torch.arange(32, device=DEV)
+    unpack = lambda wds: ((wds.long().unsqueeze(-1) >> bits) & 1).reshape(wds.shape[0], -1)
+    for s, T in enumerate(lengths):
+        sl = slice(lay.starts[s], lay.starts[s] + T)
+        assert torch.equal(unpack(masks[sl, 0:2]) != 0, h[sl] > 0)
+        assert torch.equal(unpack(masks[sl, 2:4]) != 0, keep_rows[sl] != 0)
+    gu, gx = ops.layer_bwd_tc(gy, masks, w1, w2, lay, shifts, p)
+    gu_ref = ops.tapgemm(gy, ops.prep_weight(w2, transpose=True), lay, C, C, (0,), relu_mask=h, in_drop_p=p, seed=seed,
+                         stream_id=sid)
+    gx_ref = ops.tapgemm(gu_ref, ops.prep_weight(w1, transpose=True), lay, C, C, tuple(-s for s in shifts), residual=gy)
+    torch.cuda.synchronize()
+    for s, T in enumerate(lengths):
+        sl = slice(lay.starts[s], lay.starts[s] + T)
+        assert _maxabs(gu[sl], gu_ref[sl]) <= 2e-5, (s, T)
+        assert _maxabs(gx[sl], gx_ref[sl]) <= 2e-5, (s, T)
+        # fp64: gv = keep * gy / (1 - p); gu = (gv W2) * [h > 0]; gx[t] = gy[t] + sum_k W1_k^T gu[t - s_k]
+        gyd, kd = gy[sl].double(), keep_rows[sl].double()
+        gud = ((gyd * kd / (1.0 - p)) @ w2[:, :, 0].double()) * (h[sl] > 0).double()
+        gxd = gyd.clone()
+        for k, sh in enumerate(shifts):
+            contrib = gud @ w1[:, :, k].double()              # lands on frame t + s_k
+            if sh >= 0:
+                if sh < T:
+                    gxd[sh:] += contrib[:T - sh]
+            elif -sh < T:
+                gxd[:T + sh] += contrib[-sh:]
+        assert _maxabs(gu[sl], gud) <= 2e-5 and _maxabs(gx[sl], gxd) <= 3e-5, (s, T)
+
+
 def test_stage_against_golden(golden_dir):
     from computervision_codes_b200.tcn import BaseCausalTCN, Refinement
 

@@ -156,6 +156,7 @@ class BceArgs(C.Structure):
 SIGNATURES = {
     "tcn_version": (C.c_int, []),
     "tcn_last_error": (C.c_char_p, []),
+    "tcn_launch_count": (C.c_longlong, []),
     "tcn_device_info": (C.c_int, [C.POINTER(C.c_int)] * 4),
     "tcn_prep_weight_floats": (C.c_longlong, [C.c_int] * 4),
     "tcn_prep_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

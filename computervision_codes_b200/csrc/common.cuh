@@ -10,7 +10,8 @@ namespace tcn {
 // ----------------------------------------------------------------------------------------------
 // error plumbing (host)
 void set_error(const char* fmt, ...);
-int check_launch(const char* what);  // cudaGetLastError() -> TCN_ERR_CUDA
+int check_launch(const char* what);  // cudaGetLastError() -> TCN_ERR_CUDA; counts the launch on success
+long long launch_count();
 int num_sms();
 bool pdl_enabled();  // TCN_NO_PDL=1 turns programmatic dependent launch off
 

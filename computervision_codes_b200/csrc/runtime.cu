@@ -1,4 +1,5 @@
 // Library runtime: error strings, device queries.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -8,6 +9,7 @@
 namespace tcn {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};  // kernels of this library enqueued (or captured into a graph) so far
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -22,8 +24,11 @@ int check_launch(const char* what) {
     set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
     return TCN_ERR_CUDA;
   }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return TCN_OK;
 }
+
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 bool pdl_enabled() {
   static int v = -1;
@@ -48,6 +53,7 @@ int num_sms() {
 
 extern "C" int tcn_version(void) { return TCN_VERSION; }
 extern "C" const char* tcn_last_error(void) { return tcn::g_err; }
+extern "C" long long tcn_launch_count(void) { return tcn::launch_count(); }
 
 extern "C" int tcn_device_info(int* cc_major, int* cc_minor, int* nsm, int* built_for_sm) {
   int dev = 0;

@@ -127,6 +127,7 @@ class TemporalTrainer:
         self._outs = [None, None]
         self.rng = torch.Generator().manual_seed(seed)
         self.training = True
+        self._launches_per_step = None
         # {lr, weight_decay, grad_scale} live on the device: the captured graph follows set_lr() / an LR schedule
         self._hyper_host = torch.tensor([lr, weight_decay, 1.0 / max(1, world_size)], dtype=torch.float32).pin_memory()
         self.hyper = self._hyper_host.to(dev)
@@ -150,14 +151,19 @@ class TemporalTrainer:
         return out
 
     def launches_per_step(self):
-        """Kernels of this library enqueued by one step (static count of the executor's schedule)."""
-        L = self.ex.cfg.layers_pg + self.ex.cfg.layers_r * self.ex.cfg.num_r
-        fwd_layer = 1 if self.ex.cfg.channels == 64 else 2
-        # 2 weight preps + proj split + chan-scale + proj + layers + 3 lateral + 4 heads + bce (4 levels) + finish
-        fwd = 2 + 1 + 1 + 1 + L * fwd_layer + 3 + 4 + 1 + 1
-        # 4 x (head wgrad + dgrad) + 3 lateral wgrad + L x (dgrad1, wgrad2, wgrad1, dgrad2) + 3 lateral dgrad + proj wgrad
-        bwd = 8 + 3 + 4 * L + 3 + 1
-        return fwd + bwd + 1  # + sgd
+        """Kernels of this library one step enqueues: counted by the library itself (tcn_launch_count) around the
+        step body -- under a CUDA graph, around its capture; every replay launches the same kernels."""
+        assert self._launches_per_step is not None, "launches_per_step(): run a step first"
+        return self._launches_per_step
+
+    def _counted_body(self, slot):
+        from . import _lib
+
+        lib = _lib.load()
+        n0 = lib.tcn_launch_count()
+        out = self._body(slot)
+        self._launches_per_step = int(lib.tcn_launch_count() - n0)
+        return out
 
     def _stage(self, slot, x_rows, labels_u8, lengths):
         """Copy one batch into an input slot on the current stream (H2D when the sources are pinned host tensors)."""
@@ -224,7 +230,7 @@ class TemporalTrainer:
         seed = int(torch.randint(0, 2 ** 31 - 1, (1,), generator=self.rng).item())
         self.ex.set_batch(lay, seed)
         if not self.use_graph:
-            out = self._body(slot)
+            out = self._counted_body(slot)
         else:
             if self.graphs[slot] is None:
                 # warm-up outside capture (lazy module loading, cudaFuncSetAttribute), then capture once per slot
@@ -234,7 +240,7 @@ class TemporalTrainer:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._outs[slot] = self._body(slot)
+                    self._outs[slot] = self._counted_body(slot)
                 self.flat_p.copy_(snap_p)
                 self.graphs[slot] = g
             self.graphs[slot].replay()

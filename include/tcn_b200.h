@@ -38,6 +38,9 @@ typedef struct CUstream_st* tcn_stream_t;
 /* ---- library ---------------------------------------------------------------------------------- */
 int tcn_version(void);
 const char* tcn_last_error(void);
+/* Kernels this library has enqueued on a stream (or captured into a CUDA graph) since it was loaded; process wide.
+ * bench.py's "gpu_launches" is the difference over one step x the steps timed. */
+long long tcn_launch_count(void);
 /* compute capability of the current device and the architecture the kernels were built for (100) */
 int tcn_device_info(int* cc_major, int* cc_minor, int* num_sms, int* built_for_sm);
 

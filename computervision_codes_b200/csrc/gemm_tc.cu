@@ -432,7 +432,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   if (has_rows) {
     if (warp == 0) {
       // ===================== TMA producer =====================
-      if (lane == 0) {
+      if (elect_one()) {
         const int xrow = row0 + (p.x_unpadded ? m.in_delta : 0);
         int tap = 0, kc = 0;
         for (int kb = 0; kb < kblocks; ++kb) {
@@ -455,7 +455,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const int s = kb % TC_STAGES, ta = kb & 1;
         mbar_wait(&aready[ta], ((uint32_t)kb >> 1) & 1);   // implies full_bar[s]: the split threads waited for it
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_hi = tmem_base + kAslot + ta * 64, a_lo = a_hi + 32;
           const uint32_t b_hi = base + s * S::kStage + S::kA, b_lo = b_hi + S::kB;
 #pragma unroll
@@ -581,7 +581,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(wfull, kblocks * 2 * TP_KB);
       for (int kb = 0; kb < kblocks; ++kb) {
         tma_load_2d(wt + kb * 2 * TP_KB, &map_whi, wfull, kb * TC_BK, ntile * 64);
@@ -623,7 +623,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         const uint32_t ph = (it / TP_STAGES) & 1;
         mbar_wait(&ready_bar[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_hi = at_addr + s * 2 * TP_KA, a_lo = a_hi + TP_KA;
           const uint32_t b_hi = wt_addr + kb * 2 * TP_KB, b_lo = b_hi + TP_KB;
 #pragma unroll
@@ -766,7 +766,7 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int blk = tile % nblk, ntile = tile / nblk;
@@ -810,7 +810,7 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const uint32_t ph = (it / NST) & 1;
         mbar_wait(&ready_bar[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_hi = base + s * S::kStage, a_lo = a_hi + S::kA;
           const uint32_t b_hi = a_hi + 2 * S::kA, b_lo = b_hi + S::kB;
 #pragma unroll
@@ -1012,7 +1012,7 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(wfull, 8 * 2 * TP_KB);
       for (int kb = 0; kb < 6; ++kb) {
         tma_load_2d(wt + kb * 2 * TP_KB, &map_w1hi, wfull, kb * TC_BK, 0);
@@ -1047,7 +1047,7 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       mbar_wait(hready, (uint32_t)(t & 1));
       mbar_wait(&vempty[a], (((uint32_t)t >> 1) & 1) ^ 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t tacc = tmem_base + kV + a * 64;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -1073,7 +1073,7 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const int ta = it & 1;
         mbar_wait(&aready[ta], ((uint32_t)it >> 1) & 1);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_hi = tmem_base + kA + ta * 64, a_lo = a_hi + 32;
           const uint32_t b_hi = wt_addr + j * 2 * TP_KB, b_lo = b_hi + TP_KB;
 #pragma unroll
@@ -1340,7 +1340,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_con
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(wfull, 8 * 2 * TP_KB);
       for (int kc = 0; kc < 2; ++kc) {
         tma_load_2d(wt + kc * 2 * TP_KB, &map_w2thi, wfull, kc * TC_BK, 0);
@@ -1375,7 +1375,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_con
       mbar_wait(a2ready, (uint32_t)(u & 1));
       if (tap == 0) mbar_wait(&accempty[ab], (((uint32_t)tcount >> 1) & 1) ^ 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t tacc = tmem_base + kAcc + ab * 64;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -1403,7 +1403,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_con
           const int ta = it & 1;
           mbar_wait(&a1ready[ta], ((uint32_t)it >> 1) & 1);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t a_hi = tmem_base + kA1 + ta * 64, a_lo = a_hi + 32;
             const uint32_t b_hi = wt_addr + kc * 2 * TP_KB, b_lo = b_hi + TP_KB;
 #pragma unroll
@@ -1633,7 +1633,7 @@ gemm_tc_slab_kernel(const __grid_constant__ CUtensorMap map_x32, const __grid_co
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(wfull, 6 * 2 * TP_KB);
       for (int kb = 0; kb < 6; ++kb) {
         tma_load_2d(wt + kb * 2 * TP_KB, &map_whi, wfull, kb * TC_BK, ntile * 64);
@@ -1672,7 +1672,7 @@ gemm_tc_slab_kernel(const __grid_constant__ CUtensorMap map_x32, const __grid_co
         const uint32_t ph = (it >> 1) & 1;
         mbar_wait(&ready_bar[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
 #pragma unroll
           for (int tap = 0; tap < 3; ++tap) {
             const int sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);

@@ -69,6 +69,22 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One lane of a warp, chosen by the hardware (elect.sync; every lane of the warp must reach it).  ptxas then KNOWS that
+// exactly one thread runs the guarded region and issues tcgen05.mma / tcgen05.commit / TMA from uniform registers back to
+// back.  With `if (lane == 0)` it cannot, and wraps every such instruction in an ELECT / BRA.U.ANY loop over the
+// "possibly several" active threads: ~10 SASS instructions per MMA, which made the issuing warp the bottleneck of the
+// fused layer kernels (profiles/r1_fused_stress_source_stalls.txt).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
                : "memory");

@@ -121,7 +121,7 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
   if (total_chunks > 0) {
     if (warp == 0) {
       // ===================== TMA producer =====================
-      if (lane == 0) {
+      if (elect_one()) {
         int it = 0;
         for (int blk = blk_begin; blk < blk_end; ++blk) {
           const BlkMeta m = p.meta[blk];
@@ -154,7 +154,7 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
         const uint32_t ph = (it / WG_STAGES) & 1;
         mbar_wait(&ready_bar[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_hi = base + s * WG_STAGE, a_lo = a_hi + WG_RAW;
           const uint32_t b_hi = a_hi + 4 * WG_ATOM, b_lo = b_hi + WG_RAW;
 #pragma unroll

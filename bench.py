@@ -295,7 +295,7 @@ def main():
     trainer._prefetched = None
     e2e_value = frames_all / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel (persistent tcgen05 tap GEMM), timed live with CUDA events
+    # ---- roofline of the dominant kernel, timed live with CUDA events
     roof = measure_layer_roofline(model, lengths, batches[a.warmup], dev)
 
     def shutdown():
@@ -351,52 +351,115 @@ def _graph_time(fn, n=24):
 
 
 def measure_layer_roofline(model, lengths, batch, dev):
-    """Dominant kernel by time share (profiles/r1_launches_summary.txt, r1_tcn_step_timeline.txt):
-    `gemm_tc_persist_kernel`, the persistent tcgen05 tap GEMM behind every 1x1 contraction of the step.  Reported here:
-    its most frequent use, the input gradient of a residual layer's 1x1 conv
-    gu = ((keep * gy / (1 - p)) W2) * [h > 0]   (dropout mask regenerated as gy is loaded, ReLU mask in the epilogue),
-    timed live on this step's batch shape and on the TERL stress shape (64 x 8000 frames) where the HBM roofline is the
-    binding limit.  Algorithmic bytes per frame: 12*C (read gy, read h, write gu)."""
-    from computervision_codes_b200 import ops
+    """Roofline of the step's dominant kernel, timed live with CUDA events (graph of 24 launches on the current stream).
+
+    A train step is 41 residual layers x three launches -- `layer_fwd_tc_kernel` (fused forward), `layer_bwd_tc_kernel`
+    (fused input gradient) and `wgrad_tc_pair_kernel` (both weight gradients) -- plus a few dozen one-off launches.
+    All three are timed here on this step's batch shape and on the TERL stress shape (64 x 8000 frames, where the HBM
+    roofline is the binding limit); the one with the largest time per step is the dominant kernel and fills `roofline`,
+    the others are listed under `roofline.kernels`.  Algorithmic bytes per frame (DESIGN.md section 3, C = 64 fp32):
+      layer_fwd_tc  12*C + 16  read x, write h, write y (+ 16 B of ReLU / dropout bit words)
+      layer_bwd_tc  12*C + 16  read gy, write gu, write gx (+ the bit words)
+      wgrad_tc_pair 16*C       read gu, x, gy, h (the 64 x 256 weight-gradient tile is negligible)"""
+    import ctypes as Ct
+
+    from computervision_codes_b200 import _lib, ops
     from computervision_codes_b200.layout import SeqLayout
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak, src = 6650.0, "fallback"
     if os.path.exists(peaks_path):
         peak, src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
+    lib = _lib.load()
     layer = model.PG.layers[4]
-    hi, lo = ops.split_weight(layer.conv_1x1.weight.detach(), transpose=True)
+    d = int(layer.conv_dilated.dilation[0])
+    shifts = (-2 * d, -d, 0)
+    C = C_MAPS
+    w1, w2 = layer.conv_dilated.weight.detach(), layer.conv_1x1.weight.detach()
+    b1, b2 = layer.conv_dilated.bias.detach().contiguous(), layer.conv_1x1.bias.detach().contiguous()
+    w1h, w1l = ops.split_weight(w1)
+    w2h, w2l = ops.split_weight(w2)
+    w1th, w1tl = ops.split_weight(w1, transpose=True)
+    w2th, w2tl = ops.split_weight(w2, transpose=True)
+    p_drop = 0.5
 
     def run(lens, nbuf):
         lay = SeqLayout.get(lens, dev)
-        gy = [torch.randn(lay.rows, C_MAPS, device=dev) for _ in range(nbuf)]
-        h = [torch.randn(lay.rows, C_MAPS, device=dev).relu_() for _ in range(nbuf)]
-        out = [torch.zeros(lay.rows, C_MAPS, device=dev) for _ in range(nbuf)]
+        rnd = lambda: [torch.randn(lay.rows, C, device=dev) for _ in range(nbuf)]
+        xs, gys = rnd(), rnd()
+        ys, hs, gus, gxs = ([torch.zeros(lay.rows, C, device=dev) for _ in range(nbuf)] for _ in range(4))
+        masks = [torch.zeros(lay.rows, 4, device=dev, dtype=torch.int32) for _ in range(nbuf)]
+        gw1, gb1 = torch.zeros(C, C, 3, device=dev), torch.zeros(C, device=dev)
+        gw2, gb2 = torch.zeros(C, C, 1, device=dev), torch.zeros(C, device=dev)
         it = [0]
 
-        def fn():
+        def fwd():
             i = it[0] % nbuf
             it[0] += 1
-            ops.gemm_tc(gy[i], hi, lo, lay, C_MAPS, C_MAPS, (0,), out=out[i], relu_mask=h[i], in_drop_p=0.5,
-                        in_drop_rescale=True, seed=7, stream_id=4)
+            a = _lib.LayerFwdTcArgs()
+            a.x, a.x_rows, a.y, a.h = xs[i].data_ptr(), lay.rows, ys[i].data_ptr(), hs[i].data_ptr()
+            a.w1_hi, a.w1_lo, a.w2_hi, a.w2_lo = w1h.data_ptr(), w1l.data_ptr(), w2h.data_ptr(), w2l.data_ptr()
+            a.b1, a.b2 = b1.data_ptr(), b2.data_ptr()
+            a.meta, a.nblk, a.channels = lay.meta.data_ptr(), lay.nblk, C
+            for k, s_ in enumerate(shifts):
+                a.shift[k] = s_
+            a.drop_p, a.drop_seed, a.drop_stream = p_drop, 7, 4
+            a.masks = masks[i].data_ptr()
+            _lib.check(lib.tcn_layer_fwd_tc(Ct.byref(a), _lib.stream_ptr()), "tcn_layer_fwd_tc")
 
-        ms = _graph_time(fn)
+        def bwd():
+            i = it[0] % nbuf
+            it[0] += 1
+            a = _lib.LayerBwdTcArgs()
+            a.gy, a.g_rows, a.gu, a.gx = gys[i].data_ptr(), lay.rows, gus[i].data_ptr(), gxs[i].data_ptr()
+            a.masks = masks[i].data_ptr()
+            a.w2t_hi, a.w2t_lo, a.w1t_hi, a.w1t_lo = w2th.data_ptr(), w2tl.data_ptr(), w1th.data_ptr(), w1tl.data_ptr()
+            a.meta, a.nblk, a.channels = lay.meta.data_ptr(), lay.nblk, C
+            for k, s_ in enumerate(shifts):
+                a.shift[k] = s_
+            a.drop_p = p_drop
+            _lib.check(lib.tcn_layer_bwd_tc(Ct.byref(a), _lib.stream_ptr()), "tcn_layer_bwd_tc")
+
+        def wg():
+            i = it[0] % nbuf
+            it[0] += 1
+            ops.wgrad_tc_layer_pair(gus[i], xs[i], gys[i], hs[i], lay, shifts, gw1, gb1, gw2, gb2, drop_p=p_drop, seed=7,
+                                    stream_id=4)
+
         frames = sum(lens)
-        return frames, ms, 12 * C_MAPS * frames / (ms * 1e-3) / 1e9
+        out = {}
+        for name, fn, byt in (("layer_fwd_tc_kernel", fwd, 12 * C + 16), ("layer_bwd_tc_kernel", bwd, 12 * C + 16),
+                              ("wgrad_tc_pair_kernel", wg, 16 * C)):
+            ms = _graph_time(fn)
+            out[name] = {"frames_per_launch": frames, "ms_per_launch": ms, "alg_bytes_per_frame": byt,
+                         "achieved": byt * frames / (ms * 1e-3) / 1e9}
+            out[name]["frac"] = out[name]["achieved"] / peak
+        return out
 
-    frames, ms, gbs = run([lengths[v] for v in batch], 8)
-    sframes, sms, sgbs = run([8000] * 64, 6)
-    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, from the committed ncu capture
+    here = run([lengths[v] for v in batch], 8)       # fwd() fills the masks bwd() reads
+    stress = run([8000] * 64, 6)
+    what = {"layer_fwd_tc_kernel": "fused residual layer forward: dilated conv + ReLU + 1x1 conv + dropout + residual, "
+                                   "both GEMMs with A from tensor memory",
+            "layer_bwd_tc_kernel": "fused residual layer input gradient: gu recomputed per tap in tensor memory",
+            "wgrad_tc_pair_kernel": "both weight gradients of a residual layer, contraction over frames on tcgen05"}
+    dom = max(here, key=lambda k: here[k]["ms_per_launch"])   # each runs once per layer: largest time per step
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, from the committed ncu capture
     tpath = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
-    return {"bound": "hbm", "kernel": "gemm_tc_persist_kernel (tcgen05 tap GEMM; here: input gradient of the 1x1 conv "
-                                      "with ReLU mask and dropout-on-load)",
-            "achieved": gbs, "peak": peak, "peak_source": src, "unit": "GB/s", "frac": gbs / peak, "traffic": traffic,
-            "frames_per_launch": frames, "ms_per_launch": ms,
-            "stress_shape": {"frames_per_launch": sframes, "ms_per_launch": sms, "achieved": sgbs, "frac": sgbs / peak},
-            "note": "at this step's batch (a few MB per activation, L2-resident, one wave of CTAs) the kernel is "
-                    "latency-bound; the stress shape (64 x 8000 frames, 131 MB per activation) is HBM-bound"}
+        tj = json.load(open(tpath))
+        if tj.get("kernel") == dom:
+            traffic = tj.get("traffic_bytes_per_launch")
+    kernels = {k: {"what": what[k], "step_shape": here[k], "stress_shape": stress[k]} for k in here}
+    return {"bound": "hbm", "kernel": dom + " (" + what[dom] + ")",
+            "achieved": here[dom]["achieved"], "peak": peak, "peak_source": src, "unit": "GB/s",
+            "frac": here[dom]["frac"], "traffic": traffic,
+            "frames_per_launch": here[dom]["frames_per_launch"], "ms_per_launch": here[dom]["ms_per_launch"],
+            "alg_bytes_per_frame": here[dom]["alg_bytes_per_frame"],
+            "stress_shape": {k: stress[dom][k] for k in ("frames_per_launch", "ms_per_launch", "achieved", "frac")},
+            "kernels": kernels,
+            "note": "dominant = largest time per step among the three per-layer kernels (41 launches each); at this "
+                    "step's batch (a few MB per activation, L2-resident, one tile per CTA) every kernel is latency-bound; "
+                    "the stress shape (64 x 8000 frames, 131 MB per activation) is where HBM binds"}
 
 
 if __name__ == "__main__":

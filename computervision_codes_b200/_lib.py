@@ -163,6 +163,7 @@ SIGNATURES = {
     "tcn_tapgemm": (C.c_int, [C.POINTER(TapGemmArgs), C.c_void_p]),
     "tcn_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     "tcn_wgrad_tc": (C.c_int, [C.POINTER(WgradTcArgs), C.c_void_p]),
+    "tcn_wgrad_tc_pair": (C.c_int, [C.POINTER(WgradTcArgs), C.POINTER(WgradTcArgs), C.c_void_p]),
     "tcn_layer_fwd": (C.c_int, [C.POINTER(LayerFwdArgs), C.c_void_p]),
     "tcn_layer_fwd_tc": (C.c_int, [C.POINTER(LayerFwdTcArgs), C.c_void_p]),
     "tcn_layer_bwd_tc": (C.c_int, [C.POINTER(LayerBwdTcArgs), C.c_void_p]),

@@ -420,7 +420,8 @@ int launch_wgrad_tc_pair(const CUtensorMap& mx0, const CUtensorMap& mg0, WgradTc
 
 using namespace tcn;
 
-extern "C" int tcn_wgrad_tc(const tcn_wgrad_tc_args* a, tcn_stream_t stream) {
+// argument check + tensor maps + device descriptor of one tcn_wgrad_tc_args problem
+static int wgrad_tc_from_args(const tcn_wgrad_tc_args* a, CUtensorMap* mx, CUtensorMap* mg, WgradTcDev* out) {
   TCN_REQUIRE(a && a->g && a->x && a->dw && a->meta, "tcn_wgrad_tc: null pointer");
   TCN_REQUIRE(a->nblk > 0 && a->c_in > 0 && a->n_out > 0 && a->ntaps >= 1 && a->ntaps <= 3, "tcn_wgrad_tc: bad shape");
   if (a->ldx % 4 != 0 || a->ldg % 4 != 0 || a->c_in % 4 != 0) {
@@ -431,9 +432,8 @@ extern "C" int tcn_wgrad_tc(const tcn_wgrad_tc_args* a, tcn_stream_t stream) {
   TCN_REQUIRE((reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->g) & 15) == 0,
               "tcn_wgrad_tc: x and g must be 16-byte aligned");
   TCN_REQUIRE(a->g_drop_p >= 0.f && a->g_drop_p < 1.f, "tcn_wgrad_tc: g_drop_p must be in [0, 1)");
-  CUtensorMap mx, mg;
-  TCN_CHECK(make_tensor_map_2d(&mx, a->x, a->x_rows, a->c_in, a->ldx, WG_RC, true));
-  TCN_CHECK(make_tensor_map_2d(&mg, a->g, a->g_rows, a->g_cols, a->ldg, WG_RC, true));
+  TCN_CHECK(make_tensor_map_2d(mx, a->x, a->x_rows, a->c_in, a->ldx, WG_RC, true));
+  TCN_CHECK(make_tensor_map_2d(mg, a->g, a->g_rows, a->g_cols, a->ldg, WG_RC, true));
   WgradTcDev p;
   memset(&p, 0, sizeof(p));
   p.meta = reinterpret_cast<const BlkMeta*>(a->meta); p.nblk = a->nblk; p.dyn = nullptr;
@@ -445,5 +445,23 @@ extern "C" int tcn_wgrad_tc(const tcn_wgrad_tc_args* a, tcn_stream_t stream) {
   p.g_drop_scale = a->g_drop_p > 0.f ? 1.f / (1.f - a->g_drop_p) : 1.f;
   p.g_drop_seed = a->drop_seed; p.g_drop_stream = a->drop_stream;
   p.x_drop_scale = 1.f;
+  *out = p;
+  return TCN_OK;
+}
+
+extern "C" int tcn_wgrad_tc(const tcn_wgrad_tc_args* a, tcn_stream_t stream) {
+  CUtensorMap mx, mg;
+  WgradTcDev p;
+  TCN_CHECK(wgrad_tc_from_args(a, &mx, &mg, &p));
   return launch_wgrad_tc(mx, mg, p, 0, (cudaStream_t)stream);
+}
+
+extern "C" int tcn_wgrad_tc_pair(const tcn_wgrad_tc_args* a0, const tcn_wgrad_tc_args* a1, tcn_stream_t stream) {
+  CUtensorMap mx0, mg0, mx1, mg1;
+  WgradTcDev p0, p1;
+  TCN_CHECK(wgrad_tc_from_args(a0, &mx0, &mg0, &p0));
+  TCN_CHECK(wgrad_tc_from_args(a1, &mx1, &mg1, &p1));
+  TCN_REQUIRE(a0->meta == a1->meta && a0->nblk == a1->nblk, "tcn_wgrad_tc_pair: both problems must share the block table");
+  TCN_REQUIRE(!a0->x_unpadded && !a1->x_unpadded, "tcn_wgrad_tc_pair: padded operands only");
+  return launch_wgrad_tc_pair(mx0, mg0, p0, mx1, mg1, p1, 0, (cudaStream_t)stream);
 }

@@ -84,10 +84,8 @@ def wgrad(g, x, lay: SeqLayout, n_out, c_in, shifts, dw, db=None, x_unpadded=Fal
     _lib.check(lib.tcn_wgrad(C.byref(a), _lib.stream_ptr()), "tcn_wgrad")
 
 
-def wgrad_tc(g, x, lay: SeqLayout, n_out, c_in, shifts, dw, db=None, x_unpadded=False, colscale=None, g_drop_p=0.0,
-             seed=0, stream_id=0):
-    """tcgen05/TMA weight gradient (same contract as wgrad)."""
-    lib = _lib.load()
+def _wgrad_tc_args(g, x, lay: SeqLayout, n_out, c_in, shifts, dw, db=None, x_unpadded=False, colscale=None,
+                   g_drop_p=0.0, seed=0, stream_id=0):
     assert g.is_contiguous() and x.is_contiguous() and dw.is_contiguous()
     a = _lib.WgradTcArgs()
     a.g, a.ldg, a.g_cols, a.g_rows = _lib.ptr(g), g.shape[1], min(round_up(n_out, 4), g.shape[1]), g.shape[0]
@@ -99,7 +97,25 @@ def wgrad_tc(g, x, lay: SeqLayout, n_out, c_in, shifts, dw, db=None, x_unpadded=
         a.shift[i] = int(s)
     a.dw, a.db = _lib.ptr(dw), _lib.ptr(db)
     a.g_drop_p, a.drop_seed, a.drop_stream = float(g_drop_p), int(seed) & 0xFFFFFFFF, int(stream_id) & 0xFFFFFFFF
+    return a
+
+
+def wgrad_tc(g, x, lay: SeqLayout, n_out, c_in, shifts, dw, db=None, x_unpadded=False, colscale=None, g_drop_p=0.0,
+             seed=0, stream_id=0):
+    """tcgen05/TMA weight gradient (same contract as wgrad)."""
+    lib = _lib.load()
+    a = _wgrad_tc_args(g, x, lay, n_out, c_in, shifts, dw, db, x_unpadded, colscale, g_drop_p, seed, stream_id)
     _lib.check(lib.tcn_wgrad_tc(C.byref(a), _lib.stream_ptr()), "tcn_wgrad_tc")
+
+
+def wgrad_tc_layer_pair(gu, x, gy, h, lay: SeqLayout, shifts, gw1, gb1, gw2, gb2, drop_p=0.0, seed=0, stream_id=0):
+    """Both weight gradients of a residual layer in one launch: gW1 / gb1 += (gu, x over the taps), gW2 / gb2 += (gv, h)
+    with gv = keep * gy / (1 - p) regenerated from (seed, stream_id)."""
+    lib = _lib.load()
+    Cc = gu.shape[1]
+    a1 = _wgrad_tc_args(gu, x, lay, Cc, Cc, shifts, gw1, gb1)
+    a2 = _wgrad_tc_args(gy, h, lay, Cc, Cc, (0,), gw2, gb2, g_drop_p=drop_p, seed=seed, stream_id=stream_id)
+    _lib.check(lib.tcn_wgrad_tc_pair(C.byref(a1), C.byref(a2), _lib.stream_ptr()), "tcn_wgrad_tc_pair")
 
 
 def layer_fwd(x, w1f, w2f, b1, b2, lay: SeqLayout, shifts, save_h=True, drop_p=0.0, seed=0, stream_id=0):

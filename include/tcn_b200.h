@@ -134,6 +134,10 @@ typedef struct {
   float g_drop_p; unsigned drop_seed; unsigned drop_stream;
 } tcn_wgrad_tc_args;
 int tcn_wgrad_tc(const tcn_wgrad_tc_args* args, tcn_stream_t stream);
+/* The two weight gradients of one residual layer (gW1 / gb1 from (gu, x), gW2 / gb2 from (gy, h); network.py:186-198
+ * backward) in ONE launch: the grid is split between the two problems.  Both must share meta / nblk, have
+ * n_out <= 64 and padded operands.  This is the launch the executor issues per layer. */
+int tcn_wgrad_tc_pair(const tcn_wgrad_tc_args* w1, const tcn_wgrad_tc_args* w2, tcn_stream_t stream);
 
 /* ---- fused residual layer, forward ---------------------------------------------------------------
  * y = x + Dropout_p(W2 relu(W1 (*)_d x + b1) + b2), one launch: DilatedResidualLayer.forward

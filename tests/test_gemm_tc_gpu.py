@@ -158,3 +158,29 @@ def test_wgrad_tc_matches_fp64(lengths, c_in, n_out, shifts, unpadded):
     # accumulates: a second call doubles the result
     ops.wgrad_tc(g_dev, x_dev, lay, n_out, c_in, shifts, dw, db, x_unpadded=unpadded, g_drop_p=p, seed=11, stream_id=4)
     assert _maxabs(dw, 2 * dw_ref) <= 4e-5 * max(1.0, float(dw_ref.abs().max()))
+
+
+@pytest.mark.parametrize("lengths,shifts,p", [([300, 129, 1], (-4, 0, 4), 0.5), ([2250] * 8, (-64, -32, 0), 0.0),
+                                              ([5000, 77], (-1024, 0, 1024), 0.3)])
+def test_wgrad_tc_layer_pair_matches_two_launches(lengths, shifts, p):
+    """tcn_wgrad_tc_pair (both weight gradients of a residual layer in one launch, the executor's per-layer launch)
+    against two tcn_wgrad_tc launches on the same operands (same kernel body: equal up to the order of the fp32 atomics)."""
+    from computervision_codes_b200 import ops
+    from computervision_codes_b200.layout import SeqLayout
+
+    torch.manual_seed(sum(lengths) % 1000)
+    C = 64
+    lay = SeqLayout.get(lengths, DEV)
+    bufs = [torch.zeros(lay.rows, C, device=DEV) for _ in range(4)]
+    for s, T in enumerate(lengths):
+        for b in bufs:
+            b[lay.starts[s]:lay.starts[s] + T] = torch.randn(T, C, device=DEV)
+    gu, x, gy, h = bufs
+    z = lambda *shape: torch.zeros(*shape, device=DEV)
+    gw1, gb1, gw2, gb2 = z(C, C, 3), z(C), z(C, C, 1), z(C)
+    ops.wgrad_tc_layer_pair(gu, x, gy, h, lay, shifts, gw1, gb1, gw2, gb2, drop_p=p, seed=5, stream_id=9)
+    rw1, rb1, rw2, rb2 = z(C, C, 3), z(C), z(C, C, 1), z(C)
+    ops.wgrad_tc(gu, x, lay, C, C, shifts, rw1, rb1)
+    ops.wgrad_tc(gy, h, lay, C, C, (0,), rw2, rb2, g_drop_p=p, seed=5, stream_id=9)
+    for got, ref in ((gw1, rw1), (gb1, rb1), (gw2, rw2), (gb2, rb2)):
+        assert _maxabs(got, ref) <= 2e-5 * max(1.0, float(ref.abs().max()))

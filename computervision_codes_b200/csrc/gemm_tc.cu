@@ -1276,8 +1276,12 @@ int launch_layer_fwd_tc(const CUtensorMap& mx, const CUtensorMap& w1hi, const CU
 // to TMEM and feeds them to the tap's GEMM against W1_k^T -- gu never returns from HBM.  The centre tap (s = 0)
 // also writes gu once for the weight-gradient kernel.  Dropout / ReLU masks come as 32-bit words per (frame, half)
 // written by layer_fwd_tc_kernel, so the backward pass hashes nothing.
-//   TMEM (512 columns): gu accumulators U[2] @ 0 / 64, gx accumulators ACC[2] @ 128 / 192, gv operand slots @ 256 / 320
-//   (hi | lo, one 32-channel block each), gu operand @ 384 (hi) / 448 (lo)
+//   TMEM (512 columns): gu accumulators U[2] @ 0 / 64 -- the gu warps write the hi half of the masked gu back IN PLACE, so
+//   U[b] is also the hi operand of the tap GEMM --, gx accumulators ACC[2] @ 128 / 192, gv operand slots @ 256 / 320
+//   (hi | lo, one 32-channel block each), lo halves of gu @ 384 / 448.  Both gu operand buffers alternate per tap: the gu
+//   warps convert tap n + 1 while the tensor pipe runs the tap GEMM of tap n.  The MMA warp issues one flat, software-
+//   pipelined sequence over (tile, tap) steps: U(0), then { U(n + 1), G2(n) } -- tcgen05.mma executes in issue order, so
+//   U(n + 2) overwriting buffer n & 1 after G2(n) read it needs no barrier.
 //   warp 0: TMA | warp 1: MMA + TMEM owner | warps 2-5: gy -> gv split | warps 6-9: U -> gu (TMEM + HBM) |
 //   warps 10-13: ACC + gy -> gx
 __global__ void __launch_bounds__(LFT_THREADS, 1)
@@ -1300,10 +1304,8 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_con
   uint64_t* a1ready = empty_bar + LFT_STAGES;     // [2] gv operand slot written (128 split threads)
   uint64_t* a1empty = a1ready + 2;                // [2] ... consumed (tcgen05.commit)
   uint64_t* ufull = a1empty + 2;                  // [2] gu accumulator complete
-  uint64_t* uempty = ufull + 2;                   // [2] ... read by the gu warps
-  uint64_t* a2ready = uempty + 2;                 // gu operand written to TMEM (128 threads)
-  uint64_t* a2empty = a2ready + 1;                // ... consumed (tcgen05.commit)
-  uint64_t* accfull = a2empty + 1;                // [2] gx accumulator complete
+  uint64_t* a2ready = ufull + 2;                  // [2] gu operand (hi in place of U, lo) written to TMEM (128 threads)
+  uint64_t* accfull = a2ready + 2;                // [2] gx accumulator complete
   uint64_t* accempty = accfull + 2;               // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
 
@@ -1317,12 +1319,10 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_con
       mbar_init(&a1ready[s], 128);
       mbar_init(&a1empty[s], 1);
       mbar_init(&ufull[s], 1);
-      mbar_init(&uempty[s], 128);
+      mbar_init(&a2ready[s], 128);
       mbar_init(&accfull[s], 1);
       mbar_init(&accempty[s], 128);
     }
-    mbar_init(a2ready, 128);
-    mbar_init(a2empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
@@ -1334,7 +1334,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t kU = 0, kAcc = 128, kA1 = 256, kA2hi = 384, kA2lo = 448;
+  constexpr uint32_t kU = 0, kAcc = 128, kA1 = 256, kA2lo = 384;
   pdl_launch_dependents();
   pdl_wait();
 
@@ -1370,58 +1370,60 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_con
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, 64);
     mbar_wait(wfull, 0);
-    int it = 0, uc = 0, tcount = 0;
-    auto gemm2 = [&](int u, int tap, int ab) {  // ACC[ab] (+)= gu_tap W1_tap^T, gu taken from TMEM
-      mbar_wait(a2ready, (uint32_t)(u & 1));
-      if (tap == 0) mbar_wait(&accempty[ab], (((uint32_t)tcount >> 1) & 1) ^ 1);
+    int ntiles = 0;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      const BlkMeta m = p.gx.meta[blk];
+      if (blk * kBlkRows < m.hi) ++ntiles;
+    }
+    const int nsteps = ntiles * 3;   // (tile, tap) steps of this CTA
+    int it = 0;
+    auto gemm1 = [&](int n) {  // U[n & 1] = gv W2 for step n: two 32-channel operand slots from the split warps
+      const uint32_t tacc = tmem_base + kU + (n & 1) * 64;
+      for (int kc = 0; kc < 2; ++kc, ++it) {
+        const int ta = it & 1;
+        mbar_wait(&a1ready[ta], ((uint32_t)it >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_hi = tmem_base + kA1 + ta * 64, a_lo = a_hi + 32;
+          const uint32_t b_hi = wt_addr + kc * 2 * TP_KB, b_lo = b_hi + TP_KB;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint64_t dbh = umma_desc_sw128(b_hi + k * 32), dbl = umma_desc_sw128(b_lo + k * 32);
+            umma_tf32_ts(tacc, a_lo + k * 8, dbh, idesc, (kc | k) != 0);
+            umma_tf32_ts(tacc, a_hi + k * 8, dbl, idesc, 1u);
+            umma_tf32_ts(tacc, a_hi + k * 8, dbh, idesc, 1u);
+          }
+          umma_commit(&a1empty[ta]);
+          if (kc == 1) umma_commit(&ufull[n & 1]);
+        }
+        __syncwarp();
+      }
+    };
+    auto gemm2 = [&](int n, int tap, int tile) {  // ACC[tile & 1] (+)= gu_tap W1_tap^T, gu (hi in place of U, lo) from TMEM
+      const int ub = n & 1, ab = tile & 1;
+      mbar_wait(&a2ready[ub], ((uint32_t)n >> 1) & 1);
+      if (tap == 0) mbar_wait(&accempty[ab], (((uint32_t)tile >> 1) & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t tacc = tmem_base + kAcc + ab * 64;
+        const uint32_t a_hi = tmem_base + kU + ub * 64, a_lo = tmem_base + kA2lo + ub * 64;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t b_hi = wt_addr + (2 + tap * 2 + (k >> 2)) * 2 * TP_KB + (k & 3) * 32, b_lo = b_hi + TP_KB;
           const uint64_t dbh = umma_desc_sw128(b_hi), dbl = umma_desc_sw128(b_lo);
-          umma_tf32_ts(tacc, tmem_base + kA2lo + k * 8, dbh, idesc, (tap | k) != 0);
-          umma_tf32_ts(tacc, tmem_base + kA2hi + k * 8, dbl, idesc, 1u);
-          umma_tf32_ts(tacc, tmem_base + kA2hi + k * 8, dbh, idesc, 1u);
+          umma_tf32_ts(tacc, a_lo + k * 8, dbh, idesc, (tap | k) != 0);
+          umma_tf32_ts(tacc, a_hi + k * 8, dbl, idesc, 1u);
+          umma_tf32_ts(tacc, a_hi + k * 8, dbh, idesc, 1u);
         }
-        umma_commit(a2empty);
         if (tap == 2) umma_commit(&accfull[ab]);
       }
       __syncwarp();
     };
-    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-      const BlkMeta m = p.gx.meta[blk];
-      if (blk * kBlkRows >= m.hi) continue;
-      const int ab = tcount & 1;
-      for (int tap = 0; tap < 3; ++tap, ++uc) {
-        const int ub = uc & 1;
-        mbar_wait(&uempty[ub], (((uint32_t)uc >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t tacc = tmem_base + kU + ub * 64;
-        for (int kc = 0; kc < 2; ++kc, ++it) {
-          const int ta = it & 1;
-          mbar_wait(&a1ready[ta], ((uint32_t)it >> 1) & 1);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t a_hi = tmem_base + kA1 + ta * 64, a_lo = a_hi + 32;
-            const uint32_t b_hi = wt_addr + kc * 2 * TP_KB, b_lo = b_hi + TP_KB;
-#pragma unroll
-            for (int k = 0; k < TC_BK / 8; ++k) {
-              const uint64_t dbh = umma_desc_sw128(b_hi + k * 32), dbl = umma_desc_sw128(b_lo + k * 32);
-              umma_tf32_ts(tacc, a_lo + k * 8, dbh, idesc, (kc | k) != 0);
-              umma_tf32_ts(tacc, a_hi + k * 8, dbl, idesc, 1u);
-              umma_tf32_ts(tacc, a_hi + k * 8, dbh, idesc, 1u);
-            }
-            umma_commit(&a1empty[ta]);
-            if (kc == 1) umma_commit(&ufull[ub]);
-          }
-          __syncwarp();
-        }
-        if (tap > 0) gemm2(uc - 1, tap - 1, ab);
-      }
-      gemm2(uc - 1, 2, ab);
-      ++tcount;
+    if (nsteps > 0) gemm1(0);
+    for (int n = 0, tap = 0, tile = 0; n < nsteps; ++n) {
+      if (n + 1 < nsteps) gemm1(n + 1);
+      gemm2(n, tap, tile);
+      if (++tap == 3) { tap = 0; ++tile; }
     }
   } else if (warp < 6) {
     // ===================== gy -> gv (warps 2..5): one frame = one thread = one TMEM lane =====================
@@ -1485,26 +1487,22 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_con
           const uint2 w = __ldg(reinterpret_cast<const uint2*>(p.masks + (size_t)src * 4));
           pos0 = w.x; pos1 = w.y;
         }
+        // U[ub] complete; the tap GEMM that read this operand buffer two steps ago was issued before it: in-order pipe
         mbar_wait(&ufull[ub], ((uint32_t)uc >> 1) & 1);
-        mbar_wait(a2empty, ((uint32_t)uc & 1) ^ 1);   // the previous tap's GEMM has consumed the gu operand
         tc_fence_after();
 #pragma unroll 1
         for (int c0 = 0; c0 < 64; c0 += 32) {
           const uint32_t pos = c0 == 0 ? pos0 : pos1;
           float u[32], hi[32], lo[32];
           tmem_ld32(lane_base + kU + ub * 64 + c0, u);
-          if (c0 == 32) {
-            tc_fence_before();
-            mbar_arrive(&uempty[ub]);
-          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             u[j] = (pos >> j) & 1u ? u[j] : 0.f;
             hi[j] = __uint_as_float(__float_as_uint(u[j]) & 0xffffe000u);
             lo[j] = u[j] - hi[j];
           }
-          tmem_st32(lane_base + kA2hi + c0, hi);
-          tmem_st32(lane_base + kA2lo + c0, lo);
+          tmem_st32(lane_base + kU + ub * 64 + c0, hi);      // in place: U[ub] becomes the hi operand
+          tmem_st32(lane_base + kA2lo + ub * 64 + c0, lo);
           if (sh == 0 && p.gu.Y != nullptr) {   // the centre tap is gu of this tile: keep it for the weight gradients
             float4 none[8];
             epilogue_block32<false, false, false, false>(u, st, lane, row0 + q * 32, m.hi, c0, p.gu, 0u, none);
@@ -1512,7 +1510,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_con
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(a2ready);
+        mbar_arrive(&a2ready[ub]);
       }
     }
   } else {

@@ -254,6 +254,34 @@ __device__ __forceinline__ void epilogue_block32(const float (&v)[32], float4* s
   __syncwarp();
 }
 
+// The same block epilogue with the dropout decision taken from a keep word per row instead of the hash: `keepw` is the
+// word of the row this lane owns in the accumulator layout (bit j: column n_base + j is kept); after the transpose a lane
+// writes rows i * 4 + lane / 8, so it fetches their words with a shuffle.  y = R + keep * scale * (acc + bias).
+__device__ __forceinline__ void epilogue_block32_keepbits(const float (&v)[32], float4* st, int lane, int row_base,
+                                                          int row_hi, int n_base, const GemmTcDev& p, uint32_t keepw,
+                                                          float scale, const float4 (&rr)[8]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    st[lane * 8 + (c ^ (lane & 7))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+  __syncwarp();
+  const int c = lane & 7, n = n_base + c * 4;
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3), row = row_base + r;
+    const uint32_t bits = __shfl_sync(0xffffffffu, keepw, r) >> (c * 4);
+    const float4 a = st[r * 8 + (c ^ (r & 7))];
+    float4 o;
+    o.x = (bits & 1u) ? (a.x + b.x) * scale : 0.f;
+    o.y = (bits & 2u) ? (a.y + b.y) * scale : 0.f;
+    o.z = (bits & 4u) ? (a.z + b.z) * scale : 0.f;
+    o.w = (bits & 8u) ? (a.w + b.w) * scale : 0.f;
+    o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w;
+    if (row < row_hi) *reinterpret_cast<float4*>(p.Y + (size_t)row * p.ldy + n) = o;
+  }
+  __syncwarp();
+}
+
 // Same 32 x 32 block epilogue with the feature set read from `p` at run time (bias / ReLU / ReLU-mask / dropout /
 // residual), plus the scalar path for ragged column counts.  Used by the persistent kernels, whose eight epilogue warps
 // each own one TMEM lane quadrant x 32 columns.
@@ -1096,6 +1124,8 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     // ===================== operand split of x (warps 2..5): one frame = one thread = one TMEM lane ================
     const int r = (warp & 3) * 32 + lane;                      // frame inside the tile == TMEM lane
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t keep_seed = p.y.drop_seed ^ dseed;
+    uint32_t keepw0 = 0u, keepw1 = 0u;
     int it = 0;
     for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
       const BlkMeta m = p.y.meta[blk];
@@ -1120,13 +1150,36 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           hi[4 * c + 3] = __uint_as_float(__float_as_uint(x3) & 0xffffe000u); lo[4 * c + 3] = x3 - hi[4 * c + 3];
         }
         mbar_arrive(&empty_bar[s]);                            // the raw tile is in registers: TMA may refill the slot
+        if (p.masks != nullptr && j < 4) {
+          // dropout keep bits of this thread's frame (the v -> y warps are the busy ones; these warps wait for the tensor
+          // pipe anyway): 16 columns per operand slot, bit c of word c / 32 = column c kept.  v -> y reads the words back
+          // after GEMM 2 of this tile, the fused backward kernel reads them as its dropout mask.
+          uint32_t bits = 0xffffu;
+          if (p.y.drop_thresh != 0u) {
+            bits = 0u;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t h = drop_hash4(keep_seed, p.y.drop_stream, (uint32_t)(row0 + r), (uint32_t)(j * 4 + g));
+#pragma unroll
+              for (int e = 0; e < 4; ++e) bits |= (drop_rotl(h, e) >= p.y.drop_thresh ? 1u : 0u) << (g * 4 + e);
+            }
+          }
+          if (j == 0) keepw0 = bits;
+          else if (j == 1) keepw0 |= bits << 16;
+          else if (j == 2) keepw1 = bits;
+          else {
+            keepw1 |= bits << 16;
+            if (row0 + r < m.hi)
+              *reinterpret_cast<uint2*>(p.masks + (size_t)(row0 + r) * 4 + 2) = make_uint2(keepw0, keepw1);
+          }
+        }
         mbar_wait(&aempty[ta], (((uint32_t)it >> 1) & 1) ^ 1);
         tc_fence_after();
         tmem_st32(lane_base + kA + ta * 64, hi);
         tmem_st32(lane_base + kA + ta * 64 + 32, lo);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&aready[ta]);
+        mbar_arrive(&aready[ta]);                              // (release: also publishes the keep words)
       }
     }
   } else if (warp < 10) {
@@ -1201,6 +1254,11 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       const int a = tcount & 1;
       mbar_wait(&vfull[a], ((uint32_t)tcount >> 1) & 1);
       tc_fence_after();
+      uint2 kw = make_uint2(0u, 0u);   // keep words of this lane's frame, written by the split warps before GEMM 1
+      if (p.masks != nullptr) {
+        const int row = min(row0 + q * 32 + lane, m.hi - 1);
+        kw = __ldcg(reinterpret_cast<const uint2*>(p.masks + (size_t)row * 4 + 2));
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 32) {
         // (fetching the residual before the wait, as the persistent kernels do, measured slower here: the same rows
@@ -1216,27 +1274,7 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         if (p.masks == nullptr) {
           epilogue_block32<false, true, true>(v, st, lane, row0 + q * 32, m.hi, c0, p.y, out_seed, rr);
         } else {
-          // bias + dropout in the accumulator layout (one frame per thread), so that the keep-mask of the frame can be
-          // saved as a bit word for the fused backward kernel
-          const int row = row0 + q * 32 + lane;
-          uint32_t keep = 0xffffffffu;
-          if (p.y.drop_thresh != 0u) keep = 0u;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.y.bias + c0 + j));
-            float f[4] = {1.f, 1.f, 1.f, 1.f};
-            if (p.y.drop_thresh != 0u) {
-              drop_factor4(out_seed, p.y.drop_stream, p.y.drop_thresh, p.y.drop_scale, row, c0 + j, f);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) keep |= (f[e] != 0.f ? 1u : 0u) << (j + e);
-            }
-            v[j + 0] = (v[j + 0] + b.x) * f[0];
-            v[j + 1] = (v[j + 1] + b.y) * f[1];
-            v[j + 2] = (v[j + 2] + b.z) * f[2];
-            v[j + 3] = (v[j + 3] + b.w) * f[3];
-          }
-          if (row < m.hi) p.masks[(size_t)row * 4 + 2 + (c0 >> 5)] = keep;
-          epilogue_block32<false, true, false, false>(v, st, lane, row0 + q * 32, m.hi, c0, p.y, out_seed, rr);
+          epilogue_block32_keepbits(v, st, lane, row0 + q * 32, m.hi, c0, p.y, c0 == 0 ? kw.x : kw.y, p.y.drop_scale, rr);
         }
       }
       ++tcount;

@@ -975,13 +975,14 @@ static int wide_bn(const GemmTcDev& p, int nb) {
 // W1 / W2 (hi and lo) stay resident in shared memory; the MMA warp issues GEMM 1 of tile i + 1 before GEMM 2 of tile i.
 //   TMEM (512 columns): u[2] @ 0 / 64, v[2] @ 128 / 192, h_hi @ 256, h_lo @ 320, x operand slots @ 384 / 448 (hi | lo)
 //   warp 0: TMA | warp 1: MMA + TMEM owner | warps 2-5: operand split of x | warps 6-9: u -> h (TMEM + HBM) |
-//   warps 10-13: v -> y.  The two epilogue groups work on different tiles at the same time.
+//   warps 10-13: v -> y | warps 14-15: dropout keep words.  The two epilogue groups work on different tiles at the same time.
 constexpr int LFT_STAGES = 4;
 constexpr int LFT_THREADS = 448;
+constexpr int LFT_FWD_THREADS = 512;   // forward kernel: + two warps that precompute the dropout keep words
 constexpr int LFT_EPI = 8 * 4096;   // eight epilogue warps x (32 x 32 fp32) staging
 static inline int lft_smem_bytes() { return 8 * 2 * TP_KB + LFT_STAGES * TP_KA + LFT_EPI + 1024 + 256; }
 
-__global__ void __launch_bounds__(LFT_THREADS, 1)
+__global__ void __launch_bounds__(LFT_FWD_THREADS, 1)
 layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1hi,
                     const __grid_constant__ CUtensorMap map_w1lo, const __grid_constant__ CUtensorMap map_w2hi,
                     const __grid_constant__ CUtensorMap map_w2lo, const LayerTcDev p) {
@@ -1006,6 +1007,7 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   uint64_t* vempty = vfull + 2;                   // [2]
   uint64_t* hready = vempty + 2;                  // h_hi / h_lo written to TMEM (128 epilogue threads)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hready + 1);
+  uint32_t* kcount = tmem_slot + 1;               // keep-word threads done, 64 per tile (warps 14-15 -> v -> y warps)
 
   if (threadIdx.x == 0) {
     mbar_init(wfull, 1);
@@ -1022,6 +1024,7 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       mbar_init(&vempty[s], 128);
     }
     mbar_init(hready, 128);
+    *kcount = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
@@ -1124,8 +1127,6 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     // ===================== operand split of x (warps 2..5): one frame = one thread = one TMEM lane ================
     const int r = (warp & 3) * 32 + lane;                      // frame inside the tile == TMEM lane
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t keep_seed = p.y.drop_seed ^ dseed;
-    uint32_t keepw0 = 0u, keepw1 = 0u;
     int it = 0;
     for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
       const BlkMeta m = p.y.meta[blk];
@@ -1150,36 +1151,13 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           hi[4 * c + 3] = __uint_as_float(__float_as_uint(x3) & 0xffffe000u); lo[4 * c + 3] = x3 - hi[4 * c + 3];
         }
         mbar_arrive(&empty_bar[s]);                            // the raw tile is in registers: TMA may refill the slot
-        if (p.masks != nullptr && j < 4) {
-          // dropout keep bits of this thread's frame (the v -> y warps are the busy ones; these warps wait for the tensor
-          // pipe anyway): 16 columns per operand slot, bit c of word c / 32 = column c kept.  v -> y reads the words back
-          // after GEMM 2 of this tile, the fused backward kernel reads them as its dropout mask.
-          uint32_t bits = 0xffffu;
-          if (p.y.drop_thresh != 0u) {
-            bits = 0u;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t h = drop_hash4(keep_seed, p.y.drop_stream, (uint32_t)(row0 + r), (uint32_t)(j * 4 + g));
-#pragma unroll
-              for (int e = 0; e < 4; ++e) bits |= (drop_rotl(h, e) >= p.y.drop_thresh ? 1u : 0u) << (g * 4 + e);
-            }
-          }
-          if (j == 0) keepw0 = bits;
-          else if (j == 1) keepw0 |= bits << 16;
-          else if (j == 2) keepw1 = bits;
-          else {
-            keepw1 |= bits << 16;
-            if (row0 + r < m.hi)
-              *reinterpret_cast<uint2*>(p.masks + (size_t)(row0 + r) * 4 + 2) = make_uint2(keepw0, keepw1);
-          }
-        }
         mbar_wait(&aempty[ta], (((uint32_t)it >> 1) & 1) ^ 1);
         tc_fence_after();
         tmem_st32(lane_base + kA + ta * 64, hi);
         tmem_st32(lane_base + kA + ta * 64 + 32, lo);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&aready[ta]);                              // (release: also publishes the keep words)
+        mbar_arrive(&aready[ta]);
       }
     }
   } else if (warp < 10) {
@@ -1240,6 +1218,42 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       }
       ++tcount;
     }
+  } else if (warp >= 14) {
+    // ===================== dropout keep words (warps 14..15) =====================
+    // bit c of word c / 32 of a frame = column c is kept.  Two frames per thread and tile; the words go to the mask array
+    // (the fused backward kernel reads them as its dropout mask) and v -> y reads them back instead of hashing: the hash
+    // costs ~25 instructions per four columns, which made the v -> y warps (later the split warps) the bottleneck.
+    // Nothing here depends on the pipeline, so these warps run ahead of it.
+    if (p.masks != nullptr) {
+      const uint32_t keep_seed = p.y.drop_seed ^ dseed;
+      const int hrow = threadIdx.x - 14 * 32;   // 0..63
+      for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const BlkMeta m = p.y.meta[blk];
+        const int row0 = blk * kBlkRows;
+        if (row0 >= m.hi) continue;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const int row = row0 + hrow + half * 64;
+          uint32_t w[2] = {0xffffffffu, 0xffffffffu};
+          if (p.y.drop_thresh != 0u) {
+#pragma unroll
+            for (int wi = 0; wi < 2; ++wi) {
+              uint32_t bits = 0u;
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const uint32_t h = drop_hash4(keep_seed, p.y.drop_stream, (uint32_t)row, (uint32_t)(wi * 8 + g));
+#pragma unroll
+                for (int e = 0; e < 4; ++e) bits |= (drop_rotl(h, e) >= p.y.drop_thresh ? 1u : 0u) << (g * 4 + e);
+              }
+              w[wi] = bits;
+            }
+          }
+          if (row < m.hi) *reinterpret_cast<uint2*>(p.masks + (size_t)row * 4 + 2) = make_uint2(w[0], w[1]);
+        }
+        __threadfence_block();
+        atomicAdd(kcount, 1u);
+      }
+    }
   } else {
     // ===================== v -> y: bias, dropout, + x (warps 10..13) =====================
     const int q = warp & 3;
@@ -1254,8 +1268,10 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       const int a = tcount & 1;
       mbar_wait(&vfull[a], ((uint32_t)tcount >> 1) & 1);
       tc_fence_after();
-      uint2 kw = make_uint2(0u, 0u);   // keep words of this lane's frame, written by the split warps before GEMM 1
+      uint2 kw = make_uint2(0u, 0u);   // keep words of this lane's frame, written by warps 14-15 (normally long ago)
       if (p.masks != nullptr) {
+        while (*reinterpret_cast<volatile uint32_t*>(kcount) < 64u * (uint32_t)(tcount + 1)) {}
+        __threadfence_block();
         const int row = min(row0 + q * 32 + lane, m.hi - 1);
         kw = __ldcg(reinterpret_cast<const uint2*>(p.masks + (size_t)row * 4 + 2));
       }
@@ -1301,7 +1317,7 @@ int launch_layer_fwd_tc(const CUtensorMap& mx, const CUtensorMap& w1hi, const CU
   const int nb = cap_nblk > 0 ? cap_nblk : p.y.nblk;
   int gx = num_sms();
   if (gx > nb) gx = nb;
-  launch_kernel(layer_fwd_tc_kernel, dim3(gx), dim3(LFT_THREADS), lft_smem_bytes(), stream, true, mx, w1hi, w1lo, w2hi, w2lo,
+  launch_kernel(layer_fwd_tc_kernel, dim3(gx), dim3(LFT_FWD_THREADS), lft_smem_bytes(), stream, true, mx, w1hi, w1lo, w2hi, w2lo,
                 p);
   return check_launch("layer_fwd_tc_kernel");
 }

@@ -19,6 +19,7 @@ constexpr int kMaxHeads = 8;
 // loss[h] accumulates  sum_{r, c in head h} row_scale(r) * col_unit(c) * bce(r, c),  col_unit = 1 / K_head
 // (so that loss[h] is the reference's mean-BCE of head h, averaged over the sequences of the batch);
 // dL carries the full chain factor col_scale(c) (= head_weight / K_head) * row_scale(r) * grad_scale.
+constexpr int kBceMaxIt = 8;   // column c = lane + 32 k, k < kBceMaxIt: up to 256 logits per row on the fast path
 __global__ void __launch_bounds__(256) bce_rows_kernel(const BceDev p) {
   __shared__ float red[8][kMaxHeads];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -30,6 +31,17 @@ __global__ void __launch_bounds__(256) bce_rows_kernel(const BceDev p) {
   const float rsc = p.dyn ? 1.f / (float)p.dyn->num_seqs : p.row_scale_const;
   const float* logits = p.nlev > 0 ? p.logits_lv[blockIdx.y] : p.logits;
   float* dL = p.nlev > 0 ? p.dL_lv[blockIdx.y] : p.dL;
+  const bool fast = p.zero_cols <= 32 * kBceMaxIt;
+  // fast path: a lane owns the same columns in every row, so the per-column constants live in registers and the loss is
+  // summed per column; the head of each column is looked at once, after the row loop
+  float acc[kBceMaxIt], cpw[kBceMaxIt], cscale[kBceMaxIt];
+#pragma unroll
+  for (int k = 0; k < kBceMaxIt; ++k) {
+    const int c = lane + 32 * k;
+    acc[k] = 0.f;
+    cpw[k] = (fast && c < p.ncols && p.pos_w) ? __ldg(p.pos_w + c) : 1.f;
+    cscale[k] = (fast && c < p.ncols) ? __ldg(p.col_scale + c) * p.grad_scale : 0.f;
+  }
   for (int row = blockIdx.x * 8 + warp; row < nrows; row += gridDim.x * 8) {
     float rs = rsc;
     int lrow = row;
@@ -41,12 +53,38 @@ __global__ void __launch_bounds__(256) bce_rows_kernel(const BceDev p) {
     }
     const float* x = logits + (size_t)row * p.ldl;
     const uint8_t* y = p.labels + (size_t)lrow * p.ldlab;
+    if (fast) {
+#pragma unroll
+      for (int k = 0; k < kBceMaxIt; ++k) {
+        const int c = lane + 32 * k;
+        if (c < p.ncols) {
+          const float xv = x[c];
+          const float yv = y[c] ? 1.f : 0.f;
+          const float pw = cpw[k];
+          // (1 - y) x + (1 + (pw - 1) y) (log1p(exp(-|x|)) + max(-x, 0))      [torch's stable form]
+          // exp / log / divide on the SFU fast paths (ex2.approx, lg2.approx, rcp.approx: <= 2 ulp each); log(1 + e)
+          // instead of log1p(e) costs <= 6e-8 absolute per term.  The libm versions made this kernel issue-bound (71 us).
+          const float e = __expf(-fabsf(xv));
+          const float lw = 1.f + (pw - 1.f) * yv;
+          const float sp = __logf(1.f + e) + fmaxf(-xv, 0.f);
+          acc[k] += rs * ((1.f - yv) * xv + lw * sp);
+          if (dL != nullptr) {
+            const float inv = __fdividef(1.f, 1.f + e);           // sigmoid(x) from the same exp(-|x|)
+            const float sg = xv >= 0.f ? inv : e * inv;
+            const float gr = sg * (pw * yv + 1.f - yv) - pw * yv;
+            dL[(size_t)row * p.lddl + c] = gr * rs * cscale[k];
+          }
+        } else if (c < p.zero_cols && dL != nullptr) {
+          dL[(size_t)row * p.lddl + c] = 0.f;
+        }
+      }
+      continue;
+    }
     for (int c = lane; c < p.zero_cols; c += 32) {
       if (c < p.ncols) {
         const float xv = x[c];
         const float yv = y[c] ? 1.f : 0.f;
         const float pw = p.pos_w ? __ldg(p.pos_w + c) : 1.f;
-        // (1 - y) x + (1 + (pw - 1) y) (log1p(exp(-|x|)) + max(-x, 0))      [torch's stable form]
         const float lw = 1.f + (pw - 1.f) * yv;
         const float sp = log1pf(expf(-fabsf(xv))) + fmaxf(-xv, 0.f);
         const float l = (1.f - yv) * xv + lw * sp;
@@ -61,6 +99,18 @@ __global__ void __launch_bounds__(256) bce_rows_kernel(const BceDev p) {
         }
       } else if (dL != nullptr) {
         dL[(size_t)row * p.lddl + c] = 0.f;
+      }
+    }
+  }
+  if (fast) {
+#pragma unroll
+    for (int k = 0; k < kBceMaxIt; ++k) {
+      const int c = lane + 32 * k;
+      if (c < p.ncols) {
+        const int h = __ldg(p.col_head + c);
+        const float lu = acc[k] * __ldg(p.col_unit + c);
+#pragma unroll
+        for (int j = 0; j < kMaxHeads; ++j) part[j] += (j == h) ? lu : 0.f;
       }
     }
   }

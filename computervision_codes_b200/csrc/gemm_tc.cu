@@ -2033,6 +2033,7 @@ extern "C" int tcn_gemm_tc(const tcn_gemm_tc_args* a, tcn_stream_t stream) {
   TCN_CHECK(make_tensor_map_2d(&mh, a->w_hi, wrows, wcols, wcols, 64));
   TCN_CHECK(make_tensor_map_2d(&ml, a->w_lo, wrows, wcols, wcols, 64));
   GemmTcDev p;
+  memset(&p, 0, sizeof(p));
   p.Y = a->y; p.ldy = a->ldy; p.N = a->n_out; p.bias = a->bias;
   p.R = a->residual; p.ldr = a->ldr; p.M = a->relu_mask; p.ldm = a->ldm; p.relu = a->relu;
   p.meta = reinterpret_cast<const BlkMeta*>(a->meta); p.nblk = a->nblk; p.dyn = nullptr;

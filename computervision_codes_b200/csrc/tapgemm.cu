@@ -15,6 +15,7 @@
 // prep_weight_kernel: for k-step ks (8 K-values) and n8-tile nt, lane l holds the float4
 //   { B[ks*8 + (l&3)][nt*8 + (l>>2)], B[ks*8 + (l&3) + 4][...] } as (hi.x, hi.y, lo.x, lo.y),
 // so a warp fetches its B fragments for one MMA with a single coalesced 512-byte read-only load.
+#include <cstring>
 #include "common.cuh"
 
 namespace tcn {
@@ -481,6 +482,7 @@ extern "C" int tcn_wgrad(const tcn_wgrad_args* a, tcn_stream_t stream) {
               "tcn_wgrad: g_cols must be a multiple of 4 in [n_out, ldg]");
   TCN_REQUIRE(a->g_drop_p >= 0.f && a->g_drop_p < 1.f, "tcn_wgrad: g_drop_p must be in [0, 1)");
   WgradDev p;
+  memset(&p, 0, sizeof(p));
   p.G = a->g; p.ldg = a->ldg; p.g_cols = a->g_cols;
   p.X = a->x; p.ldx = a->ldx; p.x_unpadded = a->x_unpadded;
   p.colscale = a->colscale; p.colscale_ld = a->colscale_ld;

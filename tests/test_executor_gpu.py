@@ -84,16 +84,18 @@ def test_executor_eval_matches_oracle_and_eager(C, causal):
                 assert _maxabs(feats[lv][r0:r0 + T].cpu(), outs[4][lv][0].t()) <= 1e-4
 
 
-def test_executor_train_mode_with_the_kernels_own_masks():
+@pytest.mark.parametrize("D", [40, 96])
+def test_executor_train_mode_with_the_kernels_own_masks(D):
     """Train mode: input mask (p=0.25, no rescale), Dropout2d over input channels, nn.Dropout in every layer.
-    The oracle is run with the very keep-masks the kernels derive from (seed, stream id)."""
+    The oracle is run with the very keep-masks the kernels derive from (seed, stream id).  D = 96: the projection and its
+    weight gradient run on the tcgen05 kernels (TMA needs a 16-byte row pitch); D = 40: mma.sync kernels."""
     from computervision_codes_b200 import ops
     from computervision_codes_b200.executor import ModelExecutor
     from computervision_codes_b200.layout import SeqLayout
     from computervision_codes_b200.tcn import VideoNas
 
     torch.manual_seed(4)
-    C, D, heads = 64, 40, (100, 6, 10, 15)
+    C, heads = 64, (100, 6, 10, 15)
     m = VideoNas(ARGS, 3, 2, 3, C, D, 100).to(DEV)
     sd64 = {k: v.detach().double().cpu() for k, v in m.state_dict().items()}
     lengths = [150, 200]

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""The two fused residual-layer kernels (tcn_layer_fwd_tc, tcn_layer_bwd_tc) alone at the TERL stress shape
-(64 x 8000 frames), alternating, for an `ncu --set full --import-source on` capture of one launch of each:
-  ncu --set full --import-source on --clock-control none -k regex:layer_(fwd|bwd)_tc_kernel --launch-skip 4 \
-      --launch-count 2 -o gpurun_out/fused_stress python tools/exp/fused_stress.py"""
+"""The three per-layer kernels (tcn_layer_fwd_tc, tcn_layer_bwd_tc, tcn_wgrad_tc_pair) alone at the TERL stress shape
+(64 x 8000 frames), in turn, for an `ncu --set full --import-source on` capture of one launch of each:
+  ncu --set full --import-source on --clock-control none -k "regex:layer_(fwd|bwd)_tc_kernel|wgrad_tc_pair" \\
+      --launch-skip 6 --launch-count 3 -o gpurun_out/fused_stress python tools/exp/fused_stress.py"""
 import os
 import sys
 
@@ -24,9 +24,12 @@ w2 = torch.randn(C, C, 1, device=DEV) / C ** 0.5
 b = torch.zeros(C, device=DEV)
 xs = [torch.randn(lay.rows, C, device=DEV) for _ in range(3)]
 gys = [torch.randn(lay.rows, C, device=DEV) for _ in range(3)]
+gw1, gb1 = torch.zeros(C, C, 3, device=DEV), torch.zeros(C, device=DEV)
+gw2, gb2 = torch.zeros(C, C, 1, device=DEV), torch.zeros(C, device=DEV)
 for i in range(4):
     y, h, masks = ops.layer_fwd_tc(xs[i % 3], w1, w2, b, b, lay, shifts, True, 0.5, 1, 2, save_masks=True)
     gu, gx = ops.layer_bwd_tc(gys[i % 3], masks, w1, w2, lay, shifts, 0.5)
+    ops.wgrad_tc_layer_pair(gu, xs[i % 3], gys[i % 3], h, lay, shifts, gw1, gb1, gw2, gb2, drop_p=0.5, seed=1, stream_id=2)
     del y, h, gu, gx
 torch.cuda.synchronize()
 print("ok")

@@ -61,6 +61,9 @@ class FeatureCache:
         self.feats: Dict[str, torch.Tensor] = {}
         self.labels: Dict[str, torch.Tensor] = {}
         self.kept: Dict[str, torch.Tensor] = {}
+        self.arena_x = None        # pack(): every video in one (frames, D) tensor / one (frames, 132) label tensor
+        self.arena_lab = None
+        self.offset: Dict[str, int] = {}
 
     def add_video(self, vid: str, feats, y_i, y_v, y_t, y_ivt, drop_id_column: bool = False):
         """feats (T, D) float; y_* (T, K) integer matrices (with the leading frame-id column of the reference's
@@ -76,6 +79,35 @@ class FeatureCache:
             self.kept[vid] = keep
             f, lab = f[keep].contiguous(), lab[keep].contiguous()
         self.feats[vid], self.labels[vid] = f.contiguous(), lab
+        self.arena_x = self.arena_lab = None   # a new video invalidates the arena: pack() again
+
+    def pack(self):
+        """Move every video into ONE arena.  A step on cached clips (``TemporalTrainer.step_cached``) then reads features
+        and labels in place -- the block table carries each clip's position inside the arena -- instead of copying them
+        device-to-device into the trainer's input slot.  ``feats[vid]`` / ``labels[vid]`` become views of the arena."""
+        vids = list(self.feats)
+        assert vids, "pack(): the cache is empty"
+        D, L = self.feats[vids[0]].shape[1], self.labels[vids[0]].shape[1]
+        total = sum(self.feats[v].shape[0] for v in vids)
+        ax = torch.empty(total, D, device=self.device, dtype=torch.float32)
+        al = torch.empty(total, L, device=self.device, dtype=torch.uint8)
+        off = 0
+        for v in vids:
+            n = self.feats[v].shape[0]
+            ax[off:off + n].copy_(self.feats[v])
+            al[off:off + n].copy_(self.labels[v])
+            self.offset[v] = off
+            self.feats[v], self.labels[v] = ax[off:off + n], al[off:off + n]
+            off += n
+        self.arena_x, self.arena_lab = ax, al
+        return self
+
+    def add_packed(self, vid: str, feats: torch.Tensor, labels_u8: torch.Tensor):
+        """A video whose features (T, D) fp32 and packed uint8 labels (T, 132; ``losses.pack_labels``) already exist."""
+        assert feats.shape[0] == labels_u8.shape[0] and labels_u8.dtype == torch.uint8
+        self.feats[vid] = feats.to(self.device, torch.float32).contiguous()
+        self.labels[vid] = labels_u8.to(self.device).contiguous()
+        self.arena_x = self.arena_lab = None
 
     def add_pickle(self, path: str, labels: Dict[str, Sequence], drop_id_column: bool = True):
         """``k{fold}_feats.pkl`` of the reference (dict: video id -> (T, D) ndarray, dataloader.py:212-214);

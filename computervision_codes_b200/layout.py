@@ -18,16 +18,22 @@ def round_up(a: int, b: int) -> int:
 
 
 class SeqLayout:
-    def __init__(self, lengths, device):
+    def __init__(self, lengths, device, in_starts=None):
+        """in_starts: first row of each sequence in the caller's unpadded arrays (features, labels).  Default: the
+        sequences are concatenated (0, T0, T0 + T1, ...); a feature arena passes the clips' positions inside it."""
         self.lengths = [int(t) for t in lengths]
         assert len(self.lengths) > 0 and all(t > 0 for t in self.lengths)
+        assert in_starts is None or len(in_starts) == len(self.lengths)
         self.device = torch.device(device)
         self.num_seqs = len(self.lengths)
+        in_starts_arg = in_starts
         starts, in_starts, meta = [], [], []
         row = 0
         src = 0
         for s, T in enumerate(self.lengths):
             starts.append(row)
+            if in_starts_arg is not None:
+                src = int(in_starts_arg[s])
             in_starts.append(src)
             nb = round_up(T, BLK) // BLK
             for _ in range(nb):
@@ -37,23 +43,43 @@ class SeqLayout:
         self.starts = starts
         self.in_starts = in_starts
         self.rows = row            # padded rows
-        self.frames = src          # valid frames
+        self.frames = sum(self.lengths)   # valid frames
         self.nblk = row // BLK
         self.meta_np = np.asarray(meta, dtype=np.int32).reshape(-1, 4)
-        self.meta = torch.from_numpy(self.meta_np).to(self.device)
         self.uniform_T = self.lengths[0] if len(set(self.lengths)) == 1 else None
-        self.seq_lo = torch.tensor(self.starts, dtype=torch.int32, device=self.device)
-        self.seq_len = torch.tensor(self.lengths, dtype=torch.int32, device=self.device)
         self.max_len = max(self.lengths)
+        self._meta = self._seq_lo = self._seq_len = None
+
+    # Device copies of the tables are made on first use: a pageable host-to-device copy blocks the host behind everything
+    # queued on the stream, and the executor path (tcn_model_set_batch uploads meta_np itself) never needs them -- a
+    # trainer that builds a new layout per step would otherwise serialise its input prefetch behind the previous step.
+    @property
+    def meta(self):
+        if self._meta is None:
+            self._meta = torch.from_numpy(self.meta_np).to(self.device)
+        return self._meta
+
+    @property
+    def seq_lo(self):
+        if self._seq_lo is None:
+            self._seq_lo = torch.tensor(self.starts, dtype=torch.int32, device=self.device)
+        return self._seq_lo
+
+    @property
+    def seq_len(self):
+        if self._seq_len is None:
+            self._seq_len = torch.tensor(self.lengths, dtype=torch.int32, device=self.device)
+        return self._seq_len
 
     @staticmethod
-    def get(lengths, device) -> "SeqLayout":
-        key = (tuple(int(t) for t in lengths), str(torch.device(device)))
+    def get(lengths, device, in_starts=None) -> "SeqLayout":
+        key = (tuple(int(t) for t in lengths), str(torch.device(device)),
+               None if in_starts is None else tuple(int(t) for t in in_starts))
         lay = _cache.get(key)
         if lay is None:
-            if len(_cache) > 256:
+            if len(_cache) > 4096:
                 _cache.clear()
-            lay = _cache[key] = SeqLayout(lengths, device)
+            lay = _cache[key] = SeqLayout(lengths, device, in_starts)
         return lay
 
     @staticmethod

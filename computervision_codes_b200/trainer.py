@@ -128,6 +128,7 @@ class TemporalTrainer:
         self.rng = torch.Generator().manual_seed(seed)
         self.training = True
         self._launches_per_step = None
+        self._arena_graphs = {}
         # {lr, weight_decay, grad_scale} live on the device: the captured graph follows set_lr() / an LR schedule
         self._hyper_host = torch.tensor([lr, weight_decay, 1.0 / max(1, world_size)], dtype=torch.float32).pin_memory()
         self.hyper = self._hyper_host.to(dev)
@@ -139,12 +140,42 @@ class TemporalTrainer:
         self.hyper.copy_(self._hyper_host, non_blocking=True)
 
     def step_cached(self, cache, items):
-        """One step on clips / videos of a ``data.FeatureCache``: items = [(video, start, length), ...]."""
-        xs, ls, lens = cache.batch(items)
-        return self.step(xs, ls, lens)
+        """One step on clips / videos of a ``data.FeatureCache``: items = [(video, start, length), ...].
+        A packed cache (``cache.pack()``) is read in place: no copy, the block table addresses the arena."""
+        items = list(items)
+        if getattr(cache, "arena_x", None) is None:
+            xs, ls, lens = cache.batch(items)
+            return self.step(xs, ls, lens)
+        lens, starts = [], []
+        for vid, start, n in items:
+            assert 0 <= start and n > 0 and start + n <= cache.frames(vid), (vid, start, n)
+            lens.append(int(n))
+            starts.append(cache.offset[vid] + int(start))
+        lay = SeqLayout.get(lens, self.ex.device, in_starts=starts)
+        seed = int(torch.randint(0, 2 ** 31 - 1, (1,), generator=self.rng).item())
+        self.ex.set_batch(lay, seed)
+        x, lab = cache.arena_x, cache.arena_lab
+        if not self.use_graph:
+            return self._counted_body(None, x, lab)
+        key = (x.data_ptr(), lab.data_ptr())
+        if key not in self._arena_graphs:
+            snap_p = self.flat_p.clone()
+            self._body(None, x, lab)
+            self.flat_p.copy_(snap_p)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._counted_body(None, x, lab)
+            self.flat_p.copy_(snap_p)
+            self._arena_graphs[key] = (g, out, x, lab)
+        g, out = self._arena_graphs[key][:2]
+        g.replay()
+        return out
 
-    def _body(self, slot):
-        out = self.ex.train_step(self.x_slots[slot], self.lab_slots[slot], training=self.training)
+    def _body(self, slot, x=None, lab=None):
+        if x is None:
+            x, lab = self.x_slots[slot], self.lab_slots[slot]
+        out = self.ex.train_step(x, lab, training=self.training)
         if self.world > 1:
             torch.distributed.all_reduce(self.flat_g, group=self.pg)
         ops.sgd_step_dev(self.flat_p, self.flat_g, self.hyper)
@@ -156,12 +187,12 @@ class TemporalTrainer:
         assert self._launches_per_step is not None, "launches_per_step(): run a step first"
         return self._launches_per_step
 
-    def _counted_body(self, slot):
+    def _counted_body(self, slot, x=None, lab=None):
         from . import _lib
 
         lib = _lib.load()
         n0 = lib.tcn_launch_count()
-        out = self._body(slot)
+        out = self._body(slot, x, lab)
         self._launches_per_step = int(lib.tcn_launch_count() - n0)
         return out
 
@@ -252,3 +283,4 @@ class TemporalTrainer:
         """Drop the captured graphs (do this before destroying a process group they reference)."""
         self.graphs = [None, None]
         self._outs = [None, None]
+        self._arena_graphs = {}

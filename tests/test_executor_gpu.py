@@ -212,10 +212,16 @@ def test_step_cached_reads_clips_from_the_gpu_resident_feature_cache():
     while len({n == cache.frames(v) for v, _, n in items}) < 2:   # make sure both a clip and a whole video occur
         items = [(v, *sampler.sample(cache.frames(v))) for v in ("03", "01", "02")]
     out = []
-    for cached in (True, False):
+    for cached in (True, False, "packed", "packed-eager"):
         torch.manual_seed(4)
         m = VideoNas(ARGS, 3, 2, 3, 64, D, 100).to(DEV).train()
-        tr = TemporalTrainer(m, lr=0.05, weight_decay=1e-5, max_frames=2048, max_seqs=4, seed=8)
+        tr = TemporalTrainer(m, lr=0.05, weight_decay=1e-5, max_frames=2048, max_seqs=4, seed=8,
+                             use_graph=cached != "packed-eager")
+        if cached == "packed":
+            # one arena for all videos: the step reads clips in place (no copy), the block table addresses the arena
+            cache.pack()
+            assert cache.arena_x.shape[0] == 400 + 260 + 1100 and cache.feats["02"].data_ptr() == \
+                cache.arena_x[400:].data_ptr()
         for _ in range(2):
             if cached:
                 loss = tr.step_cached(cache, items)
@@ -225,7 +231,8 @@ def test_step_cached_reads_clips_from_the_gpu_resident_feature_cache():
                 loss = tr.step(xs, ls, [n for _, _, n in items])
         out.append((loss.clone(), tr.flat_p.clone()))
     # same frames, same seeds; fp32 atomics in the weight-gradient kernels make runs differ in the last bits only
-    assert _maxabs(out[0][0], out[1][0]) <= 1e-5 and _maxabs(out[0][1], out[1][1]) <= 1e-5
+    for k in (1, 2, 3):
+        assert _maxabs(out[0][0], out[k][0]) <= 1e-5 and _maxabs(out[0][1], out[k][1]) <= 1e-5, k
 
 
 @pytest.mark.parametrize("causal", [False, True])

@@ -113,3 +113,43 @@ def test_artefact_pickles_round_trip(tmp_path):
     zeros = [np.zeros((7, k), dtype=np.int64) for k in (6, 10, 15, 100)]
     cache.add_pickle(str(path), {"01": zeros}, drop_id_column=False)
     assert len(cache) == 1 and cache.frames("01") == 7
+
+
+def test_packed_cache_is_one_arena_and_the_block_table_addresses_it():
+    """f1, zero-copy steps: ``FeatureCache.pack()`` moves every video into one arena (views stay valid) and a layout
+    built with ``in_starts`` points each 128-row block at its clip inside the arena: block b of sequence s covers padded
+    rows [lo, hi) and reads unpadded rows ``row + in_delta`` -- exactly the clip's frames."""
+    from computervision_codes_b200.layout import SeqLayout
+
+    rng = np.random.default_rng(3)
+    cache = FeatureCache("cpu")
+    ref = {}
+    for vid, T in (("a", 300), ("b", 129), ("c", 1000)):
+        f = rng.standard_normal((T, 8)).astype(np.float32)
+        ys = [(rng.random((T, k)) < 0.2).astype(np.int64) for k in (6, 10, 15, 100)]
+        cache.add_video(vid, f, *ys)
+        ref[vid] = (torch.from_numpy(f), cache.labels[vid].clone())
+    assert cache.arena_x is None
+    cache.pack()
+    assert cache.arena_x.shape == (1429, 8) and cache.arena_lab.shape == (1429, 132)
+    assert [cache.offset[v] for v in "abc"] == [0, 300, 429]
+    for vid in "abc":   # the per-video tensors are now views of the arena with the same contents
+        assert torch.equal(cache.feats[vid], ref[vid][0]) and torch.equal(cache.labels[vid], ref[vid][1])
+        assert cache.feats[vid].data_ptr() == cache.arena_x[cache.offset[vid]:].data_ptr()
+    items = [("c", 200, 500), ("a", 0, 300), ("b", 100, 29)]
+    lens = [n for _, _, n in items]
+    starts = [cache.offset[v] + s for v, s, _ in items]
+    lay = SeqLayout.get(lens, "cpu", in_starts=starts)
+    assert lay.frames == sum(lens) and lay.rows == 512 + 384 + 128 and lay.nblk == 8
+    for lo, hi, delta, s in lay.meta_np.tolist():
+        vid, start, n = items[s]
+        assert hi - lo == n and lo % 128 == 0
+        rows = torch.arange(lo, hi)
+        assert torch.equal(cache.arena_x[rows + delta], ref[vid][0][start:start + n])
+    # the default layout (concatenated inputs) is unchanged and cached under a different key
+    cat = SeqLayout.get(lens, "cpu")
+    assert cat.in_starts == [0, 500, 800] and cat is not lay and SeqLayout.get(lens, "cpu", in_starts=starts) is lay
+    # adding a video invalidates the arena
+    cache.add_video("d", rng.standard_normal((5, 8)).astype(np.float32),
+                    *[np.zeros((5, k), dtype=np.int64) for k in (6, 10, 15, 100)])
+    assert cache.arena_x is None

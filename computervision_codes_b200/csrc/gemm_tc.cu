@@ -43,8 +43,8 @@ __device__ __forceinline__ void split_tile(float4* __restrict__ xa, float4* __re
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int src = row0 + ((ct + i * NT) >> 3) + sh;
-    const float keep = (src >= m.lo && src < m.hi) ? 1.f : 0.f;
-    v[i].x *= keep; v[i].y *= keep; v[i].z *= keep; v[i].w *= keep;
+    // select, not multiply: a pad row may hold anything (0 * NaN would poison the accumulator)
+    if (!(src >= m.lo && src < m.hi)) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (p.colscale != nullptr || p.in_drop_thresh != 0u) {  // CTA-uniform, rare (projection in training)
 #pragma unroll
@@ -1139,12 +1139,12 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         mbar_wait(&full_bar[s], (it / LFT_STAGES) & 1);
         const float4* row = reinterpret_cast<const float4*>(at + s * TP_KA) + r * 8;
         const int src = row0 + r + sh;
-        const float keep = (src >= m.lo && src < m.hi) ? 1.f : 0.f;
+        const bool keep = src >= m.lo && src < m.hi;           // select, not multiply: pad rows may hold anything
         float hi[32], lo[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 v = row[c ^ (r & 7)];                   // undo the 128B swizzle: logical 16-byte chunk c
-          const float x0 = v.x * keep, x1 = v.y * keep, x2 = v.z * keep, x3 = v.w * keep;
+          const float x0 = keep ? v.x : 0.f, x1 = keep ? v.y : 0.f, x2 = keep ? v.z : 0.f, x3 = keep ? v.w : 0.f;
           hi[4 * c + 0] = __uint_as_float(__float_as_uint(x0) & 0xffffe000u); lo[4 * c + 0] = x0 - hi[4 * c + 0];
           hi[4 * c + 1] = __uint_as_float(__float_as_uint(x1) & 0xffffe000u); lo[4 * c + 1] = x1 - hi[4 * c + 1];
           hi[4 * c + 2] = __uint_as_float(__float_as_uint(x2) & 0xffffe000u); lo[4 * c + 2] = x2 - hi[4 * c + 2];
@@ -1771,9 +1771,9 @@ gemm_tc_slab_kernel(const __grid_constant__ CUtensorMap map_x32, const __grid_co
             const int c = c0 + i * 128;
             if (c < nchunks) {
               const int src = row0 + smin + (c >> 3);  // a slab row is valid iff its source frame is inside the sequence
-              const float keep = (src >= m.lo && src < m.hi) ? 1.f : 0.f;
+              const bool keep = src >= m.lo && src < m.hi;   // select, not multiply: pad rows may hold anything
               float4 h, l;
-              const float x0 = v[i].x * keep, x1 = v[i].y * keep, x2 = v[i].z * keep, x3 = v[i].w * keep;
+              const float x0 = keep ? v[i].x : 0.f, x1 = keep ? v[i].y : 0.f, x2 = keep ? v[i].z : 0.f, x3 = keep ? v[i].w : 0.f;
               h.x = __uint_as_float(__float_as_uint(x0) & 0xffffe000u); l.x = x0 - h.x;
               h.y = __uint_as_float(__float_as_uint(x1) & 0xffffe000u); l.y = x1 - h.y;
               h.z = __uint_as_float(__float_as_uint(x2) & 0xffffe000u); l.z = x2 - h.z;

@@ -201,8 +201,8 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
             const int r = ct >> 3;                      // ... at frame r of the chunk
             int src = r0 + r;
             if (atom < 4) src += a_tap[atom] == 0 ? p.shift[0] : (a_tap[atom] == 1 ? p.shift[1] : p.shift[2]);
-            const float keep = (src >= m.lo && src < m.hi) ? 1.f : 0.f;
-            v[i].x *= keep; v[i].y *= keep; v[i].z *= keep; v[i].w *= keep;
+            // select, not multiply: a pad row may hold anything (0 * NaN would poison the accumulator)
+            if (!(src >= m.lo && src < m.hi)) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (extras) {
               if (atom < 4) {
                 const int col = a_cb[atom] * 32 + lc * 4;

@@ -31,7 +31,16 @@ def canonical_param_names(layers_pg, layers_r, num_r):
 class ModelExecutor:
     def __init__(self, model, max_rows, max_seqs=64):
         lib = _lib.load()
-        assert model.use_fpn, "the executor implements the --fpn path (every reference script uses it)"
+        # the configurations csrc/model.cu implements; anything else would silently train a different network
+        if not model.use_fpn:
+            raise _lib.TcnError("ModelExecutor implements the --fpn path (every reference script uses it)")
+        if model.use_output:
+            raise _lib.TcnError("ModelExecutor: args.output=True (Rs.*.conv_1x1 on the stage input, network.py:150-151) "
+                                "is not on the executor path; use the module forward (forward_packed)")
+        if len(model.Rs) != 3:
+            raise _lib.TcnError("ModelExecutor: the FPN needs exactly 3 refinement stages (network.py:98-106)")
+        if any(getattr(R, "hier", False) for R in model.Rs):
+            raise _lib.TcnError("ModelExecutor: args.hier (AvgPool1d between stages) is not on the executor path")
         self.model = model
         dev = next(model.parameters()).device
         if dev.type != "cuda":

@@ -77,7 +77,7 @@ class _MultiHeadBceFn(torch.autograd.Function):
         dls = []
         for lg in logit_rows:
             lg = lg if lg.is_contiguous() else lg.contiguous()
-            dl = torch.empty_like(lg) if need_grad else None
+            dl = torch.zeros_like(lg) if need_grad else None   # the kernel skips pad rows: they must read as zero
             _bce_launch(lg, labels_u8, ncols, cols, 1.0 / lay.num_seqs, loss8, dl, meta=lay.meta, nrows=lay.rows,
                         lab_unpadded=lab_unpadded)
             dls.append(dl)

@@ -118,6 +118,16 @@ def wgrad_tc_layer_pair(gu, x, gy, h, lay: SeqLayout, shifts, gw1, gb1, gw2, gb2
     _lib.check(lib.tcn_wgrad_tc_pair(C.byref(a1), C.byref(a2), _lib.stream_ptr()), "tcn_wgrad_tc_pair")
 
 
+def layer_wgrad_kernel_name() -> str:
+    """Name of the kernel layer_wgrad() launches (for bench.py's roofline block)."""
+    return "wgrad_tc_pair_kernel"
+
+
+def layer_wgrad(gu, x, gy, h, lay: SeqLayout, shifts, gw1, gb1, gw2, gb2, drop_p=0.0, seed=0, stream_id=0, masks=None):
+    """All weight / bias gradients of one residual layer (accumulating into gw1 / gb1 / gw2 / gb2)."""
+    wgrad_tc_layer_pair(gu, x, gy, h, lay, shifts, gw1, gb1, gw2, gb2, drop_p=drop_p, seed=seed, stream_id=stream_id)
+
+
 def layer_fwd(x, w1f, w2f, b1, b2, lay: SeqLayout, shifts, save_h=True, drop_p=0.0, seed=0, stream_id=0):
     """Fused residual layer forward (64 channels): returns (y, h)."""
     lib = _lib.load()

@@ -208,6 +208,10 @@ class _VideoNasExecFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, x_rows, lay, training, need_grad, *params):
         ex = module._get_executor(lay)
+        # the executor keeps ONE set of saved activations: stamp this forward so that a backward that follows a later
+        # forward (two forwards before backward, a grad-enabled validation pass, a re-created executor) fails loudly
+        module._exec_gen += 1
+        ctx.exec_gen, ctx.ex = module._exec_gen, ex
         ex.set_batch(lay, ops.new_seed() if training else 0)
         feats, logits = ex.forward(x_rows, training=training, keep_activations=need_grad)
         outs = [t.clone() for t in logits] + [t.clone() for t in feats]  # executor memory is reused by the next call
@@ -220,6 +224,11 @@ class _VideoNasExecFn(torch.autograd.Function):
     def backward(ctx, *gouts):
         module = ctx.module
         ex = module._executor
+        if ex is not ctx.ex or module._exec_gen != ctx.exec_gen:
+            raise RuntimeError("VideoNas (native executor): backward() of a forward whose saved activations were "
+                               "overwritten by a later forward -- the executor supports one outstanding forward "
+                               "(INTEGRATION.md); call backward before the next forward, or run the later forward "
+                               "under torch.no_grad() on a second module")
         glogits = []
         for i in range(4):
             g = gouts[i]
@@ -285,6 +294,7 @@ class VideoNas(nn.Module):
 
     # ---- native executor path --------------------------------------------------------------------------
     _executor = None
+    _exec_gen = 0
 
     def _get_executor(self, lay):
         from ..executor import ModelExecutor, canonical_param_names

@@ -125,7 +125,13 @@ class TemporalTrainer:
         self.use_graph = use_graph
         self.graphs = [None, None]
         self._outs = [None, None]
-        self.rng = torch.Generator().manual_seed(seed)
+        # data parallel: every rank must start from rank 0's weights, and draws its own dropout / input-mask stream
+        rank = 0
+        if world_size > 1:
+            rank = torch.distributed.get_rank(process_group)
+            torch.distributed.broadcast(self.flat_p, src=torch.distributed.get_global_rank(process_group, 0)
+                                        if process_group is not None else 0, group=process_group)
+        self.rng = torch.Generator().manual_seed(int(seed) * 1000003 + rank)
         self.training = True
         self._launches_per_step = None
         self._arena_graphs = {}
@@ -134,10 +140,11 @@ class TemporalTrainer:
         self.hyper = self._hyper_host.to(dev)
 
     def set_lr(self, lr: float):
-        """New learning rate for the following steps (stream-ordered H2D of 4 bytes; no graph re-capture)."""
+        """New learning rate for the following steps (no graph re-capture).  The value travels as a kernel argument of
+        a stream-ordered fill, so steps already queued keep the rate they were enqueued with."""
         self.lr = float(lr)
         self._hyper_host[0] = self.lr
-        self.hyper.copy_(self._hyper_host, non_blocking=True)
+        self.hyper[0:1].fill_(self.lr)
 
     def step_cached(self, cache, items):
         """One step on clips / videos of a ``data.FeatureCache``: items = [(video, start, length), ...].

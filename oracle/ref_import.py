@@ -1,8 +1,10 @@
 """Import the reference's own modules from /root/reference.  TEST INFRASTRUCTURE ONLY.
 
-Works only in the build container (the GPU box has no /root/reference); used by
-``oracle/gen_golden.py`` to write ``tests/golden/*.npz`` and by the not-gpu tests that
-re-check the oracle against the live reference when it is present.
+In the build container the modules come from /root/reference; on the GPU box (which has no
+/root/reference) from ``baseline/_ref`` -- the same files, copied unmodified by
+``oracle/vendor_ref.py``.  Used by ``oracle/gen_golden*.py`` to write ``tests/golden/*.npz``, by the
+tests that re-check against the live reference when it is present, and by bench.py's reference /
+eager-GPU-baseline arms.
 """
 from __future__ import annotations
 
@@ -13,7 +15,20 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("CVC_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_VENDORED = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")   # written by oracle/vendor_ref.py (git-ignored)
+
+
+def _default_root() -> str:
+    env = os.environ.get("CVC_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/MT4MTLKD"):
+        return "/root/reference"
+    return _VENDORED   # the GPU box: the unmodified module files copied by the recipe
+
+
+REF_ROOT = _default_root()
 
 
 def available() -> bool:

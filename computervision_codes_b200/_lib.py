@@ -107,6 +107,18 @@ class WgradTcArgs(C.Structure):
     ]
 
 
+class WgradLayerArgs(C.Structure):
+    _fields_ = [
+        ("gu", C.c_void_p), ("x", C.c_void_p), ("gy", C.c_void_p), ("h", C.c_void_p), ("rows", C.c_longlong),
+        ("masks", C.c_void_p),
+        ("meta", C.c_void_p), ("nblk", C.c_int), ("channels", C.c_int),
+        ("shift", C.c_int * 3),
+        ("drop_p", C.c_float), ("drop_seed", C.c_uint), ("drop_stream", C.c_uint),
+        ("dw1", C.c_void_p), ("db1", C.c_void_p), ("dw2", C.c_void_p), ("db2", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong),
+    ]
+
+
 class AttnArgs(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("ldq", C.c_int), ("k", C.c_void_p), ("ldk", C.c_int), ("v", C.c_void_p), ("ldv", C.c_int),
@@ -164,6 +176,8 @@ SIGNATURES = {
     "tcn_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     "tcn_wgrad_tc": (C.c_int, [C.POINTER(WgradTcArgs), C.c_void_p]),
     "tcn_wgrad_tc_pair": (C.c_int, [C.POINTER(WgradTcArgs), C.POINTER(WgradTcArgs), C.c_void_p]),
+    "tcn_wgrad_layer_workspace_bytes": (C.c_longlong, [C.c_int]),
+    "tcn_wgrad_layer": (C.c_int, [C.POINTER(WgradLayerArgs), C.c_void_p]),
     "tcn_layer_fwd": (C.c_int, [C.POINTER(LayerFwdArgs), C.c_void_p]),
     "tcn_layer_fwd_tc": (C.c_int, [C.POINTER(LayerFwdTcArgs), C.c_void_p]),
     "tcn_layer_bwd_tc": (C.c_int, [C.POINTER(LayerBwdTcArgs), C.c_void_p]),

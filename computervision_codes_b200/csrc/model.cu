@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "gemm_tc.cuh"
+#include "wgrad_layer.cuh"
 
 namespace tcn {
 
@@ -69,6 +70,15 @@ struct tcn_model {
     int2* tiles = nullptr;
     std::vector<int> tile_first, tile_count, row_splits;   // per stage
   } wgm[2];
+  // per-layer weight gradients (wgrad_layer.cu): descriptor tables in backward order, built lazily per training flag
+  struct WlTable {
+    bool ready = false;
+    WgLayerDev* descs = nullptr;
+    WgLayerOut* outs = nullptr;
+  } wl[2];
+  float* wl_part = nullptr;   // [L][wl_splits][WL_PART_FLOATS] partial slabs
+  int wl_lg = 1, wl_splits = 1;
+  bool use_wl = true;         // TCN_WGRAD_PAIR=1: round 1's pair kernel (fp32 atomics) instead (A/B)
   bool wg_multi = false;  // TCN_WGRAD_MULTI=1: one launch per stage (measured slower than per-layer pair launches:
                           // 3.12 vs 3.09 ms / step -- the long per-CTA frame loops lose more than the launches save)
   bool overlap_wgrad = true;
@@ -323,6 +333,48 @@ int build_wg_multi(tcn_model* m, int training) {
   return TCN_OK;
 }
 
+// Descriptor tables of the per-layer weight-gradient kernel, in the order model_backward visits the layers.
+int build_wl_table(tcn_model* m, int training) {
+  tcn_model::WlTable& t = m->wl[training];
+  const float pl = training ? m->layer_drop_p : 0.f;
+  std::vector<WgLayerDev> descs;
+  std::vector<WgLayerOut> outs;
+  const float* g = m->Gp[3];
+  int gi = 0;
+  for (int s = 3; s >= 0; --s) {
+    for (int l = m->stage_first[s + 1] - 1; l >= m->stage_first[s]; --l) {
+      WgLayerDev d;
+      memset(&d, 0, sizeof(d));
+      TCN_CHECK(make_wgrad_layer_maps(&d, m->act[l], m->H[l], m->gus[l], g, m->cfg.max_rows));
+      d.masks = m->masks[l];
+      layer_shifts(m, l, d.shift);
+      d.use_drop = pl > 0.f ? 1 : 0;
+      d.drop_scale = pl > 0.f ? 1.f / (1.f - pl) : 1.f;
+      d.drop_thresh = pl > 0.f ? drop_thresh(pl) : 0u;
+      d.drop_seed = 0u; d.drop_stream = (uint32_t)l;
+      d.part = m->wl_part + (size_t)descs.size() * m->wl_splits * WL_PART_FLOATS;
+      WgLayerOut o;
+      o.part = d.part;
+      o.dw1 = m->g_(m->off_w1[l]); o.db1 = m->g_(m->off_b1[l]);
+      o.dw2 = m->g_(m->off_w2[l]); o.db2 = m->g_(m->off_b2[l]);
+      descs.push_back(d);
+      outs.push_back(o);
+      g = m->gpool[gi++];
+    }
+    if (s > 0) g = m->gpool[gi++];
+  }
+  if (cudaMalloc(&t.descs, descs.size() * sizeof(WgLayerDev)) != cudaSuccess ||
+      cudaMalloc(&t.outs, outs.size() * sizeof(WgLayerOut)) != cudaSuccess ||
+      cudaMemcpy(t.descs, descs.data(), descs.size() * sizeof(WgLayerDev), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(t.outs, outs.data(), outs.size() * sizeof(WgLayerOut), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("tcn_model backward: descriptor upload failed: %s (the first backward of a model must run outside "
+              "stream capture)", cudaGetErrorString(cudaGetLastError()));
+    return TCN_ERR_CUDA;
+  }
+  t.ready = true;
+  return TCN_OK;
+}
+
 }  // namespace
 
 // ================================================================================================ create
@@ -442,6 +494,8 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
   for (int i = 0; i < 4; ++i) o_Gp[i] = carve((size_t)rows * C * 4);
   for (auto& o : o_gpool) o = carve((size_t)rows * C * 4);
   for (auto& o : o_gus) o = carve((size_t)rows * C * 4);
+  wgrad_layers_plan(m->max_blk, &m->wl_lg, &m->wl_splits);
+  const size_t o_wlpart = carve((size_t)m->L * m->wl_splits * WL_PART_FLOATS * 4);
   const size_t o_cs = carve((size_t)cfg->max_seqs * D * 4);
   m->proj_tc = tcn_gemm_tc_supported(D, C) != 0;
   const size_t proj_wf = (size_t)tcn_split_weight_floats(C, D, 1, 0);
@@ -479,6 +533,8 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
   }
   for (auto o : o_gpool) m->gpool.push_back(reinterpret_cast<float*>(m->ws + o));
   for (auto o : o_gus) m->gus.push_back(reinterpret_cast<float*>(m->ws + o));
+  m->wl_part = reinterpret_cast<float*>(m->ws + o_wlpart);
+  m->use_wl = std::getenv("TCN_WGRAD_PAIR") == nullptr;
   m->overlap_wgrad = std::getenv("TCN_NO_WGRAD_STREAM") == nullptr;
   if (cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess) m->overlap_wgrad = false;
   m->evs.resize(m->L + 8, nullptr);
@@ -540,6 +596,10 @@ extern "C" void tcn_model_destroy(tcn_model* m) {
   for (auto& t : m->wgm) {
     if (t.descs) cudaFree(t.descs);
     if (t.tiles) cudaFree(t.tiles);
+  }
+  for (auto& t : m->wl) {
+    if (t.descs) cudaFree(t.descs);
+    if (t.outs) cudaFree(t.outs);
   }
   for (auto ev : m->evs)
     if (ev) cudaEventDestroy(ev);
@@ -812,6 +872,21 @@ static int model_backward(tcn_model* m, const float* x, long x_rows, const float
   const int tr = m->fwd_training ? 1 : 0;
   const bool multi = m->wg_multi && m->use_tc && C == 64 && m->max_blk <= 2 * num_sms();
   if (multi && !m->wgm[tr].ready) TCN_CHECK(build_wg_multi(m, tr));
+  // per-layer weight gradients from one pass (wgrad_layer.cu): wl_lg layers per launch behind their input gradients,
+  // slabs added in fixed order by ONE reduction launch at the end
+  const bool wl = m->use_wl && !multi && m->fused_bwd && m->use_tc && C == 64;
+  if (wl && !m->wl[tr].ready) TCN_CHECK(build_wl_table(m, tr));
+  WgLayersLaunch wq;
+  wq.meta = m->meta; wq.nblk = m->max_blk; wq.dyn = m->desc; wq.splits = m->wl_splits;
+  int wl_first = 0, wl_pending = 0;
+  auto wl_flush = [&]() -> int {
+    if (wl_pending == 0) return TCN_OK;
+    TCN_CHECK(hand_over());  // gy and gu of the pending layers are final
+    TCN_CHECK(launch_wgrad_layers(m->wl[tr].descs + wl_first, wl_pending, wq, ws));
+    wl_first += wl_pending;
+    wl_pending = 0;
+    return TCN_OK;
+  };
   const float* g = m->Gp[3];
   int gi = 0;
   for (int s = 3; s >= 0; --s) {
@@ -853,7 +928,9 @@ static int model_backward(tcn_model* m, const float* x, long x_rows, const float
         if (pl > 0.f) { p.in_drop_thresh = drop_thresh(pl); p.in_drop_scale = 1.f / (1.f - pl); p.in_drop_stream = (uint32_t)l; }
         TCN_CHECK(gemm(m, p, C, C, st));
       }
-      if (!multi) {
+      if (wl) {
+        if (++wl_pending == m->wl_lg) TCN_CHECK(wl_flush());
+      } else if (!multi) {
       TCN_CHECK(hand_over());  // gy (= g) and gu of this layer are final
         WgradDev w2 = base_wgrad(m);
         w2.G = g; w2.ldg = C; w2.g_cols = C; w2.X = m->H[l]; w2.ldx = C; w2.n_out = C; w2.c_in = C;
@@ -887,6 +964,10 @@ static int model_backward(tcn_model* m, const float* x, long x_rows, const float
       TCN_CHECK(gemm(m, p, C, C, st));
       g = m->gpool[gi++];
     }
+  }
+  if (wl) {
+    TCN_CHECK(wl_flush());
+    TCN_CHECK(launch_wgrad_layers_reduce(m->wl[tr].outs, m->L, m->wl_splits, ws));
   }
   // projection weight grads (x is a leaf: no input gradient); same mask / channel scale as the forward
   {

@@ -120,12 +120,33 @@ def wgrad_tc_layer_pair(gu, x, gy, h, lay: SeqLayout, shifts, gw1, gb1, gw2, gb2
 
 def layer_wgrad_kernel_name() -> str:
     """Name of the kernel layer_wgrad() launches (for bench.py's roofline block)."""
-    return "wgrad_tc_pair_kernel"
+    return "wgrad_layer_kernel"
+
+
+_wl_workspace: dict = {}
 
 
 def layer_wgrad(gu, x, gy, h, lay: SeqLayout, shifts, gw1, gb1, gw2, gb2, drop_p=0.0, seed=0, stream_id=0, masks=None):
-    """All weight / bias gradients of one residual layer (accumulating into gw1 / gb1 / gw2 / gb2)."""
-    wgrad_tc_layer_pair(gu, x, gy, h, lay, shifts, gw1, gb1, gw2, gb2, drop_p=drop_p, seed=seed, stream_id=stream_id)
+    """All weight / bias gradients of one 64-channel residual layer, deterministic (csrc/wgrad_layer.cu): accumulates
+    gW1 (C, C, 3) / gb1 over the taps of (gu, x) and gW2 (C, C, 1) / gb2 of (gv, h), gv = keep * gy / (1 - p) with the
+    keep bits taken from `masks` (the words layer_fwd_tc saved) or regenerated from (seed, stream_id)."""
+    lib = _lib.load()
+    assert gu.shape[1] == 64 and all(t.is_contiguous() for t in (gu, x, gy, h, gw1, gw2))
+    dev = gu.device
+    ws = _wl_workspace.get(dev)
+    need = int(lib.tcn_wgrad_layer_workspace_bytes(lay.nblk))
+    if ws is None or ws.numel() < need:
+        ws = _wl_workspace[dev] = torch.empty(need, device=dev, dtype=torch.uint8)
+    a = _lib.WgradLayerArgs()
+    a.gu, a.x, a.gy, a.h, a.rows = _lib.ptr(gu), _lib.ptr(x), _lib.ptr(gy), _lib.ptr(h), gu.shape[0]
+    a.masks = _lib.ptr(masks)
+    a.meta, a.nblk, a.channels = _lib.ptr(lay.meta), lay.nblk, 64
+    for i, s in enumerate(shifts):
+        a.shift[i] = int(s)
+    a.drop_p, a.drop_seed, a.drop_stream = float(drop_p), int(seed) & 0xFFFFFFFF, int(stream_id) & 0xFFFFFFFF
+    a.dw1, a.db1, a.dw2, a.db2 = _lib.ptr(gw1), _lib.ptr(gb1), _lib.ptr(gw2), _lib.ptr(gb2)
+    a.workspace, a.workspace_bytes = _lib.ptr(ws), ws.numel()
+    _lib.check(lib.tcn_wgrad_layer(C.byref(a), _lib.stream_ptr()), "tcn_wgrad_layer")
 
 
 def layer_fwd(x, w1f, w2f, b1, b2, lay: SeqLayout, shifts, save_h=True, drop_p=0.0, seed=0, stream_id=0):
@@ -377,6 +398,13 @@ class DilatedResidualFn(torch.autograd.Function):
         lay, shifts, p = ctx.lay, ctx.shifts, ctx.p
         gy = _f32c(gy)
         Cc = w1.shape[0]
+        if ctx.masks is not None:  # 64 channels on tcgen05: fused input gradient + ONE deterministic weight-gradient pass
+            gu, gx = layer_bwd_tc(gy, ctx.masks, w1, w2, lay, shifts, p)
+            z = lambda *shape: torch.zeros(*shape, device=gy.device, dtype=torch.float32)
+            gw1, gb1, gw2, gb2 = z(Cc, Cc, 3), z(Cc), z(Cc, Cc, 1), z(Cc)
+            layer_wgrad(gu, x, gy, h, lay, shifts, gw1, gb1, gw2, gb2, drop_p=p, seed=ctx.seed, stream_id=ctx.stream_id,
+                        masks=ctx.masks)
+            return gx, gw1, gb1, gw2.view_as(w2), gb2, None, None, None, None, None, None
         # gv = keep * gy / (1 - p) is never materialised: the mask is regenerated as gy is loaded
         gw2 = torch.zeros(Cc, Cc, 1, device=gy.device, dtype=torch.float32)
         gb2 = torch.zeros(Cc, device=gy.device, dtype=torch.float32)

@@ -138,6 +138,26 @@ int tcn_wgrad_tc(const tcn_wgrad_tc_args* args, tcn_stream_t stream);
  * backward) in ONE launch: the grid is split between the two problems.  Both must share meta / nblk, have
  * n_out <= 64 and padded operands.  This is the launch the executor issues per layer. */
 int tcn_wgrad_tc_pair(const tcn_wgrad_tc_args* w1, const tcn_wgrad_tc_args* w2, tcn_stream_t stream);
+/* ALL weight / bias gradients of one 64-channel residual layer in one pass over the frames, deterministic (what autograd
+ * accumulates into conv_dilated.{weight,bias}.grad and conv_1x1.{weight,bias}.grad of network.py:186-198 / :165-183):
+ *   dw1[n, c, k] += sum_t gu[t, n] x[t + shift[k], c]     db1[n] += sum_t gu[t, n]
+ *   dw2[n, c]    += sum_t gv[t, n] h[t, c]                db2[n] += sum_t gv[t, n],   gv = keep * gy / (1 - drop_p)
+ * (csrc/wgrad_layer.cu).  One CTA per frame range computes the four products, stores its partial to a slab of
+ * `workspace` and a second launch adds the slabs in a fixed order: no atomics, bit-identical from run to run.
+ * gu / x / gy / h: packed (rows, 64) fp32, 16-byte aligned.  masks: the (rows, 4) bit words of tcn_layer_fwd_tc (dropout
+ * keep bits in words 2 and 3) or NULL, in which case the keep mask is regenerated from (drop_seed, drop_stream).
+ * workspace: at least tcn_wgrad_layer_workspace_bytes(nblk) bytes of device memory, 16-byte aligned. */
+typedef struct {
+  const float* gu; const float* x; const float* gy; const float* h; long long rows;
+  const unsigned* masks;
+  const int* meta; int nblk; int channels;
+  int shift[3];
+  float drop_p; unsigned drop_seed; unsigned drop_stream;
+  float* dw1; float* db1; float* dw2; float* db2;   /* db1 / db2 may be NULL */
+  void* workspace; long long workspace_bytes;
+} tcn_wgrad_layer_args;
+long long tcn_wgrad_layer_workspace_bytes(int nblk);
+int tcn_wgrad_layer(const tcn_wgrad_layer_args* args, tcn_stream_t stream);
 
 /* ---- fused residual layer, forward ---------------------------------------------------------------
  * y = x + Dropout_p(W2 relu(W1 (*)_d x + b1) + b2), one launch: DilatedResidualLayer.forward

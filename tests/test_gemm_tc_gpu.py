@@ -184,3 +184,64 @@ def test_wgrad_tc_layer_pair_matches_two_launches(lengths, shifts, p):
     ops.wgrad_tc(gy, h, lay, C, C, (0,), rw2, rb2, g_drop_p=p, seed=5, stream_id=9)
     for got, ref in ((gw1, rw1), (gb1, rb1), (gw2, rw2), (gb2, rb2)):
         assert _maxabs(got, ref) <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("lengths,shifts,p,use_masks", [([300, 129, 1], (-4, 0, 4), 0.5, True),
+                                                        ([2250] * 8, (-64, -32, 0), 0.0, False),
+                                                        ([5000, 77], (-1024, 0, 1024), 0.3, False),
+                                                        ([1800], (-512, 0, 512), 0.5, True),
+                                                        ([17, 16, 15, 128, 129], (-2, -1, 0), 0.5, True),
+                                                        ([40000], (-8, 0, 8), 0.5, True)])
+def test_wgrad_layer_matches_fp64_and_is_deterministic(lengths, shifts, p, use_masks):
+    """tcn_wgrad_layer (csrc/wgrad_layer.cu: the four weight-gradient products of a residual layer from one pass, slab
+    reduction in fixed order) against fp64 -- SURVEY 8a closed forms gW1[:, :, k] = sum_t gu[t] x[t + s_k]^T,
+    gW2 = sum_t gv[t] h[t]^T -- with the dropout keep bits either handed over as the forward kernel's bit words or
+    regenerated from the key; two runs must agree bit for bit."""
+    from computervision_codes_b200 import ops
+    from computervision_codes_b200.layout import SeqLayout
+    from oracle import tcn_oracle as O
+
+    torch.manual_seed(sum(lengths) % 1000 + len(lengths))
+    C = 64
+    lay = SeqLayout.get(lengths, DEV)
+    host = [[torch.randn(T, C) for T in lengths] for _ in range(4)]   # gu, x, gy, h per sequence
+    bufs = [torch.full((lay.rows, C), float("nan")) for _ in range(4)]  # pad rows poisoned: the kernel must ignore them
+    for b, hs in zip(bufs, host):
+        for s, T in enumerate(lengths):
+            b[lay.starts[s]:lay.starts[s] + T] = hs[s]
+    gu, x, gy, h = [b.to(DEV) for b in bufs]
+    keep = ops.dropout_keep_mask(lay.rows, C, p, 5, 9, DEV) if p > 0 else torch.ones(lay.rows, C, device=DEV, dtype=torch.uint8)
+    masks = None
+    if use_masks:
+        w = (keep.view(lay.rows, 2, 32).long() << torch.arange(32, device=DEV)).sum(-1)   # bit c of word c // 32
+        w = torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32)
+        masks = torch.zeros(lay.rows, 4, device=DEV, dtype=torch.int32)
+        masks[:, 2:] = w
+    z = lambda *shape: torch.zeros(*shape, device=DEV)
+    outs = []
+    for _ in range(2):
+        gw1, gb1, gw2, gb2 = z(C, C, 3), z(C), z(C, C, 1), z(C)
+        ops.layer_wgrad(gu, x, gy, h, lay, shifts, gw1, gb1, gw2, gb2, drop_p=p, seed=5, stream_id=9, masks=masks)
+        outs.append((gw1, gb1, gw2, gb2))
+    torch.cuda.synchronize()
+    for a, b in zip(*outs):
+        assert torch.equal(a, b), "the slab reduction must be bit-identical from run to run"
+    kd = keep.cpu().double() / (1.0 - p)
+    rw1, rb1 = torch.zeros(C, C, 3, dtype=torch.float64), torch.zeros(C, dtype=torch.float64)
+    rw2, rb2 = torch.zeros(C, C, dtype=torch.float64), torch.zeros(C, dtype=torch.float64)
+    for s, T in enumerate(lengths):
+        gud, xd, gyd, hd = (host[i][s].double() for i in range(4))
+        gvd = gyd * kd[lay.starts[s]:lay.starts[s] + T]
+        xb = xd.t().unsqueeze(0)
+        for k, sh in enumerate(shifts):
+            rw1[:, :, k] += torch.einsum("to,ct->oc", gud, O.shift_time(xb, sh)[0])
+        rb1 += gud.sum(0)
+        rw2 += gvd.t() @ hd
+        rb2 += gvd.sum(0)
+    gw1, gb1, gw2, gb2 = outs[0]
+    for got, ref in ((gw1, rw1), (gb1, rb1), (gw2.view(C, C), rw2), (gb2, rb2)):
+        assert torch.isfinite(got).all()
+        assert _maxabs(got, ref) <= 2e-5 * max(1.0, float(ref.abs().max())), (lengths, shifts, p)
+    # accumulates into dW like the other weight-gradient entry points
+    ops.layer_wgrad(gu, x, gy, h, lay, shifts, gw1, gb1, gw2, gb2, drop_p=p, seed=5, stream_id=9, masks=masks)
+    assert _maxabs(gw1, 2 * rw1) <= 4e-5 * max(1.0, float(rw1.abs().max()))

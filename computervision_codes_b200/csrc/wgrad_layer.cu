@@ -279,6 +279,7 @@ wgrad_layer_kernel(const __grid_constant__ WgLayerDev d, const WgLayersLaunch q)
 
 // dW / db += sum over the slabs in slab order (one thread per 4 consecutive partial elements; fixed order => deterministic)
 __device__ __forceinline__ void wl_reduce_body(const WgLayerOut& o, int splits) {
+  pdl_wait();   // launched with programmatic serialization: the slabs are final only when the producer grid has completed
   const int e4 = blockIdx.x * blockDim.x + threadIdx.x;
   if (e4 >= WL_PART_FLOATS / 4) return;
   const float4* p = reinterpret_cast<const float4*>(o.part) + e4;

@@ -33,6 +33,17 @@ def _check_input(x: torch.Tensor):
 class _LayerBase(nn.Module):
     causal = False
 
+    def __deepcopy__(self, memo):
+        """A plain deep copy with its own dropout stream id.  It must not draw from the RNG: the reference builds its
+        stages as copy.deepcopy(Layer(...)) (network.py:112,142), so under the same seed this mirror has to consume the
+        generator exactly as nn.Module's default deepcopy does -- not at all."""
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        new._stream_id = _next_stream_id()
+        return new
+
     def _run_packed(self, x_rows, lay):
         """x_rows: packed (rows, C).  Returns packed (rows, C)."""
         p = self.dropout.p if self.training else 0.0
@@ -62,11 +73,6 @@ class DilatedResidualLayer(_LayerBase):
         self.dilation = dilation
         self._stream_id = _next_stream_id()
 
-    def __deepcopy__(self, memo):
-        new = DilatedResidualLayer(self.dilation, self.conv_dilated.in_channels, self.conv_dilated.out_channels)
-        new.load_state_dict(self.state_dict())
-        new.train(self.training)
-        return new
 
 
 class DilatedResidualCausalLayer(_LayerBase):
@@ -85,12 +91,6 @@ class DilatedResidualCausalLayer(_LayerBase):
         self.dilation = dilation
         self._stream_id = _next_stream_id()
 
-    def __deepcopy__(self, memo):
-        new = DilatedResidualCausalLayer(self.dilation, self.conv_dilated.in_channels,
-                                         self.conv_dilated.out_channels)
-        new.load_state_dict(self.state_dict())
-        new.train(self.training)
-        return new
 
 
 def _make_layers(num_layers, num_f_maps, causal):

@@ -55,13 +55,14 @@ def gen_layers(net):
     np.savez_compressed(os.path.join(OUT, "tcn_layers.npz"), **out)
 
 
-def gen_videonas(net):
-    """a3-a7: VideoNas(fpn) eval forward, tenco / TERL loss composition, parameter grads."""
+def gen_videonas(net, fname="tcn_videonas.npz", C=16, D=24, T=70, B=1, seed=7):
+    """a3-a7: VideoNas(fpn) eval forward, tenco / TERL loss composition, parameter grads.
+    The default fixture has 16 channels (mma.sync kernels); tcn_videonas_c64.npz (C = 64) pins the tcgen05 fused-layer
+    kernels against the reference in one hop."""
     out = {}
     args = types.SimpleNamespace(fpn=True, output=False, feature=False, trans=False,
                                  mask=False, hier=False)
-    torch.manual_seed(7)
-    C, D, T, B = 16, 24, 70, 1
+    torch.manual_seed(seed)
     m = net.VideoNas(args, 5, 4, 3, C, D, 100).eval()
     x = torch.randn(B, T, D)
     g = torch.Generator().manual_seed(1)
@@ -98,7 +99,7 @@ def gen_videonas(net):
     for fn, lst, y in zip(fns, (outs[1], outs[2], outs[3], outs[0]), labels):
         terms.append(sum(fn(pd[0].transpose(0, 1), y.float()) for pd in lst))
     out["terl_loss_terms"] = np.array([float(t) for t in terms], dtype=np.float64)
-    np.savez_compressed(os.path.join(OUT, "tcn_videonas.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, fname), **out)
 
 
 def gen_stage(net):
@@ -182,6 +183,7 @@ def main():
     net = ref_import.tenco_network()
     gen_layers(net)
     gen_videonas(net)
+    gen_videonas(net, "tcn_videonas_c64.npz", C=64, D=96, T=300, B=1, seed=8)
     gen_stage(net)
     gen_kd()
     from . import gen_golden_mstct

@@ -240,10 +240,13 @@ def test_stage_against_golden(golden_dir):
         assert torch.equal(l1.argmax(1).cpu(), _t(z[tag + ".l1"]).argmax(1))  # phase predictions identical
 
 
-def test_videonas_against_golden(golden_dir):
+@pytest.mark.parametrize("fixture", ["tcn_videonas.npz", "tcn_videonas_c64.npz"])
+def test_videonas_against_golden(golden_dir, fixture):
+    """tcn_videonas.npz has 16 channels (mma.sync kernels); tcn_videonas_c64.npz (C = 64, D = 96, T = 300) pins the
+    tcgen05 fused-layer / weight-gradient kernels against the reference's own outputs in one hop."""
     from computervision_codes_b200.tcn import VideoNas
 
-    z = _load(golden_dir, "tcn_videonas.npz")
+    z = _load(golden_dir, fixture)
     nl_pg, nl_r, n_r, C, D, K, T, B = [int(v) for v in z["cfg"]]
     args = types.SimpleNamespace(fpn=True, output=False, feature=False, trans=False, mask=False, hier=False)
     m = VideoNas(args, nl_pg, nl_r, n_r, C, D, K).to(DEV).eval()

@@ -32,6 +32,7 @@ constexpr int WL_HALF = WL_NATOM * WL_ATOM;   // 24576 B raw (= hi) region; the 
 constexpr int WL_STAGE = 2 * WL_HALF;         // 49152 B
 constexpr int WL_STAGES = 4;
 constexpr int WL_SMEM = WL_STAGES * WL_STAGE + 1024 + 256;
+constexpr int WL_PREFETCH = 8;                // slots prefetched into L2 ahead of the TMA loads
 constexpr int WL_TMEM_COLS = 256;             // D_a @ 0 (64 columns), D_b @ 64 (128 columns)
 
 __device__ __forceinline__ uint64_t wl_desc(uint32_t smem_addr) {   // MN-major, SWIZZLE_128B_BASE32B, LBO = one box
@@ -101,10 +102,38 @@ __device__ __forceinline__ void wgrad_layer_body(const WgLayerDev* __restrict__ 
     // ===================== TMA producer =====================
     if (elect_one()) {
       int it = 0;
+      // L2 prefetch WL_PREFETCH valid slots ahead of the loads: x and h of a layer were written in the forward pass and
+      // come from HBM; with 4 x 24 KB of loads in flight per SM the ring is bound by latency, so the latency must be L2's
+      int pf = s_lo, pf_ahead = 0;
+      auto prefetch_more = [&]() {
+        while (pf_ahead < WL_PREFETCH && pf < s_hi) {
+          const int pblk = pf >> 3;
+          const int pr0 = pblk * kBlkRows + (pf & 7) * WL_RC;
+          if (pr0 < q.meta[pblk].hi) {
+#pragma unroll
+            for (int tap = 0; tap < 3; ++tap) {
+              const int sh = tap == 0 ? d->shift[0] : (tap == 1 ? d->shift[1] : d->shift[2]);
+              tma_prefetch_2d(&d->mx, 0, pr0 + sh);
+              tma_prefetch_2d(&d->mx, 32, pr0 + sh);
+            }
+            tma_prefetch_2d(&d->mh, 0, pr0);
+            tma_prefetch_2d(&d->mh, 32, pr0);
+            tma_prefetch_2d(&d->mgu, 0, pr0);
+            tma_prefetch_2d(&d->mgu, 32, pr0);
+            tma_prefetch_2d(&d->mgy, 0, pr0);
+            tma_prefetch_2d(&d->mgy, 32, pr0);
+            ++pf_ahead;
+          }
+          ++pf;
+        }
+      };
+      prefetch_more();
       for (int slot = s_lo; slot < s_hi; ++slot) {
         const int blk = slot >> 3;
         const int r0 = blk * kBlkRows + (slot & 7) * WL_RC;
         if (r0 >= q.meta[blk].hi) continue;
+        --pf_ahead;
+        prefetch_more();
         const int s = it % WL_STAGES;
         mbar_wait(&empty_bar[s], ((it / WL_STAGES) & 1) ^ 1);
         uint8_t* st = tiles + s * WL_STAGE;
@@ -277,25 +306,38 @@ wgrad_layer_kernel(const __grid_constant__ WgLayerDev d, const WgLayersLaunch q)
   wgrad_layer_body(&d, q, blockIdx.x);
 }
 
-// dW / db += sum over the slabs in slab order (one thread per 4 consecutive partial elements; fixed order => deterministic)
+// dW / db += sum over the slabs.  Block = 32 float4 columns x 8 slab groups: group g adds slabs g, g + 8, ... in order,
+// then the eight group sums are added in group order -- a fixed tree for a given split count => bit-identical results.
+constexpr int WL_RED_GROUPS = 8;
 __device__ __forceinline__ void wl_reduce_body(const WgLayerOut& o, int splits) {
+  __shared__ float4 red[WL_RED_GROUPS][32];
   pdl_wait();   // launched with programmatic serialization: the slabs are final only when the producer grid has completed
-  const int e4 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e4 >= WL_PART_FLOATS / 4) return;
-  const float4* p = reinterpret_cast<const float4*>(o.part) + e4;
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int e4 = blockIdx.x * 32 + lane;
   constexpr size_t kStride = WL_PART_FLOATS / 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  int s = 0;
-  for (; s + 4 <= splits; s += 4) {   // four loads in flight, additions in slab order
-    const float4 a = __ldg(p + (size_t)(s + 0) * kStride), b = __ldg(p + (size_t)(s + 1) * kStride);
-    const float4 c = __ldg(p + (size_t)(s + 2) * kStride), e = __ldg(p + (size_t)(s + 3) * kStride);
-    acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
-    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
-    acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
-    acc.x += e.x; acc.y += e.y; acc.z += e.z; acc.w += e.w;
+  if (e4 < WL_PART_FLOATS / 4) {
+    const float4* p = reinterpret_cast<const float4*>(o.part) + e4;
+    int s = g;
+    for (; s + 3 * WL_RED_GROUPS < splits; s += 4 * WL_RED_GROUPS) {   // four loads in flight, additions in slab order
+      const float4 a = __ldg(p + (size_t)s * kStride), b = __ldg(p + (size_t)(s + WL_RED_GROUPS) * kStride);
+      const float4 c = __ldg(p + (size_t)(s + 2 * WL_RED_GROUPS) * kStride), e = __ldg(p + (size_t)(s + 3 * WL_RED_GROUPS) * kStride);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+      acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+      acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
+      acc.x += e.x; acc.y += e.y; acc.z += e.z; acc.w += e.w;
+    }
+    for (; s < splits; s += WL_RED_GROUPS) {
+      const float4 a = __ldg(p + (size_t)s * kStride);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
   }
-  for (; s < splits; ++s) {
-    const float4 a = __ldg(p + (size_t)s * kStride);
+  red[g][lane] = acc;
+  __syncthreads();
+  if (g != 0 || e4 >= WL_PART_FLOATS / 4) return;
+#pragma unroll
+  for (int k = 1; k < WL_RED_GROUPS; ++k) {
+    const float4 a = red[k][lane];
     acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
   }
   const float av[4] = {acc.x, acc.y, acc.z, acc.w};
@@ -358,7 +400,7 @@ int launch_wgrad_layers(const WgLayerDev* descs_dev, int nlayers, const WgLayers
 }
 
 int launch_wgrad_layers_reduce(const WgLayerOut* outs_dev, int nlayers, int splits, cudaStream_t stream) {
-  const int nb = (WL_PART_FLOATS / 4 + 255) / 256;
+  const int nb = (WL_PART_FLOATS / 4 + 31) / 32;
   launch_kernel(wgrad_layers_reduce_kernel, dim3(nb, nlayers, 1), dim3(256), 0, stream, true, outs_dev, splits);
   return check_launch("wgrad_layers_reduce_kernel");
 }
@@ -411,7 +453,7 @@ extern "C" int tcn_wgrad_layer(const tcn_wgrad_layer_args* a, tcn_stream_t strea
   TCN_CHECK(check_launch("wgrad_layer_kernel"));
   WgLayerOut o;
   o.part = d.part; o.dw1 = a->dw1; o.db1 = a->db1; o.dw2 = a->dw2; o.db2 = a->db2;
-  const int nb = (WL_PART_FLOATS / 4 + 255) / 256;
+  const int nb = (WL_PART_FLOATS / 4 + 31) / 32;
   launch_kernel(wgrad_layer_reduce_kernel, dim3(nb, 1, 1), dim3(256), 0, (cudaStream_t)stream, true, o, splits);
   return check_launch("wgrad_layer_reduce_kernel");
 }

@@ -329,7 +329,12 @@ class VideoNas(nn.Module):
         lay = SeqLayout.uniform(B, T, x.device)
         x_btd = x.contiguous().float()
         mask_btd = None
-        if getattr(self.args, "mask", False) and ismask:
+        want_mask = bool(getattr(self.args, "mask", False) and ismask)
+        # Executor path in train mode: the 25 % input mask (network.py:43-48) and Dropout2d are drawn on the device by
+        # the projection kernel's counter-based generator (Bernoulli(0.25) per element instead of the reference's
+        # exact-count permutation), as in TemporalTrainer -- no host randperm, no H2D, no eager multiply.
+        device_mask = want_mask and self.training and self._executor_ok() and not x.requires_grad
+        if want_mask and not device_mask:
             n = x_btd.numel()
             num_mask = int(n * 0.75)
             mask = torch.cat((torch.zeros(n - num_mask), torch.ones(num_mask)))
@@ -339,7 +344,8 @@ class VideoNas(nn.Module):
             xin = x_btd if mask_btd is None else x_btd * mask_btd
             x_rows = xin.reshape(B * T, D).contiguous()
             lay_e = lay
-            self._get_executor(lay_e)
+            ex = self._get_executor(lay_e)
+            ex.set_dropout(0.25 if device_mask else 0.0, self.PG.channel_dropout.p, self.PG.layers[0].dropout.p)
             plist = [p for _, p in self._exec_params]
             need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in plist)
             outs = _VideoNasExecFn.apply(self, x_rows, lay_e, self.training, need_grad, *plist)

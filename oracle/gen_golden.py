@@ -130,6 +130,24 @@ def gen_stage(net):
     np.savez_compressed(os.path.join(OUT, "tcn_stage.npz"), **out)
 
 
+def gen_refine_output(net):
+    """a4 with args.output = True: Refinement applies its own conv_1x1 (K -> C) to the previous stage's K-channel output
+    (network.py:150-151).  Forward + all parameter gradients."""
+    out = {}
+    torch.manual_seed(13)
+    C, K, T, B, L = 32, 10, 90, 2, 4
+    rf = net.Refinement(types.SimpleNamespace(output=True, hier=False), L, C, K, K, None).eval()
+    x = torch.randn(B, K, T)
+    f, lg = rf(x)
+    gf, gl = torch.randn_like(f), torch.randn_like(lg)
+    ((f * gf).sum() + (lg * gl).sum()).backward()
+    out["cfg"] = np.array([L, C, K, T, B])
+    out["x"], out["f"], out["logits"], out["gf"], out["gl"] = _np(x), _np(f), _np(lg), _np(gf), _np(gl)
+    out.update({"sd." + k: _np(v) for k, v in rf.state_dict().items()})
+    out.update({"grad." + k: _np(v.grad) for k, v in rf.named_parameters() if v.grad is not None})
+    np.savez_compressed(os.path.join(OUT, "tcn_refine_output.npz"), **out)
+
+
 def gen_kd():
     """a8: DistillKL (the reference class itself) + BCE / MSE composition of Spatial_cnn/run.py."""
     out = {}
@@ -185,6 +203,7 @@ def main():
     gen_videonas(net)
     gen_videonas(net, "tcn_videonas_c64.npz", C=64, D=96, T=300, B=1, seed=8)
     gen_stage(net)
+    gen_refine_output(net)
     gen_kd()
     from . import gen_golden_mstct
     gen_golden_mstct.main()

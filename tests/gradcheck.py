@@ -1,0 +1,31 @@
+"""Gradient comparison for whole-model tests.
+
+A ReLU network's gradient is a discontinuous function of its pre-activations.  Two correct finite-precision forward
+passes (this library's 3xTF32 kernels, torch's fp32 convolutions, the fp64 oracle) disagree by ~1e-6 in u = conv(x), so
+wherever |u[t, c]| is that small they take different sides of the ReLU: gu[t, c] is either g or 0, and a handful of rows
+of the upstream weight gradients move by about one frame's contribution (~1e-3 of the tensor's largest entry) -- in a
+41-layer model on 1,800 frames a few of the 4.7 M pre-activations always fall inside that band (counted on the fp64
+reference: 5 of 725,760 below 2e-6 in the edge-length test).  Kernel-level tests (given masks) hold every gradient to
+2e-5; here the bulk must agree that tightly and the few flipped rows are bounded.
+"""
+import torch
+
+
+def grad_errors(got, ref):
+    g, r = got.detach().double().cpu().reshape(-1), ref.detach().double().cpu().reshape(-1)
+    scale = max(float(r.abs().max()), 1e-30)
+    d = (g - r).abs()
+    return float(d.max()), scale, float(torch.linalg.vector_norm(g - r) / max(float(torch.linalg.vector_norm(r)), 1e-30)), d
+
+
+def assert_grad_close(got, ref, name="", strict=3e-5, flip_frac=0.03, flip_max=5e-3, flip_l2=2e-3, atol=1e-6):
+    """Strict: max |got - ref| <= strict * max(1, max |ref|) + atol.  Otherwise the deviation must look like ReLU flips:
+    at most flip_frac of the entries outside the strict band, none further than flip_max * max |ref|, relative L2 error
+    <= flip_l2.  A structural bug (wrong tap, mask, scale) moves most entries by O(1) and fails all three."""
+    maxerr, scale, rel_l2, d = grad_errors(got, ref)
+    band = strict * max(1.0, scale) + atol
+    if maxerr <= band:
+        return
+    frac = float((d > band).double().mean())
+    assert frac <= flip_frac and maxerr <= flip_max * scale + atol and rel_l2 <= flip_l2, \
+        (name, {"max_err": maxerr, "max_ref": scale, "rel_l2": rel_l2, "frac_outside_strict_band": frac})

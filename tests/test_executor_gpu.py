@@ -6,6 +6,8 @@ import torch
 
 from oracle import tcn_oracle as O
 
+from gradcheck import assert_grad_close
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 ARGS = types.SimpleNamespace(fpn=True, output=False, feature=False, trans=False, mask=False, hier=False)
@@ -68,7 +70,7 @@ def test_executor_eval_matches_oracle_and_eager(C, causal):
         if r is None:
             continue
         assert p.grad is not None, name
-        assert _maxabs(p.grad, r) <= 3e-5 * max(1.0, float(r.abs().max())) + 1e-6, (name, _maxabs(p.grad, r))
+        assert_grad_close(p.grad, r, name)
     # inference outputs of the executor == oracle (logits <= 1e-3, argmax identical)
     feats, logits = ex.forward(x_rows, training=False)
     torch.cuda.synchronize()
@@ -129,7 +131,7 @@ def test_executor_train_mode_with_the_kernels_own_masks(D):
         r = ref_grads[name]
         if r is None:
             continue
-        assert _maxabs(p.grad, r) <= 3e-5 * max(1.0, float(r.abs().max())) + 1e-6, (name, _maxabs(p.grad, r))
+        assert_grad_close(p.grad, r, name)
 
 
 def test_trainer_graph_replay_equals_eager_steps():
@@ -264,7 +266,7 @@ def test_executor_edge_lengths_one_frame_to_block_boundaries(causal):
         r = ref_grads[name]
         if r is None:
             continue
-        assert _maxabs(p.grad, r) <= 3e-5 * max(1.0, float(r.abs().max())) + 1e-6, (name, _maxabs(p.grad, r))
+        assert_grad_close(p.grad, r, name)
     feats, logits = ex.forward(torch.cat(xs).to(DEV), training=False)
     torch.cuda.synchronize()
     with torch.no_grad():

@@ -13,6 +13,8 @@ import torch
 
 from oracle import tcn_oracle as O
 
+from gradcheck import assert_grad_close
+
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda"
@@ -275,7 +277,7 @@ def test_videonas_against_golden(golden_dir, fixture):
         if "grad." + k in z.files:
             ref = _t(z["grad." + k])
             assert v.grad is not None, k
-            assert _maxabs(v.grad, ref) <= 2e-5 * max(1.0, float(ref.abs().max())) + 1e-6, (k, _maxabs(v.grad, ref))
+            assert_grad_close(v.grad, ref, k, strict=2e-5)
         else:
             assert k in nograd and v.grad is None, k  # stays None so SGD weight decay skips it, as in the reference
 
@@ -294,7 +296,7 @@ def test_videonas_against_golden(golden_dir, fixture):
     for k, v in m.named_parameters():
         if "grad." + k in z.files:
             ref = _t(z["grad." + k])
-            assert _maxabs(v.grad, ref) <= 2e-5 * max(1.0, float(ref.abs().max())) + 1e-6, (k, _maxabs(v.grad, ref))
+            assert_grad_close(v.grad, ref, k, strict=2e-5)
     with torch.no_grad():
         _, li, lv, lt, livt = losses.tenco_loss(logit_rows, lab, lay, terl_pos_weight=True)
     np.testing.assert_allclose([float(li), float(lv), float(lt), float(livt)], z["terl_loss_terms"], rtol=1e-4)
@@ -469,3 +471,70 @@ def test_video_ap_matches_sklearn_average_precision():
         classwise = np.nanmean(np.stack(per_video), axis=0)
     assert np.allclose(res["AP"], classwise, atol=2e-6, equal_nan=True)
     assert abs(res["mAP"] - np.nanmean(classwise)) <= 2e-6
+
+
+def test_refinement_with_args_output_against_golden(golden_dir):
+    """Refinement(args.output=True) (network.py:150-151): its own conv_1x1 (K -> C) on a K-channel input; outputs and
+    every parameter gradient against the reference's run (K = 10: the row pitch is not a multiple of 16 bytes, so the
+    projection takes the mma.sync tap GEMM)."""
+    from computervision_codes_b200.tcn import Refinement
+
+    z = _load(golden_dir, "tcn_refine_output.npz")
+    L, C, K, T, B = [int(v) for v in z["cfg"]]
+    rf = Refinement(types.SimpleNamespace(output=True, hier=False), L, C, K, K, None).to(DEV).eval()
+    rf.load_state_dict({k[3:]: _t(z[k]) for k in z.files if k.startswith("sd.")})
+    f, lg = rf(_t(z["x"]).to(DEV))
+    assert _maxabs(f, _t(z["f"])) <= 1e-4 and _maxabs(lg, _t(z["logits"])) <= 1e-4
+    ((f * _t(z["gf"]).to(DEV)).sum() + (lg * _t(z["gl"]).to(DEV)).sum()).backward()
+    for k, v in rf.named_parameters():
+        ref = _t(z["grad." + k])
+        assert _maxabs(v.grad, ref) <= 3e-5 * max(1.0, float(ref.abs().max())), k
+
+
+def test_args_hier_is_refused_loudly():
+    """args.hier (AvgPool1d(7, 3) between stages, network.py:145,156-157) is not on the CUDA path: constructing a stage
+    with it must raise instead of silently running a different network (no reference script enables it)."""
+    from computervision_codes_b200.tcn import Refinement, VideoNas
+
+    with pytest.raises(NotImplementedError):
+        Refinement(types.SimpleNamespace(output=False, hier=True), 2, 16, 16, 7, None)
+    with pytest.raises(NotImplementedError):
+        VideoNas(types.SimpleNamespace(fpn=True, output=False, feature=False, trans=False, mask=False, hier=True),
+                 2, 2, 3, 16, 24, 100)
+
+
+def test_second_forward_before_backward_is_refused():
+    """The native executor keeps one set of saved activations: backward of a forward that a later forward has overwritten
+    must raise, not return gradients of the wrong batch."""
+    from computervision_codes_b200.tcn import VideoNas
+
+    args = types.SimpleNamespace(fpn=True, output=False, feature=False, trans=False, mask=False, hier=False)
+    torch.manual_seed(0)
+    m = VideoNas(args, 3, 2, 3, 64, 32, 100).to(DEV).train()
+    x1, x2 = torch.randn(1, 200, 32, device=DEV), torch.randn(1, 200, 32, device=DEV)
+    o1 = m(x1, False)
+    o2 = m(x2, False)
+    with pytest.raises(RuntimeError, match="one outstanding forward"):
+        o1[0][0].sum().backward()
+    o2[0][0].sum().backward()   # the latest forward is fine
+    assert m.PG.conv_1x1.weight.grad is not None
+
+
+def test_drop_in_forward_with_mask_runs_the_device_side_generator():
+    """forward(x, ismask=True) with args.mask in train mode: the 25 % input mask is drawn inside the projection kernel
+    (no host randperm / H2D); two calls draw different masks, the gradient is finite, eval mode is unaffected."""
+    from computervision_codes_b200.tcn import VideoNas
+
+    args = types.SimpleNamespace(fpn=True, output=False, feature=False, trans=False, mask=True, hier=False)
+    torch.manual_seed(0)
+    m = VideoNas(args, 3, 2, 3, 64, 32, 100).to(DEV).train()
+    x = torch.randn(1, 300, 32, device=DEV)
+    a = m(x, True)[0][0].detach().clone()
+    out = m(x, True)
+    assert not torch.equal(a, out[0][0])
+    out[0][0].sum().backward()
+    assert bool(torch.isfinite(m.PG.conv_1x1.weight.grad).all())
+    m.eval()
+    with torch.no_grad():
+        e1, e2 = m(x, False)[0][0].clone(), m(x, False)[0][0].clone()
+    assert torch.equal(e1, e2)

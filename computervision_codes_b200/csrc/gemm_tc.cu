@@ -1058,14 +1058,6 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const BlkMeta m = p.y.meta[blk];
         const int row0 = blk * kBlkRows;
         if (row0 >= m.hi) continue;
-        if (blk + (int)gridDim.x < nblk) {   // this CTA's next tile: pull it into L2 while this one is processed
-          const int nrow0 = (blk + (int)gridDim.x) * kBlkRows;
-#pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            const int sh = (j >> 1) == 0 ? p.y.shift[0] : ((j >> 1) == 1 ? p.y.shift[1] : p.y.shift[2]);
-            tma_prefetch_2d(&map_x, (j & 1) * TC_BK, nrow0 + sh);
-          }
-        }
         for (int j = 0; j < 6; ++j, ++it) {
           const int tap = j >> 1, kc = j & 1;
           const int s = it % LFT_STAGES;
@@ -1417,14 +1409,6 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_con
         const BlkMeta m = p.gx.meta[blk];
         const int row0 = blk * kBlkRows;
         if (row0 >= m.hi) continue;
-        if (blk + (int)gridDim.x < nblk) {   // this CTA's next tile: pull it into L2 while this one is processed
-          const int nrow0 = (blk + (int)gridDim.x) * kBlkRows;
-#pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            const int sh = (j >> 1) == 0 ? p.gx.shift[0] : ((j >> 1) == 1 ? p.gx.shift[1] : p.gx.shift[2]);
-            tma_prefetch_2d(&map_gy, (j & 1) * TC_BK, nrow0 + sh);
-          }
-        }
         for (int j = 0; j < 6; ++j, ++it) {
           const int tap = j >> 1, kc = j & 1;
           const int s = it % LFT_STAGES;

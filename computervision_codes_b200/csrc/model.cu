@@ -877,7 +877,7 @@ static int model_backward(tcn_model* m, const float* x, long x_rows, const float
   const bool wl = m->use_wl && !multi && m->fused_bwd && m->use_tc && C == 64;
   if (wl && !m->wl[tr].ready) TCN_CHECK(build_wl_table(m, tr));
   WgLayersLaunch wq;
-  wq.meta = m->meta; wq.nblk = m->max_blk; wq.dyn = m->desc; wq.splits = m->wl_splits;
+  wq.meta = m->meta; wq.nblk = m->max_blk; wq.dyn = m->desc; wq.splits = m->wl_splits; wq.debug = 0;
   int wl_first = 0, wl_pending = 0;
   auto wl_flush = [&]() -> int {
     if (wl_pending == 0) return TCN_OK;

@@ -69,7 +69,7 @@ __device__ __forceinline__ void wgrad_layer_body(const WgLayerDev* __restrict__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < WL_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&ready_bar[s], WL_SPLIT);
+      mbar_init(&ready_bar[s], WL_SPLIT / 32);   // one arrival per split warp
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(accum_bar, 1);
@@ -105,8 +105,9 @@ __device__ __forceinline__ void wgrad_layer_body(const WgLayerDev* __restrict__ 
       // L2 prefetch WL_PREFETCH valid slots ahead of the loads: x and h of a layer were written in the forward pass and
       // come from HBM; with 4 x 24 KB of loads in flight per SM the ring is bound by latency, so the latency must be L2's
       int pf = s_lo, pf_ahead = 0;
+      const int pf_dist = (q.debug >> 8) ? (q.debug >> 8) - 1 : WL_PREFETCH;   // experiments: distance - 1 in bits 8..
       auto prefetch_more = [&]() {
-        while (pf_ahead < WL_PREFETCH && pf < s_hi) {
+        while (pf_ahead < pf_dist && pf < s_hi) {
           const int pblk = pf >> 3;
           const int pr0 = pblk * kBlkRows + (pf & 7) * WL_RC;
           if (pr0 < q.meta[pblk].hi) {
@@ -137,6 +138,15 @@ __device__ __forceinline__ void wgrad_layer_body(const WgLayerDev* __restrict__ 
         const int s = it % WL_STAGES;
         mbar_wait(&empty_bar[s], ((it / WL_STAGES) & 1) ^ 1);
         uint8_t* st = tiles + s * WL_STAGE;
+        if (q.debug & 4) {
+          mbar_arrive_expect_tx(&full_bar[s], 4 * WL_ATOM);
+          tma_load_2d(st + 0 * WL_ATOM, &d->mx, &full_bar[s], 0, r0);
+          tma_load_2d(st + 1 * WL_ATOM, &d->mx, &full_bar[s], 32, r0);
+          tma_load_2d(st + 8 * WL_ATOM, &d->mgu, &full_bar[s], 0, r0);
+          tma_load_2d(st + 9 * WL_ATOM, &d->mgu, &full_bar[s], 32, r0);
+          ++it;
+          continue;
+        }
         mbar_arrive_expect_tx(&full_bar[s], WL_HALF);
 #pragma unroll
         for (int tap = 0; tap < 3; ++tap) {
@@ -165,6 +175,7 @@ __device__ __forceinline__ void wgrad_layer_body(const WgLayerDev* __restrict__ 
         const uint32_t hi0 = base + s * WL_STAGE, lo0 = hi0 + WL_HALF;
 #pragma unroll
         for (int k = 0; k < WL_RC / 8; ++k) {
+          if (q.debug & 1) break;
           const uint32_t ko = k * 1024;   // 8 frames
           const uint64_t a1h = wl_desc(hi0 + ko), a1l = wl_desc(lo0 + ko);
           const uint64_t a2h = wl_desc(hi0 + 4 * WL_ATOM + ko), a2l = wl_desc(lo0 + 4 * WL_ATOM + ko);
@@ -194,19 +205,47 @@ __device__ __forceinline__ void wgrad_layer_body(const WgLayerDev* __restrict__ 
     float4 bs_gu = make_float4(0.f, 0.f, 0.f, 0.f), bs_gv = bs_gu;
     int it = 0;
     int cur_blk = -1;
-    BlkMeta m = {0, 0, 0, 0};
+    BlkMeta m = {0, 0, 0, 0}, m_next = {0, 0, 0, 0};
+    const bool use_bits = d->use_drop && d->masks != nullptr;
+    const int total_rows = nblk * kBlkRows;
+    // the keep word of the NEXT slot and the block table entry of the NEXT block are fetched one iteration ahead: a global
+    // load issued and consumed inside one iteration put its full latency on every slot (ncu: 22 % of all stall samples
+    // sat on the first use of the keep word)
+    uint32_t keep_pref = 0u;
+    int pref_slot = -1;
     for (int slot = s_lo; slot < s_hi; ++slot) {
       const int blk = slot >> 3;
-      if (blk != cur_blk) { m = q.meta[blk]; cur_blk = blk; }
+      if (blk != cur_blk) {
+        m = (blk == cur_blk + 1 && cur_blk >= 0) ? m_next : q.meta[blk];
+        cur_blk = blk;
+        if (blk + 1 < nblk) m_next = q.meta[blk + 1];
+      }
       const int r0 = blk * kBlkRows + (slot & 7) * WL_RC;
       if (r0 >= m.hi) continue;
       const int row = r0 + r;
       const bool row_ok = row < m.hi;
-      // dropout keep bits of (row, 32 channels of this half): fetched before the wait on the TMA bytes
+      // dropout keep bits of (row, 32 channels of this half)
       uint32_t keepw = 0xffffffffu;
-      if (d->use_drop && d->masks != nullptr && row_ok) keepw = __ldg(d->masks + (size_t)row * 4 + 2 + ph);
+      if (use_bits) {
+        if (pref_slot == slot) keepw = keep_pref;
+        else if (row_ok) keepw = __ldg(d->masks + (size_t)row * 4 + 2 + ph);
+        const int nrow = row + WL_RC;   // the same frame position in slot + 1 (blocks are contiguous)
+        if (slot + 1 < s_hi && nrow < total_rows) {
+          keep_pref = __ldg(d->masks + (size_t)nrow * 4 + 2 + ph);
+          pref_slot = slot + 1;
+        }
+      }
       const int s = it % WL_STAGES;
-      mbar_wait(&full_bar[s], (it / WL_STAGES) & 1);
+      // ONE lane polls, the warp follows through __syncwarp: ncu counts 32 shared-memory wavefronts for a try_wait executed
+      // by a full warp (9.6 M of the kernel's 15.7 M shared-load wavefronts were such replays, on a 90 % busy pipe)
+      if (lane == 0) mbar_wait(&full_bar[s], (it / WL_STAGES) & 1);
+      __syncwarp();
+      if (q.debug & 2) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready_bar[s]);
+        ++it;
+        continue;
+      }
       float4* raw = reinterpret_cast<float4*>(tiles + s * WL_STAGE) + ph * 128 + idx;
       float4* lo = raw + WL_HALF / 16;
       float4 v[6];
@@ -251,11 +290,13 @@ __device__ __forceinline__ void wgrad_layer_body(const WgLayerDev* __restrict__ 
         lo[i * 256] = l;
       }
       fence_proxy_async();
-      mbar_arrive(&ready_bar[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ready_bar[s]);
       ++it;
     }
     // ===================== epilogue: the CTA's partial to its slab =====================
-    mbar_wait(accum_bar, 0);
+    if (lane == 0) mbar_wait(accum_bar, 0);
+    __syncwarp();
     tc_fence_after();
     // bias sums: fixed-order reduction over the 16 frame positions through shared memory (the stages are free now)
     float* red = reinterpret_cast<float*>(tiles);   // [2][16][64]
@@ -449,6 +490,10 @@ extern "C" int tcn_wgrad_layer(const tcn_wgrad_layer_args* a, tcn_stream_t strea
   d.part = reinterpret_cast<float*>(a->workspace);
   WgLayersLaunch q;
   q.meta = reinterpret_cast<const BlkMeta*>(a->meta); q.nblk = a->nblk; q.dyn = nullptr; q.splits = splits;
+  {
+    const char* e = getenv("TCN_WL_DEBUG");
+    q.debug = e ? atoi(e) : 0;
+  }
   launch_kernel(wgrad_layer_kernel, dim3(splits, 1, 1), dim3(WL_THREADS), WL_SMEM, (cudaStream_t)stream, true, d, q);
   TCN_CHECK(check_launch("wgrad_layer_kernel"));
   WgLayerOut o;

@@ -22,6 +22,7 @@ struct WgLayersLaunch {
   int nblk;
   const BatchDesc* dyn;
   int splits;
+  int debug;   // experiments only (TCN_WL_DEBUG): 1 = no MMAs, 2 = no operand split, 4 = load 4 of the 12 boxes
 };
 struct WgLayerOut {   // where the reduction adds a layer's partials
   const float* part;

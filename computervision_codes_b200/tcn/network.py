@@ -158,7 +158,13 @@ class Refinement(nn.Module):
     def _features_packed(self, f_rows, lay):
         out = f_rows
         if self.use_output:
-            out = ops.tap_linear(out, self.conv_1x1.weight, self.conv_1x1.bias, lay)
+            w = self.conv_1x1.weight
+            k = out.shape[1]
+            if k % 4 != 0:   # the kernels need a 16-byte row pitch: zero-pad the K input channels (and the weight with them)
+                pad = 4 - k % 4
+                out = torch.nn.functional.pad(out, (0, pad))
+                w = torch.nn.functional.pad(w, (0, 0, 0, pad))
+            out = ops.tap_linear(out, w, self.conv_1x1.bias, lay)
         for layer in self.layers:
             out = layer._run_packed(out, lay)
         return out

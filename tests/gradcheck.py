@@ -18,7 +18,7 @@ def grad_errors(got, ref):
     return float(d.max()), scale, float(torch.linalg.vector_norm(g - r) / max(float(torch.linalg.vector_norm(r)), 1e-30)), d
 
 
-def assert_grad_close(got, ref, name="", strict=3e-5, flip_frac=0.03, flip_max=5e-3, flip_l2=2e-3, atol=1e-6):
+def assert_grad_close(got, ref, name="", strict=3e-5, flip_frac=0.03, flip_max=1e-2, flip_l2=5e-3, atol=1e-6):
     """Strict: max |got - ref| <= strict * max(1, max |ref|) + atol.  Otherwise the deviation must look like ReLU flips:
     at most flip_frac of the entries outside the strict band, none further than flip_max * max |ref|, relative L2 error
     <= flip_l2.  A structural bug (wrong tap, mask, scale) moves most entries by O(1) and fails all three."""

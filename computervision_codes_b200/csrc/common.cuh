@@ -288,6 +288,9 @@ struct BceDev {
   int nlev;
   const float* logits_lv[4];
   float* dL_lv[4];
+  // cum_lv != null (with nlev > 0): ONE warp walks the levels of a row (labels read once) and also writes the running sum
+  // cum_lv[l] = dL_lv[0] + ... + dL_lv[l]: with shared head weights the gradient w.r.t. FPN level l is cum_lv[l] W (network.py:98-106)
+  float* cum_lv[4];
 };
 int launch_bce(const BceDev& p, int cap_rows, cudaStream_t stream);
 int launch_chan_scale(float* out, int ld, int max_seqs, const BatchDesc* dyn, float p, uint32_t seed,

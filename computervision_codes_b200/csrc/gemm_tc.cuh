@@ -245,7 +245,15 @@ struct WgradTcDev {
   uint32_t x_drop_thresh;
   float x_drop_scale;
   uint32_t x_drop_seed, x_drop_stream;
+  // deterministic mode: every row split stores its partial dW / db to its own slab (pre-zeroed by the caller) instead of
+  // adding it to dW / db with fp32 atomics; slab_reduce() then adds the slabs in split order
+  float* slab;          // [slab_splits][slab_stride] or nullptr
+  long slab_stride;     // floats per split: n_out * c_in * ntaps (+ n_out for db, stored behind dW)
+  int slab_splits;      // capacity: the launcher never uses more row splits than this
 };
+// out[i] += sum over s < nsplit of slab[s * stride + i] in split order (fixed summation tree: bit-identical results)
+int launch_slab_reduce(float* out, const float* slab, long n, int nsplit, long stride, cudaStream_t stream);
+int wgrad_tc_splits_cap(int n_out, int c_in, int ntaps);   // upper bound of the row splits launch_wgrad_tc chooses
 // mx / mg: maps built with make_tensor_map_2d(..., WG_BOX_ROWS, /*atom32=*/true)
 int launch_wgrad_tc(const CUtensorMap& mx, const CUtensorMap& mg, WgradTcDev& p, int cap_nblk, cudaStream_t stream);
 // Many independent weight-gradient problems in ONE launch (all residual layers of a stage): descriptors (tensor maps +

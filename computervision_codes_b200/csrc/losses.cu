@@ -29,8 +29,9 @@ __global__ void __launch_bounds__(256) bce_rows_kernel(const BceDev p) {
 
   const int nrows = p.dyn ? p.dyn->rows : p.nrows;
   const float rsc = p.dyn ? 1.f / (float)p.dyn->num_seqs : p.row_scale_const;
-  const float* logits = p.nlev > 0 ? p.logits_lv[blockIdx.y] : p.logits;
-  float* dL = p.nlev > 0 ? p.dL_lv[blockIdx.y] : p.dL;
+  const bool walk = p.nlev > 0 && p.cum_lv[0] != nullptr;   // one warp per row over all levels (gridDim.y == 1)
+  const float* logits = p.nlev > 0 ? p.logits_lv[walk ? 0 : blockIdx.y] : p.logits;
+  float* dL = p.nlev > 0 ? p.dL_lv[walk ? 0 : blockIdx.y] : p.dL;
   const bool fast = p.zero_cols <= 32 * kBceMaxIt;
   // fast path: a lane owns the same columns in every row, so the per-column constants live in registers and the loss is
   // summed per column; the head of each column is looked at once, after the row loop
@@ -53,6 +54,54 @@ __global__ void __launch_bounds__(256) bce_rows_kernel(const BceDev p) {
     }
     const float* x = logits + (size_t)row * p.ldl;
     const uint8_t* y = p.labels + (size_t)lrow * p.ldlab;
+    if (walk) {   // fast-path arithmetic for every level of this row; labels and per-column constants are read once
+      float yv[kBceMaxIt], run[kBceMaxIt], xv[4][kBceMaxIt];
+#pragma unroll
+      for (int k = 0; k < kBceMaxIt; ++k) {
+        const int c = lane + 32 * k;
+        yv[k] = (c < p.ncols && y[c]) ? 1.f : 0.f;
+        run[k] = 0.f;
+      }
+#pragma unroll
+      for (int lv = 0; lv < 4; ++lv) {   // all loads of the row in flight before the arithmetic
+        if (lv < p.nlev) {
+          const float* xl = p.logits_lv[lv] + (size_t)row * p.ldl;
+#pragma unroll
+          for (int k = 0; k < kBceMaxIt; ++k) {
+            const int c = lane + 32 * k;
+            xv[lv][k] = c < p.ncols ? xl[c] : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int lv = 0; lv < 4; ++lv) {
+        if (lv < p.nlev) {
+          float* dl = p.dL_lv[lv] + (size_t)row * p.lddl;
+          float* cu = p.cum_lv[lv] + (size_t)row * p.lddl;
+#pragma unroll
+          for (int k = 0; k < kBceMaxIt; ++k) {
+            const int c = lane + 32 * k;
+            if (c < p.ncols) {
+              const float xx = xv[lv][k], pw = cpw[k];
+              const float e = __expf(-fabsf(xx));
+              const float lw = 1.f + (pw - 1.f) * yv[k];
+              const float sp = __logf(1.f + e) + fmaxf(-xx, 0.f);
+              acc[k] += rs * ((1.f - yv[k]) * xx + lw * sp);
+              const float inv = __fdividef(1.f, 1.f + e);
+              const float sg = xx >= 0.f ? inv : e * inv;
+              const float gr = (sg * (pw * yv[k] + 1.f - yv[k]) - pw * yv[k]) * rs * cscale[k];
+              run[k] += gr;
+              dl[c] = gr;
+              cu[c] = run[k];
+            } else if (c < p.zero_cols) {
+              dl[c] = 0.f;
+              cu[c] = 0.f;
+            }
+          }
+        }
+      }
+      continue;
+    }
     if (fast) {
 #pragma unroll
       for (int k = 0; k < kBceMaxIt; ++k) {
@@ -421,7 +470,14 @@ int launch_bce(const BceDev& p, int cap_rows, cudaStream_t stream) {
   const long cap = (long)num_sms() * 8;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
-  const int nlev = p.nlev > 0 ? p.nlev : 1;
+  int nlev = p.nlev > 0 ? p.nlev : 1;
+  if (p.nlev > 0 && p.cum_lv[0] != nullptr) {
+    if (p.zero_cols > 32 * kBceMaxIt || p.dL_lv[0] == nullptr) {
+      set_error("bce: the level-walking mode needs <= %d columns and gradient buffers", 32 * kBceMaxIt);
+      return TCN_ERR_INVALID_ARG;
+    }
+    nlev = 1;
+  }
   if (nlev > 1 && b > cap / nlev) b = cap / nlev;
   bce_rows_kernel<<<dim3((int)b, nlev), 256, 0, stream>>>(p);
   return check_launch("bce_rows_kernel");

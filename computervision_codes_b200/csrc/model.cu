@@ -55,6 +55,17 @@ struct tcn_model {
   long prep_total_f4 = 0;
   // activations
   std::vector<float*> act, H;
+  // FPN level stacks: [f0 | f1 | f2] and [p1 | p2 | p3 | p4 = f3] are contiguous (max_rows each), as are the four logit /
+  // dLogits / cumulative-dLogits / level-gradient maps, so that the heads, their weight and input gradients and the
+  // lateral weight gradient are ONE launch each over a 4x (3x) block table (meta4, desc4 / desc3)
+  float* cum[4] = {nullptr, nullptr, nullptr, nullptr};
+  BatchDesc *desc4 = nullptr, *desc3 = nullptr;
+  BlkMeta* meta4 = nullptr;
+  bool stack_levels = true;   // TCN_NO_STACK=1: one launch per level (A/B)
+  // slabs of the deterministic weight-gradient reduction of the heads, the lateral and the projection (wgrad_tc.cu)
+  float* slab[3] = {nullptr, nullptr, nullptr};
+  int slab_cap[3] = {0, 0, 0};
+  bool det_wgrad = true;      // TCN_WGRAD_ATOMIC=1: fp32 atomics instead (A/B)
   float* P[3] = {nullptr, nullptr, nullptr};
   float* logits[4] = {nullptr, nullptr, nullptr, nullptr};
   float* dL[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -171,16 +182,19 @@ WgradDev base_wgrad(const tcn_model* m) {
   return p;
 }
 
-int gemm(tcn_model* m, TapGemmDev& p, int c_in, int n_out, cudaStream_t st) {
+// levels > 1: X / Y / R are level stacks (levels * max_rows rows) and p.meta / p.dyn the stacked block table
+int gemm(tcn_model* m, TapGemmDev& p, int c_in, int n_out, cudaStream_t st, int levels = 1) {
+  const int cap_blk = levels * m->max_blk;
+  const long map_rows = (long)levels * m->cfg.max_rows;
   if (m->use_tc && !p.x_unpadded) {
     const long key = reinterpret_cast<const float*>(p.Wf) - m->wf;
     auto it = m->tcw.find(key);
     if (it != m->tcw.end()) {
-      const auto xkey = std::make_pair(p.X, p.ldx);
+      const auto xkey = std::make_pair(p.X, p.ldx + (levels << 20));
       auto xm = m->xmaps.find(xkey);
       if (xm == m->xmaps.end()) {
         CUtensorMap map;
-        TCN_CHECK(make_tensor_map_2d(&map, p.X, m->cfg.max_rows, p.ldx, p.ldx, TC_BM));
+        TCN_CHECK(make_tensor_map_2d(&map, p.X, map_rows, p.ldx, p.ldx, TC_BM));
         xm = m->xmaps.emplace(xkey, map).first;
       }
       GemmTcDev q;
@@ -199,16 +213,16 @@ int gemm(tcn_model* m, TapGemmDev& p, int c_in, int n_out, cudaStream_t st) {
         auto x32 = m->xmaps32.find(xkey);
         if (x32 == m->xmaps32.end()) {
           CUtensorMap map;
-          TCN_CHECK(make_tensor_map_2d(&map, p.X, m->cfg.max_rows, p.ldx, p.ldx, 32));
+          TCN_CHECK(make_tensor_map_2d(&map, p.X, map_rows, p.ldx, p.ldx, 32));
           x32 = m->xmaps32.emplace(xkey, map).first;
         }
         mx32 = &x32->second;
       }
-      return launch_gemm_tc(xm->second, it->second.mh, it->second.ml, q, m->max_blk, st, mx32);
+      return launch_gemm_tc(xm->second, it->second.mh, it->second.ml, q, cap_blk, st, mx32);
     }
   }
   p.c_in = c_in; p.kpt = rup(c_in, 8); p.n_out = n_out; p.NT8 = (n_out + 7) / 8;
-  return launch_tapgemm(p, 0, st);
+  return launch_tapgemm(p, levels > 1 ? cap_blk : 0, st);
 }
 
 int get_wgmap(tcn_model* m, const float* ptr, long rows, int cols, const CUtensorMap** out) {
@@ -242,15 +256,31 @@ WgradTcDev to_tc(const WgradDev& w) {
 }
 
 // weight-gradient dispatcher: tcgen05 kernel when available, mma.sync kernel otherwise
-int wgrad(tcn_model* m, WgradDev& w, long x_rows, cudaStream_t st) {
+// slab_id >= 0: deterministic reduction through m->slab[slab_id] (pre-zeroed here, added to dW / db in split order)
+int wgrad(tcn_model* m, WgradDev& w, long x_rows, cudaStream_t st, int levels = 1, int slab_id = -1) {
+  const long map_rows = (long)levels * m->cfg.max_rows;
   if (wgrad_tc_ok(m, w)) {
     const CUtensorMap *mx, *mg;
-    TCN_CHECK(get_wgmap(m, w.X, w.x_unpadded ? x_rows : m->cfg.max_rows, w.ldx, &mx));
-    TCN_CHECK(get_wgmap(m, w.G, m->cfg.max_rows, w.ldg, &mg));
+    TCN_CHECK(get_wgmap(m, w.X, w.x_unpadded ? x_rows : map_rows, w.ldx, &mx));
+    TCN_CHECK(get_wgmap(m, w.G, map_rows, w.ldg, &mg));
     WgradTcDev q = to_tc(w);
-    return launch_wgrad_tc(*mx, *mg, q, m->max_blk, st);
+    if (slab_id >= 0 && m->det_wgrad) {
+      const long nw = (long)w.n_out * w.c_in * w.ntaps;
+      q.slab = m->slab[slab_id]; q.slab_stride = nw + w.n_out; q.slab_splits = m->slab_cap[slab_id];
+      if (cudaMemsetAsync(q.slab, 0, (size_t)q.slab_splits * q.slab_stride * 4, st) != cudaSuccess) {
+        set_error("tcn_model backward: slab memset failed");
+        cudaGetLastError();
+        return TCN_ERR_CUDA;
+      }
+      TCN_CHECK(launch_wgrad_tc(*mx, *mg, q, levels * m->max_blk, st));
+      // dW and db are separate tensors of the flat gradient buffer: two short reductions
+      TCN_CHECK(launch_slab_reduce(w.dW, q.slab, nw, q.row_splits, q.slab_stride, st));
+      if (w.db != nullptr) TCN_CHECK(launch_slab_reduce(w.db, q.slab + nw, w.n_out, q.row_splits, q.slab_stride, st));
+      return TCN_OK;
+    }
+    return launch_wgrad_tc(*mx, *mg, q, levels * m->max_blk, st);
   }
-  return launch_wgrad(w, m->max_blk, st);
+  return launch_wgrad(w, levels * m->max_blk, st);
 }
 
 // the two weight gradients of one residual layer in a single launch
@@ -482,31 +512,49 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
   const size_t o_sjobs = carve(sjobs.size() * sizeof(SplitJob));
   const size_t o_tcwhi = carve((size_t)m->tc_wfloats * 4), o_tcwlo = carve((size_t)m->tc_wfloats * 4);
   std::vector<size_t> o_act(m->L + 1), o_H(m->L);
-  for (int i = 0; i <= m->L; ++i) o_act[i] = carve((size_t)rows * C * 4);
+  // stage outputs f0..f2 contiguous, then p1..p3 and f3 contiguous (rows * C * 4 is a multiple of 256: carve() adds no gap)
+  const size_t o_fstack = carve((size_t)3 * rows * C * 4);
+  const size_t o_pstack = carve((size_t)4 * rows * C * 4);
+  for (int i = 0; i <= m->L; ++i) {
+    int stage_out = -1;
+    for (int st = 0; st < 4; ++st)
+      if (i == m->stage_first[st + 1]) stage_out = st;
+    if (stage_out >= 0 && stage_out < 3) o_act[i] = o_fstack + (size_t)stage_out * rows * C * 4;
+    else if (stage_out == 3) o_act[i] = o_pstack + (size_t)3 * rows * C * 4;
+    else o_act[i] = carve((size_t)rows * C * 4);
+  }
   for (int i = 0; i < m->L; ++i) o_H[i] = carve((size_t)rows * C * 4);
   std::vector<size_t> o_masks(m->L);
   for (int i = 0; i < m->L; ++i) o_masks[i] = carve((size_t)rows * 16);
-  size_t o_P[3], o_log[4], o_dL[4], o_Gp[4];
+  size_t o_P[3], o_log[4], o_dL[4], o_Gp[4], o_cum[4];
   std::vector<size_t> o_gpool(m->L + 4), o_gus(m->L);
-  for (int i = 0; i < 3; ++i) o_P[i] = carve((size_t)rows * C * 4);
+  for (int i = 0; i < 3; ++i) o_P[i] = o_pstack + (size_t)i * rows * C * 4;
   for (int i = 0; i < 4; ++i) o_log[i] = carve((size_t)rows * m->LDH * 4);
   for (int i = 0; i < 4; ++i) o_dL[i] = carve((size_t)rows * m->LDH * 4);
   for (int i = 0; i < 4; ++i) o_Gp[i] = carve((size_t)rows * C * 4);
+  for (int i = 0; i < 4; ++i) o_cum[i] = carve((size_t)rows * m->LDH * 4);
   for (auto& o : o_gpool) o = carve((size_t)rows * C * 4);
   for (auto& o : o_gus) o = carve((size_t)rows * C * 4);
+  m->slab_cap[0] = wgrad_tc_splits_cap(NH, C, 1);
+  m->slab_cap[1] = wgrad_tc_splits_cap(C, C, 1);
+  m->slab_cap[2] = wgrad_tc_splits_cap(C, D, 1);
+  const size_t o_slab0 = carve((size_t)m->slab_cap[0] * ((size_t)NH * C + NH) * 4);
+  const size_t o_slab1 = carve((size_t)m->slab_cap[1] * ((size_t)C * C + C) * 4);
+  const size_t o_slab2 = carve((size_t)m->slab_cap[2] * ((size_t)C * D + C) * 4);
   wgrad_layers_plan(m->max_blk, &m->wl_lg, &m->wl_splits);
   const size_t o_wlpart = carve((size_t)m->L * m->wl_splits * WL_PART_FLOATS * 4);
   const size_t o_cs = carve((size_t)cfg->max_seqs * D * 4);
   m->proj_tc = tcn_gemm_tc_supported(D, C) != 0;
   const size_t proj_wf = (size_t)tcn_split_weight_floats(C, D, 1, 0);
   const size_t o_whi = carve(proj_wf * 4), o_wlo = carve(proj_wf * 4);
-  const size_t o_desc = carve(sizeof(BatchDesc) + (size_t)m->max_blk * sizeof(BlkMeta));
+  // [desc | desc4 | desc3 | meta (max_blk) | meta4 (4 max_blk)]: one upload per batch
+  const size_t o_desc = carve(3 * sizeof(BatchDesc) + (size_t)5 * m->max_blk * sizeof(BlkMeta));
   const size_t o_cu = carve((size_t)m->LDH * 4), o_cscale = carve((size_t)m->LDH * 4), o_pw = carve((size_t)m->LDH * 4);
   const size_t o_ch = carve((size_t)m->LDH * 4), o_loss = carve(64);
   m->ws_bytes = bytes;
   cudaError_t e = cudaMalloc(&m->ws, bytes);
   if (e == cudaSuccess) e = cudaMemset(m->ws, 0, bytes);
-  m->slot_bytes = sizeof(BatchDesc) + (size_t)m->max_blk * sizeof(BlkMeta);
+  m->slot_bytes = 3 * sizeof(BatchDesc) + (size_t)5 * m->max_blk * sizeof(BlkMeta);
   if (e == cudaSuccess) e = cudaMallocHost(&m->desc_host, m->slot_bytes * tcn_model::kSlots);
   for (int i = 0; i < tcn_model::kSlots && e == cudaSuccess; ++i)
     e = cudaEventCreateWithFlags(&m->slot_done[i], cudaEventDisableTiming);
@@ -530,10 +578,16 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
     m->logits[i] = reinterpret_cast<float*>(m->ws + o_log[i]);
     m->dL[i] = reinterpret_cast<float*>(m->ws + o_dL[i]);
     m->Gp[i] = reinterpret_cast<float*>(m->ws + o_Gp[i]);
+    m->cum[i] = reinterpret_cast<float*>(m->ws + o_cum[i]);
   }
+  m->stack_levels = std::getenv("TCN_NO_STACK") == nullptr;
   for (auto o : o_gpool) m->gpool.push_back(reinterpret_cast<float*>(m->ws + o));
   for (auto o : o_gus) m->gus.push_back(reinterpret_cast<float*>(m->ws + o));
   m->wl_part = reinterpret_cast<float*>(m->ws + o_wlpart);
+  m->slab[0] = reinterpret_cast<float*>(m->ws + o_slab0);
+  m->slab[1] = reinterpret_cast<float*>(m->ws + o_slab1);
+  m->slab[2] = reinterpret_cast<float*>(m->ws + o_slab2);
+  m->det_wgrad = std::getenv("TCN_WGRAD_ATOMIC") == nullptr;
   m->use_wl = std::getenv("TCN_WGRAD_PAIR") == nullptr;
   m->overlap_wgrad = std::getenv("TCN_NO_WGRAD_STREAM") == nullptr;
   if (cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess) m->overlap_wgrad = false;
@@ -551,7 +605,10 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
       m->proj_tc = false;  // driver without tensor-map support: stay on the mma.sync path
   }
   m->desc = reinterpret_cast<BatchDesc*>(m->ws + o_desc);
-  m->meta = reinterpret_cast<BlkMeta*>(m->ws + o_desc + sizeof(BatchDesc));
+  m->desc4 = m->desc + 1;
+  m->desc3 = m->desc + 2;
+  m->meta = reinterpret_cast<BlkMeta*>(m->ws + o_desc + 3 * sizeof(BatchDesc));
+  m->meta4 = m->meta + m->max_blk;
   m->col_unit = reinterpret_cast<float*>(m->ws + o_cu);
   m->col_scale = reinterpret_cast<float*>(m->ws + o_cscale);
   m->pos_w = reinterpret_cast<float*>(m->ws + o_pw);
@@ -678,9 +735,23 @@ extern "C" int tcn_model_set_batch(tcn_model* m, const int* meta_host, int nblk,
   cudaEventSynchronize(m->slot_done[sl]);
   BatchDesc* d = reinterpret_cast<BatchDesc*>(m->desc_host + (size_t)sl * m->slot_bytes);
   d->nblk = nblk; d->rows = rows; d->num_seqs = num_seqs; d->frames = frames; d->seed = seed;
-  memcpy(reinterpret_cast<char*>(d) + sizeof(BatchDesc), meta_host, (size_t)nblk * sizeof(BlkMeta));
-  cudaError_t e = cudaMemcpyAsync(m->desc, d, sizeof(BatchDesc) + (size_t)nblk * sizeof(BlkMeta),
-                                  cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  // level-stacked views: level l occupies rows [l * max_rows, (l + 1) * max_rows) of a stack and blocks
+  // [l * max_blk, l * max_blk + nblk) of meta4; the blocks in between are empty (hi = 0: every kernel skips them)
+  const int MB = m->max_blk, MR = m->cfg.max_rows;
+  d[1] = d[0]; d[1].nblk = 3 * MB + nblk; d[1].rows = 3 * MR + rows;
+  d[2] = d[0]; d[2].nblk = 2 * MB + nblk; d[2].rows = 2 * MR + rows;
+  BlkMeta* mh = reinterpret_cast<BlkMeta*>(d + 3);
+  memcpy(mh, meta_host, (size_t)nblk * sizeof(BlkMeta));
+  if (nblk < MB) memset(mh + nblk, 0, (size_t)(MB - nblk) * sizeof(BlkMeta));
+  BlkMeta* m4 = mh + MB;
+  memset(m4, 0, (size_t)4 * MB * sizeof(BlkMeta));
+  for (int lv = 0; lv < 4; ++lv)
+    for (int b = 0; b < nblk; ++b) {
+      BlkMeta e4 = mh[b];
+      e4.lo += lv * MR; e4.hi += lv * MR; e4.in_delta -= lv * MR;
+      m4[(size_t)lv * MB + b] = e4;
+    }
+  cudaError_t e = cudaMemcpyAsync(m->desc, d, m->slot_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
   if (e == cudaSuccess) e = cudaEventRecord(m->slot_done[sl], (cudaStream_t)stream);
   if (e != cudaSuccess) {
     set_error("tcn_model_set_batch: upload failed: %s", cudaGetErrorString(e));
@@ -798,6 +869,14 @@ static int model_forward(tcn_model* m, const float* x, long x_rows, int training
     top = m->P[lv];
   }
   // 4. heads on the four levels (network.py:63-67), all 131 classes in one GEMM per level
+  if (m->stack_levels) {   // [p1 | p2 | p3 | p4] -> [logits of the four levels]: one launch over the 4x block table
+    TapGemmDev p = base_tapgemm(m);
+    p.meta = m->meta4; p.nblk = 4 * m->max_blk; p.dyn = m->desc4;
+    p.X = m->P[0]; p.ldx = C; p.Wf = m->wf_(m->wf_head); p.bias = m->p_(m->off_head_b);
+    p.Y = m->logits[0]; p.ldy = m->LDH;
+    TCN_CHECK(gemm(m, p, C, m->NH, st, 4));
+    return TCN_OK;
+  }
   for (int lv = 0; lv < 4; ++lv) {
     TapGemmDev p = base_tapgemm(m);
     p.X = lv < 3 ? m->P[lv] : f[3]; p.ldx = C; p.Wf = m->wf_(m->wf_head); p.bias = m->p_(m->off_head_b);
@@ -811,7 +890,7 @@ static int model_forward(tcn_model* m, const float* x, long x_rows, int training
 // gl[lv]: gradient w.r.t. the logits of level lv (rows, LDH; pad columns zero) or nullptr;
 // gf[lv]: extra gradient w.r.t. feature level lv (rows, C) or nullptr.
 static int model_backward(tcn_model* m, const float* x, long x_rows, const float* const* gl,
-                          const float* const* gf, cudaStream_t st) {
+                          const float* const* gf, cudaStream_t st, bool cum_ready = false) {
   const int C = m->C, D = m->D, NH = m->NH, LDH = m->LDH;
   TCN_REQUIRE(m->grads != nullptr, "tcn_model backward: no gradient buffer bound");
   const float pl = m->fwd_training ? m->layer_drop_p : 0.f;
@@ -848,6 +927,32 @@ static int model_backward(tcn_model* m, const float* x, long x_rows, const float
   }
   TCN_CHECK(hand_over());  // gradient buffer zeroed, logits gradients ready
   // heads: weight grads (side stream), then the gradient of each FPN level, accumulated top-down (p_l feeds p_{l-1})
+  // stacked: the logit gradients are the executor's own dL stack and the loss kernel left their running sums in cum
+  const bool stacked = m->stack_levels && cum_ready && gl[0] == m->dL[0] && gl[1] == m->dL[1] && gl[2] == m->dL[2] &&
+                       gl[3] == m->dL[3];
+  if (stacked) {
+    {   // head weights: sum over the four levels of dL_l^T p_l
+      WgradDev w = base_wgrad(m);
+      w.meta = m->meta4; w.nblk = 4 * m->max_blk; w.dyn = m->desc4;
+      w.G = m->dL[0]; w.ldg = LDH; w.g_cols = LDH; w.X = m->P[0]; w.ldx = C;
+      w.n_out = NH; w.c_in = C; w.dW = m->g_(m->off_head_w); w.db = m->g_(m->off_head_b);
+      TCN_CHECK(wgrad(m, w, x_rows, ws, 4, 0));
+    }
+    {   // gradient of every level: (dL_0 + ... + dL_l) W_head -- the heads share their weights (network.py:63-67)
+      TapGemmDev p = base_tapgemm(m);
+      p.meta = m->meta4; p.nblk = 4 * m->max_blk; p.dyn = m->desc4;
+      p.X = m->cum[0]; p.ldx = LDH; p.Wf = m->wf_(m->wf_headT); p.Y = m->Gp[0]; p.ldy = C;
+      TCN_CHECK(gemm(m, p, LDH, C, st, 4));
+    }
+    TCN_CHECK(hand_over());  // Gp[0..3] ready
+    {   // lateral weights: sum over l = 0..2 of Gp_l^T f_l  (p_l = p_{l+1} + lat(f_l))
+      WgradDev w = base_wgrad(m);
+      w.meta = m->meta4; w.nblk = 3 * m->max_blk; w.dyn = m->desc3;
+      w.G = m->Gp[0]; w.ldg = C; w.g_cols = C; w.X = f[0]; w.ldx = C;
+      w.n_out = C; w.c_in = C; w.dW = m->g_(m->off_lat_w); w.db = m->g_(m->off_lat_b);
+      TCN_CHECK(wgrad(m, w, x_rows, ws, 3, 1));
+    }
+  } else {
   const float* prev = nullptr;
   for (int lv = 0; lv < 4; ++lv) {
     WgradDev w = base_wgrad(m);
@@ -867,6 +972,7 @@ static int model_backward(tcn_model* m, const float* x, long x_rows, const float
     w.G = m->Gp[lv]; w.ldg = C; w.g_cols = C; w.X = f[lv]; w.ldx = C;
     w.n_out = C; w.c_in = C; w.dW = m->g_(m->off_lat_w); w.db = m->g_(m->off_lat_b);
     TCN_CHECK(wgrad(m, w, x_rows, ws));
+  }
   }
   // stages, last to first
   const int tr = m->fwd_training ? 1 : 0;
@@ -978,7 +1084,7 @@ static int model_backward(tcn_model* m, const float* x, long x_rows, const float
     if (m->fwd_training && m->input_mask_p > 0.f) {
       w.x_drop_thresh = drop_thresh(m->input_mask_p); w.x_drop_scale = 1.f; w.x_drop_stream = kStreamMask;
     }
-    TCN_CHECK(wgrad(m, w, x_rows, st));
+    TCN_CHECK(wgrad(m, w, x_rows, st, 1, 2));
   }
   if (ws != st) {  // join: the caller's stream owns every gradient again
     cudaEvent_t ev = m->evs[nev++];
@@ -1040,11 +1146,14 @@ extern "C" int tcn_model_train_step(tcn_model* m, const float* x, long long x_ro
     b.col_head = m->col_head; b.row_scale_const = 1.f; b.loss = m->loss8; b.lddl = m->LDH;
     b.grad_scale = 1.f;
     b.nlev = 4;
-    for (int lv = 0; lv < 4; ++lv) { b.logits_lv[lv] = m->logits[lv]; b.dL_lv[lv] = m->dL[lv]; }
+    for (int lv = 0; lv < 4; ++lv) {
+      b.logits_lv[lv] = m->logits[lv]; b.dL_lv[lv] = m->dL[lv];
+      b.cum_lv[lv] = m->stack_levels ? m->cum[lv] : nullptr;
+    }
     TCN_CHECK(launch_bce(b, m->cfg.max_rows, st));
   }
   finish_loss_kernel<<<1, 32, 0, st>>>(m->loss8, loss_out, m->head_w[0], m->head_w[1], m->head_w[2], m->head_w[3]);
   TCN_CHECK(check_launch("finish_loss_kernel"));
   const float* gl[4] = {m->dL[0], m->dL[1], m->dL[2], m->dL[3]};
-  return model_backward(m, x, x_rows, gl, nullptr, st);
+  return model_backward(m, x, x_rows, gl, nullptr, st, m->stack_levels);
 }

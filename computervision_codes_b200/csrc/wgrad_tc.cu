@@ -255,7 +255,10 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
         asm volatile("bar.sync 1, 256;\n" ::: "memory");  // the eight split warps only
         for (int i = ct; i < NCOL; i += WG_SPLIT) {
           const int n = ntile * NCOL + i;
-          if (n < p.n_out) atomicAdd(p.db + n, bias_red[i]);
+          if (n < p.n_out) {
+            if (p.slab != nullptr) p.slab[(size_t)split * p.slab_stride + (size_t)p.n_out * p.c_in * p.ntaps + n] = bias_red[i];
+            else atomicAdd(p.db + n, bias_red[i]);
+          }
         }
       }
       // ===================== epilogue: add the partial into dW =====================
@@ -276,7 +279,11 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = ntile * NCOL + c0 + j;
-            if (n < p.n_out) atomicAdd(p.dW + ((size_t)n * p.c_in + c) * p.ntaps + a_tap[q], v[j]);
+            if (n < p.n_out) {
+              const size_t idx = ((size_t)n * p.c_in + c) * p.ntaps + a_tap[q];
+              if (p.slab != nullptr) p.slab[(size_t)split * p.slab_stride + idx] = v[j];
+              else atomicAdd(p.dW + idx, v[j]);
+            }
           }
         }
       }
@@ -335,9 +342,44 @@ static int launch_wgrad_tc_n(const CUtensorMap& mx, const CUtensorMap& mg, Wgrad
   }
   if (rs < 1) rs = 1;
   if (rs > nb) rs = nb;
+  if (p.slab != nullptr && rs > p.slab_splits) rs = p.slab_splits;
   p.row_splits = rs;
   launch_kernel(wgrad_tc_kernel<NGA>, dim3(rs, mt, nt), dim3(WG_THREADS), WgSmem<NGA>::kBytes, stream, true, mx, mg, p);
   return check_launch("wgrad_tc_kernel");
+}
+
+int wgrad_tc_splits_cap(int n_out, int c_in, int ntaps) {
+  const int cbn = (c_in + 31) / 32;
+  const int mt = (ntaps * cbn + 3) / 4;
+  int best = 1;
+  for (int nga : {2, 4, 8}) {   // whichever tile width launch_wgrad_tc picks
+    const int nt = (n_out + nga * 32 - 1) / (nga * 32);
+    const int rs = num_sms() / (mt * nt);
+    if (rs > best) best = rs;
+  }
+  return best > 6 ? best : 6;
+}
+
+constexpr int SR_GROUPS = 8;
+__global__ void __launch_bounds__(256)
+slab_reduce_kernel(float* __restrict__ out, const float* __restrict__ slab, long n, int nsplit, long stride) {
+  __shared__ float red[SR_GROUPS][32];
+  pdl_wait();
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const long i = (long)blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  if (i < n)
+    for (int s = g; s < nsplit; s += SR_GROUPS) acc += __ldg(slab + (size_t)s * stride + i);
+  red[g][lane] = acc;
+  __syncthreads();
+  if (g != 0 || i >= n) return;
+#pragma unroll
+  for (int k = 1; k < SR_GROUPS; ++k) acc += red[k][lane];
+  out[i] += acc;
+}
+int launch_slab_reduce(float* out, const float* slab, long n, int nsplit, long stride, cudaStream_t stream) {
+  launch_kernel(slab_reduce_kernel, dim3((unsigned)((n + 31) / 32)), dim3(256), 0, stream, true, out, slab, n, nsplit, stride);
+  return check_launch("slab_reduce_kernel");
 }
 
 int launch_wgrad_tc(const CUtensorMap& mx, const CUtensorMap& mg, WgradTcDev& p, int cap_nblk, cudaStream_t stream) {

@@ -273,9 +273,12 @@ int wgrad(tcn_model* m, WgradDev& w, long x_rows, cudaStream_t st, int levels = 
         return TCN_ERR_CUDA;
       }
       TCN_CHECK(launch_wgrad_tc(*mx, *mg, q, levels * m->max_blk, st));
-      // dW and db are separate tensors of the flat gradient buffer: two short reductions
-      TCN_CHECK(launch_slab_reduce(w.dW, q.slab, nw, q.row_splits, q.slab_stride, st));
-      if (w.db != nullptr) TCN_CHECK(launch_slab_reduce(w.db, q.slab + nw, w.n_out, q.row_splits, q.slab_stride, st));
+      if (w.db == w.dW + nw) {   // the bias follows its weight in the flat gradient buffer: one reduction for both
+        TCN_CHECK(launch_slab_reduce(w.dW, q.slab, nw + w.n_out, q.row_splits, q.slab_stride, st));
+      } else {
+        TCN_CHECK(launch_slab_reduce(w.dW, q.slab, nw, q.row_splits, q.slab_stride, st));
+        if (w.db != nullptr) TCN_CHECK(launch_slab_reduce(w.db, q.slab + nw, w.n_out, q.row_splits, q.slab_stride, st));
+      }
       return TCN_OK;
     }
     return launch_wgrad_tc(*mx, *mg, q, levels * m->max_blk, st);
@@ -542,6 +545,15 @@ extern "C" int tcn_model_create(const tcn_model_config* cfg, tcn_model** out) {
   const size_t o_slab1 = carve((size_t)m->slab_cap[1] * ((size_t)C * C + C) * 4);
   const size_t o_slab2 = carve((size_t)m->slab_cap[2] * ((size_t)C * D + C) * 4);
   wgrad_layers_plan(m->max_blk, &m->wl_lg, &m->wl_splits);
+  if (const char* e = std::getenv("TCN_WL_LG")) {   // experiments: layers per weight-gradient launch
+    const int lg = atoi(e);
+    if (lg >= 1 && lg <= 16) {
+      m->wl_lg = lg;
+      m->wl_splits = num_sms() / lg;
+      if (m->wl_splits > m->max_blk * 8) m->wl_splits = m->max_blk * 8;
+      if (m->wl_splits < 1) m->wl_splits = 1;
+    }
+  }
   const size_t o_wlpart = carve((size_t)m->L * m->wl_splits * WL_PART_FLOATS * 4);
   const size_t o_cs = carve((size_t)cfg->max_seqs * D * 4);
   m->proj_tc = tcn_gemm_tc_supported(D, C) != 0;

@@ -347,40 +347,45 @@ wgrad_layer_kernel(const __grid_constant__ WgLayerDev d, const WgLayersLaunch q)
   wgrad_layer_body(&d, q, blockIdx.x);
 }
 
-// dW / db += sum over the slabs.  Block = 32 float4 columns x 8 slab groups: group g adds slabs g, g + 8, ... in order,
-// then the eight group sums are added in group order -- a fixed tree for a given split count => bit-identical results.
-constexpr int WL_RED_GROUPS = 8;
+// dW / db += sum over the slabs in slab order (fixed summation tree for a given split count => bit-identical results).
+// GROUPS = 8 (one layer, up to 148 slabs, few blocks): a block is 32 float4 columns x 8 slab groups, group g adds slabs
+// g, g + 8, ... and the group sums are added in group order.  GROUPS = 1 (all layers of a model in one launch, plenty of
+// blocks): a block reads 4 KB of every slab in turn, eight loads in flight.
+template <int GROUPS>
 __device__ __forceinline__ void wl_reduce_body(const WgLayerOut& o, int splits) {
-  __shared__ float4 red[WL_RED_GROUPS][32];
+  __shared__ float4 red[GROUPS > 1 ? GROUPS : 1][32];
   pdl_wait();   // launched with programmatic serialization: the slabs are final only when the producer grid has completed
-  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int e4 = blockIdx.x * 32 + lane;
+  constexpr int COLS = 256 / GROUPS;
+  const int lane = threadIdx.x % COLS, g = threadIdx.x / COLS;
+  const int e4 = blockIdx.x * COLS + lane;
   constexpr size_t kStride = WL_PART_FLOATS / 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (e4 < WL_PART_FLOATS / 4) {
     const float4* p = reinterpret_cast<const float4*>(o.part) + e4;
     int s = g;
-    for (; s + 3 * WL_RED_GROUPS < splits; s += 4 * WL_RED_GROUPS) {   // four loads in flight, additions in slab order
-      const float4 a = __ldg(p + (size_t)s * kStride), b = __ldg(p + (size_t)(s + WL_RED_GROUPS) * kStride);
-      const float4 c = __ldg(p + (size_t)(s + 2 * WL_RED_GROUPS) * kStride), e = __ldg(p + (size_t)(s + 3 * WL_RED_GROUPS) * kStride);
-      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
-      acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
-      acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
-      acc.x += e.x; acc.y += e.y; acc.z += e.z; acc.w += e.w;
+    for (; s + 7 * GROUPS < splits; s += 8 * GROUPS) {   // eight loads in flight, additions in slab order
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (size_t)(s + u * GROUPS) * kStride);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
     }
-    for (; s < splits; s += WL_RED_GROUPS) {
+    for (; s < splits; s += GROUPS) {
       const float4 a = __ldg(p + (size_t)s * kStride);
       acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
     }
   }
-  red[g][lane] = acc;
-  __syncthreads();
-  if (g != 0 || e4 >= WL_PART_FLOATS / 4) return;
+  if (GROUPS > 1) {
+    red[g][lane] = acc;
+    __syncthreads();
+    if (g != 0) return;
 #pragma unroll
-  for (int k = 1; k < WL_RED_GROUPS; ++k) {
-    const float4 a = red[k][lane];
-    acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    for (int k = 1; k < GROUPS; ++k) {
+      const float4 a = red[k][lane];
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
   }
+  if (e4 >= WL_PART_FLOATS / 4) return;
   const float av[4] = {acc.x, acc.y, acc.z, acc.w};
   const int e0 = e4 * 4;
 #pragma unroll
@@ -399,11 +404,11 @@ __device__ __forceinline__ void wl_reduce_body(const WgLayerOut& o, int splits) 
 }
 __global__ void __launch_bounds__(256)
 wgrad_layers_reduce_kernel(const WgLayerOut* __restrict__ outs, int splits) {
-  wl_reduce_body(outs[blockIdx.y], splits);
+  wl_reduce_body<1>(outs[blockIdx.y], splits);
 }
 __global__ void __launch_bounds__(256)
 wgrad_layer_reduce_kernel(const WgLayerOut o, int splits) {
-  wl_reduce_body(o, splits);
+  wl_reduce_body<8>(o, splits);
 }
 
 static int wl_set_attr() {
@@ -421,10 +426,11 @@ static int wl_set_attr() {
 }
 
 void wgrad_layers_plan(int cap_nblk, int* layers_per_launch, int* splits) {
-  // aim at ~32 slots of 16 frames per CTA (the fixed cost of a CTA -- prologue, partial store -- is a few microseconds)
+  // aim at ~80 slots of 16 frames per CTA at capacity (measured on the bench step, 233-block capacity: 2 / 4 / 6 / 8 layers
+  // per launch -> 1.871 / 1.841 / 1.794 / 1.798 ms per step: fewer, longer CTAs amortise the prologue and the slab store)
   const int sms = num_sms();
   const long slots = (long)cap_nblk * 8;
-  long lg = (2L * sms * 32 + slots) / (2 * slots);   // round(sms * 32 / slots)
+  long lg = (2L * sms * 80 + slots) / (2 * slots);   // round(sms * 80 / slots)
   if (lg < 1) lg = 1;
   if (lg > 8) lg = 8;
   int sp = sms / (int)lg;
@@ -441,7 +447,7 @@ int launch_wgrad_layers(const WgLayerDev* descs_dev, int nlayers, const WgLayers
 }
 
 int launch_wgrad_layers_reduce(const WgLayerOut* outs_dev, int nlayers, int splits, cudaStream_t stream) {
-  const int nb = (WL_PART_FLOATS / 4 + 31) / 32;
+  const int nb = (WL_PART_FLOATS / 4 + 255) / 256;
   launch_kernel(wgrad_layers_reduce_kernel, dim3(nb, nlayers, 1), dim3(256), 0, stream, true, outs_dev, splits);
   return check_launch("wgrad_layers_reduce_kernel");
 }

@@ -243,27 +243,29 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
           ++it;
         }
       }
-      // ---- bias gradient: reduce the per-thread column sums (shared atomics), one global add per column
+      // ===================== epilogue =====================
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+      // ---- bias gradient: the per-thread column sums are added over the 32 frame positions in a fixed order through
+      // shared memory (the stages are free once the accumulator is complete) -- no shared atomics: bit-reproducible
       if (p.db != nullptr && mtile == 0) {
+        float* red = reinterpret_cast<float*>(tiles);   // [NGA][32 frame positions][32 columns]
 #pragma unroll
-        for (int a = 0; a < NGA; ++a) {
-          atomicAdd(&bias_red[a * 32 + lc * 4 + 0], bsum[a].x);
-          atomicAdd(&bias_red[a * 32 + lc * 4 + 1], bsum[a].y);
-          atomicAdd(&bias_red[a * 32 + lc * 4 + 2], bsum[a].z);
-          atomicAdd(&bias_red[a * 32 + lc * 4 + 3], bsum[a].w);
-        }
+        for (int a = 0; a < NGA; ++a)
+          *reinterpret_cast<float4*>(red + ((a * 32 + (ct >> 3)) * 32) + lc * 4) = bsum[a];
         asm volatile("bar.sync 1, 256;\n" ::: "memory");  // the eight split warps only
         for (int i = ct; i < NCOL; i += WG_SPLIT) {
+          const int a = i >> 5, col = i & 31;
+          float sacc = 0.f;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) sacc += red[(a * 32 + rr) * 32 + col];
           const int n = ntile * NCOL + i;
           if (n < p.n_out) {
-            if (p.slab != nullptr) p.slab[(size_t)split * p.slab_stride + (size_t)p.n_out * p.c_in * p.ntaps + n] = bias_red[i];
-            else atomicAdd(p.db + n, bias_red[i]);
+            if (p.slab != nullptr) p.slab[(size_t)split * p.slab_stride + (size_t)p.n_out * p.c_in * p.ntaps + n] = sacc;
+            else atomicAdd(p.db + n, sacc);
           }
         }
       }
-      // ===================== epilogue: add the partial into dW =====================
-      mbar_wait(accum_bar, 0);
-      tc_fence_after();
       const int q = warp & 3;  // TMEM lane quadrant == X block of this m-tile; two warps per quadrant split the columns
       const int half = (warp - 2) >> 2;
       const int vblk = mtile * 4 + q;

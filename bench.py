@@ -86,6 +86,37 @@ def build_model(device, C, D):
     return VideoNas(model_args(), *LAYERS, C, D, HEADS[0]).to(device).train()
 
 
+def device_for_rank(local_rank, world):
+    """Rank -> GPU.  On the 8-GPU box GPUs 0-3 and 4-7 hang off two host bridges (tools/h2d_concurrent.py,
+    profiles/r2_h2d_concurrent_8gpu.json: 2 GPUs copy at 54 GB/s each, 4 GPUs of ONE bridge at 29 GB/s each), and the
+    end-to-end arm is bound by pinned host -> device copies: with fewer ranks than GPUs the ranks are spread over both
+    bridges (0, 4, 1, 5, ...) instead of filling GPUs 0..N-1."""
+    n = torch.cuda.device_count()
+    if n == 8 and 1 < world < 8 and os.environ.get("BENCH_NO_DEVICE_MAP") is None:
+        order = [0, 4, 1, 5, 2, 6, 3, 7]
+        return order[local_rank], "ranks spread over both host bridges: " + str(order[:world])
+    return local_rank, "rank r -> GPU r"
+
+
+def h2d_cap(world, bytes_per_frame):
+    """Ceiling of the end-to-end arm from the measured concurrent pinned-copy bandwidth of the 8-GPU box."""
+    p = os.path.join(ROOT, "profiles", "r2_h2d_concurrent_8gpu.json")
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p))["concurrent_h2d"]
+    if world == 8:
+        per = min(t["8"]["per_gpu_GBps"])      # every step ends with an all-reduce: the slowest link sets the pace
+        why = "8 ranks: GPUs 0-3 share one host bridge (23.7 GB/s each), GPUs 4-7 the other (36 GB/s each)"
+    elif world == 4 and torch.cuda.device_count() != 8:
+        per = min(t["4"]["per_gpu_GBps"])
+        why = "4 ranks on one host bridge (28.9 GB/s each)"
+    else:
+        per = t["1"]["per_gpu_GBps"][0]
+        why = "at most two ranks per host bridge: the full x16 link each (54 GB/s)"
+    return {"frames_per_s": world * per * 1e9 / bytes_per_frame, "per_gpu_GBps": per, "why": why,
+            "source": "profiles/r2_h2d_concurrent_8gpu.json (tools/h2d_concurrent.py: pinned copies of one step's inputs, all ranks at once)"}
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -353,9 +384,11 @@ def run_cfg2(a, rank, world, local_rank, C, D, tag):
         return
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (use --impl reference for the CPU arm)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    clocks = ClockSampler(local_rank)
+    dev_index, dev_map = device_for_rank(local_rank, world)
+    config["device_map"] = dev_map
+    torch.cuda.set_device(dev_index)
+    dev = torch.device("cuda", dev_index)
+    clocks = ClockSampler(dev_index)
     pg = None
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
@@ -505,7 +538,8 @@ def run_cfg2(a, rank, world, local_rank, C, D, tag):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)",
             "data": "synthetic", "config": config, "clocks": ck,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": 32,
-                    "ms_per_step": ms_e2e / (a.steps * R_e2e), "inner_repeats": R_e2e, "timed_region_s": ms_e2e * 1e-3},
+                    "ms_per_step": ms_e2e / (a.steps * R_e2e), "inner_repeats": R_e2e, "timed_region_s": ms_e2e * 1e-3,
+                    "host_link_cap": h2d_cap(world, D * 4 + 132)},
             "gpu_launches": launches, "gpu_launches_per_step": trainer.launches_per_step(), "roofline": roof}
     if eager is not None:
         line["eager_gpu_baseline"] = eager

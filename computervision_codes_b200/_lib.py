@@ -116,6 +116,7 @@ class WgradLayerArgs(C.Structure):
         ("drop_p", C.c_float), ("drop_seed", C.c_uint), ("drop_stream", C.c_uint),
         ("dw1", C.c_void_p), ("db1", C.c_void_p), ("dw2", C.c_void_p), ("db2", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong),
+        ("flags", C.c_int),
     ]
 
 

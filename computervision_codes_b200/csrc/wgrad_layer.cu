@@ -502,6 +502,7 @@ extern "C" int tcn_wgrad_layer(const tcn_wgrad_layer_args* a, tcn_stream_t strea
   }
   launch_kernel(wgrad_layer_kernel, dim3(splits, 1, 1), dim3(WL_THREADS), WL_SMEM, (cudaStream_t)stream, true, d, q);
   TCN_CHECK(check_launch("wgrad_layer_kernel"));
+  if (a->flags & 1) return TCN_OK;
   WgLayerOut o;
   o.part = d.part; o.dw1 = a->dw1; o.db1 = a->db1; o.dw2 = a->dw2; o.db2 = a->db2;
   const int nb = (WL_PART_FLOATS / 4 + 31) / 32;

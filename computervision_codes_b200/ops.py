@@ -126,7 +126,8 @@ def layer_wgrad_kernel_name() -> str:
 _wl_workspace: dict = {}
 
 
-def layer_wgrad(gu, x, gy, h, lay: SeqLayout, shifts, gw1, gb1, gw2, gb2, drop_p=0.0, seed=0, stream_id=0, masks=None):
+def layer_wgrad(gu, x, gy, h, lay: SeqLayout, shifts, gw1, gb1, gw2, gb2, drop_p=0.0, seed=0, stream_id=0, masks=None,
+                skip_reduce=False):
     """All weight / bias gradients of one 64-channel residual layer, deterministic (csrc/wgrad_layer.cu): accumulates
     gW1 (C, C, 3) / gb1 over the taps of (gu, x) and gW2 (C, C, 1) / gb2 of (gv, h), gv = keep * gy / (1 - p) with the
     keep bits taken from `masks` (the words layer_fwd_tc saved) or regenerated from (seed, stream_id)."""
@@ -146,6 +147,7 @@ def layer_wgrad(gu, x, gy, h, lay: SeqLayout, shifts, gw1, gb1, gw2, gb2, drop_p
     a.drop_p, a.drop_seed, a.drop_stream = float(drop_p), int(seed) & 0xFFFFFFFF, int(stream_id) & 0xFFFFFFFF
     a.dw1, a.db1, a.dw2, a.db2 = _lib.ptr(gw1), _lib.ptr(gb1), _lib.ptr(gw2), _lib.ptr(gb2)
     a.workspace, a.workspace_bytes = _lib.ptr(ws), ws.numel()
+    a.flags = 1 if skip_reduce else 0   # benchmarks time the main kernel alone
     _lib.check(lib.tcn_wgrad_layer(C.byref(a), _lib.stream_ptr()), "tcn_wgrad_layer")
 
 

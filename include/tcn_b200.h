@@ -155,6 +155,7 @@ typedef struct {
   float drop_p; unsigned drop_seed; unsigned drop_stream;
   float* dw1; float* db1; float* dw2; float* db2;   /* db1 / db2 may be NULL */
   void* workspace; long long workspace_bytes;
+  int flags;                                        /* bit 0: leave the slabs unreduced (timing the main kernel alone) */
 } tcn_wgrad_layer_args;
 long long tcn_wgrad_layer_workspace_bytes(int nblk);
 int tcn_wgrad_layer(const tcn_wgrad_layer_args* args, tcn_stream_t stream);

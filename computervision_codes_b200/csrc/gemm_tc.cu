@@ -385,6 +385,38 @@ __device__ __forceinline__ void split_row_to_tmem(const float4* __restrict__ til
   tmem_st32(taddr + 32, lo);
 }
 
+// The same for HALF a row (16 of the 32 columns of the k-block): two threads per frame, twice the split warps.  `cs`: the
+// Dropout2d scale of this tile's sequence, staged in shared memory by the caller (nullptr: none).
+__device__ __forceinline__ void split_half_row_to_tmem(const float4* __restrict__ tile, int r, int half, int src,
+                                                       const BlkMeta& m, int kc, const GemmTcDev& p, const float* cs,
+                                                       uint32_t in_seed, uint32_t taddr) {
+  const float4* row = tile + r * 8;
+  const bool inside = src >= m.lo && src < m.hi;
+  float hi[16], lo[16];
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    const int c = half * 4 + cc;
+    float4 v = row[c ^ (r & 7)];                   // undo the 128B swizzle: logical 16-byte chunk c
+    if (!inside) v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int col = kc * TC_BK + c * 4;
+    if (cs != nullptr && col < p.c_in) {
+      const float4 sc = *reinterpret_cast<const float4*>(cs + col);   // same address for the whole warp: one broadcast read
+      v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+    }
+    if (p.in_drop_thresh != 0u) {
+      float f[4];
+      drop_factor4(in_seed, p.in_drop_stream, p.in_drop_thresh, p.in_drop_scale, src, col, f);
+      v.x *= f[0]; v.y *= f[1]; v.z *= f[2]; v.w *= f[3];
+    }
+    hi[4 * cc + 0] = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); lo[4 * cc + 0] = v.x - hi[4 * cc + 0];
+    hi[4 * cc + 1] = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); lo[4 * cc + 1] = v.y - hi[4 * cc + 1];
+    hi[4 * cc + 2] = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); lo[4 * cc + 2] = v.z - hi[4 * cc + 2];
+    hi[4 * cc + 3] = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); lo[4 * cc + 3] = v.w - hi[4 * cc + 3];
+  }
+  tmem_st16(taddr + half * 16, hi);
+  tmem_st16(taddr + 32 + half * 16, lo);
+}
+
 // Streaming kernel (long contractions: the stage-input projection, K = D): one (frame tile, 64-column tile) per CTA.
 // The raw X tile and the pre-split weight tiles of a k-block travel through a 6-deep TMA ring (32 KB per stage: the
 // ring only holds RAW activations, so 96 KB of X are in flight per SM -- the projection is bound by HBM latency x
@@ -396,10 +428,11 @@ struct TcSmem {
   static constexpr int kA = TC_BM * TC_BK * 4;  // 16384: raw X tile
   static constexpr int kB = BN * TC_BK * 4;     // one weight half
   static constexpr int kStage = kA + 2 * kB;
-  static constexpr int kBytes = kStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kScale = 16384;          // Dropout2d scale of the tile's sequence (up to 4096 input channels)
+  static constexpr int kBytes = kStages * kStage + kScale + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-constexpr int TS_THREADS = 320;   // TMA, MMA, 4 x operand split (+ epilogue), 4 x epilogue
+constexpr int TS_THREADS = 320;   // TMA, MMA, 8 x operand split (two threads per frame) + epilogue
 
 template <int BN>
 __global__ void __launch_bounds__(TS_THREADS, 1)
@@ -416,10 +449,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   // carve shared memory (tiles need 1024-byte alignment for the 128B swizzle)
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * S::kStage);
+  float* cscale = reinterpret_cast<float*>(tiles + TC_STAGES * S::kStage);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * S::kStage + S::kScale);
   uint64_t* full_bar = bars;                    // TMA bytes landed          (count 1 + tx)
   uint64_t* empty_bar = bars + TC_STAGES;       // MMAs that read the stage retired (count 1, tcgen05.commit)
-  uint64_t* aready = bars + 2 * TC_STAGES;      // [2] X halves written to the TMEM operand slot (128 split threads)
+  uint64_t* aready = bars + 2 * TC_STAGES;      // [2] X halves written to the TMEM operand slot (256 split threads)
   uint64_t* aempty = aready + 2;                // [2] ... consumed (tcgen05.commit)
   uint64_t* accum_bar = aempty + 2;             // accumulator complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
@@ -430,7 +464,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&aready[s], 128);
+      mbar_init(&aready[s], 256);
       mbar_init(&aempty[s], 1);
     }
     mbar_init(accum_bar, 1);
@@ -456,6 +490,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   const bool has_rows = active && row0 < m.hi;
   const int kblocks = p.ntaps * p.kbp;
   const uint32_t dseed = p.dyn ? p.dyn->seed : 0u;
+  // Dropout2d: the scale vector of this tile's sequence goes to shared memory once (the split threads then read it as a
+  // broadcast); read through __ldg inside the k loop it cost 70 us of the 150 us projection of a training step
+  const bool cs_smem = p.colscale != nullptr && p.c_in * 4 <= S::kScale;
+  if (has_rows && cs_smem && warp >= 2) {
+    const float* src = p.colscale + (size_t)m.seq * p.colscale_ld;
+    for (int i = threadIdx.x - 64; i < p.c_in; i += TS_THREADS - 64) cscale[i] = __ldg(src + i);
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");   // warps 2..9
+  }
+  const float* cs = p.colscale == nullptr ? nullptr : (cs_smem ? cscale : p.colscale + (size_t)m.seq * p.colscale_ld);
 
   if (has_rows) {
     if (warp == 0) {
@@ -500,9 +543,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         __syncwarp();
       }
     } else {
-      if (warp < 6) {
-        // ===================== operand split (warps 2..5): one frame = one thread = one TMEM lane ================
-        const int r = (warp & 3) * 32 + lane;
+      {
+        // ===================== operand split (warps 2..9): two threads per frame (= TMEM lane), 16 columns each =======
+        // (warps w and w + 4 share the lane quadrant w % 4; with one thread per frame the four split warps -- hash of the
+        // input mask, scale, split, tcgen05.st -- were the bottleneck of the projection: 2.4 us per k-block)
+        const int r = (warp & 3) * 32 + lane, half = (warp - 2) >> 2;
         const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t in_seed = p.in_drop_seed ^ dseed;
         int tap = 0, kc = 0;
@@ -512,8 +557,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           mbar_wait(&full_bar[s], (kb / TC_STAGES) & 1);
           mbar_wait(&aempty[ta], (((uint32_t)kb >> 1) & 1) ^ 1);
           tc_fence_after();
-          split_row_to_tmem(reinterpret_cast<const float4*>(tiles + s * S::kStage), r, row0 + r + sh, m, kc, p, in_seed,
-                            lane_base + kAslot + ta * 64);
+          split_half_row_to_tmem(reinterpret_cast<const float4*>(tiles + s * S::kStage), r, half, row0 + r + sh, m, kc, p,
+                                 cs, in_seed, lane_base + kAslot + ta * 64);
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&aready[ta]);
@@ -1039,10 +1084,10 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   const uint32_t dseed = p.y.dyn ? p.y.dyn->seed : 0u;
   constexpr uint32_t kU = 0, kV = 128, kHhi = 256, kHlo = 320, kA = 384;
   pdl_launch_dependents();
-  pdl_wait();
-
+  // The split weights are constants of the step (written by split_weight_batched, behind a full stream dependency: see
+  // launch_layer_fwd_tc): their 128 KB are requested BEFORE griddepcontrol.wait, i.e. while the predecessor's last tiles
+  // still run -- tools/exp/launch_floor.cu measures 1.4 us for this load when it sits behind the wait.
   if (warp == 0) {
-    // ===================== TMA producer =====================
     if (elect_one()) {
       mbar_arrive_expect_tx(wfull, 8 * 2 * TP_KB);
       for (int kb = 0; kb < 6; ++kb) {
@@ -1053,6 +1098,14 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         tma_load_2d(wt + (6 + kc) * 2 * TP_KB, &map_w2hi, wfull, kc * TC_BK, 0);
         tma_load_2d(wt + (6 + kc) * 2 * TP_KB + TP_KB, &map_w2lo, wfull, kc * TC_BK, 0);
       }
+    }
+    __syncwarp();
+  }
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
       int it = 0;
       for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
         const BlkMeta m = p.y.meta[blk];
@@ -1301,8 +1354,11 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u));
 }
 
+// pdl: programmatic dependent launch.  The kernel reads its weights before griddepcontrol.wait, so `pdl` may only be set when
+// the weights were final before the PREDECESSOR started -- the executor launches the first layer of a pass without it
+// (a full dependency: everything enqueued earlier, the weight split included, has completed), the C ABI never sets it.
 int launch_layer_fwd_tc(const CUtensorMap& mx, const CUtensorMap& w1hi, const CUtensorMap& w1lo, const CUtensorMap& w2hi,
-                        const CUtensorMap& w2lo, const LayerTcDev& p, int cap_nblk, cudaStream_t stream) {
+                        const CUtensorMap& w2lo, const LayerTcDev& p, int cap_nblk, cudaStream_t stream, bool pdl) {
   static bool attr_set = false;
   if (!attr_set) {
     const cudaError_t e =
@@ -1317,7 +1373,7 @@ int launch_layer_fwd_tc(const CUtensorMap& mx, const CUtensorMap& w1hi, const CU
   const int nb = cap_nblk > 0 ? cap_nblk : p.y.nblk;
   int gx = num_sms();
   if (gx > nb) gx = nb;
-  launch_kernel(layer_fwd_tc_kernel, dim3(gx), dim3(LFT_FWD_THREADS), lft_smem_bytes(), stream, true, mx, w1hi, w1lo, w2hi, w2lo,
+  launch_kernel(layer_fwd_tc_kernel, dim3(gx), dim3(LFT_FWD_THREADS), lft_smem_bytes(), stream, pdl, mx, w1hi, w1lo, w2hi, w2lo,
                 p);
   return check_launch("layer_fwd_tc_kernel");
 }
@@ -1390,10 +1446,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t kU = 0, kAcc = 128, kA1 = 256, kA2lo = 384;
   pdl_launch_dependents();
-  pdl_wait();
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {   // step-constant weights: requested before griddepcontrol.wait (see layer_fwd_tc_kernel)
     if (elect_one()) {
       mbar_arrive_expect_tx(wfull, 8 * 2 * TP_KB);
       for (int kc = 0; kc < 2; ++kc) {
@@ -1404,6 +1457,14 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_con
         tma_load_2d(wt + (2 + kb) * 2 * TP_KB, &map_w1thi, wfull, kb * TC_BK, 0);
         tma_load_2d(wt + (2 + kb) * 2 * TP_KB + TP_KB, &map_w1tlo, wfull, kb * TC_BK, 0);
       }
+    }
+    __syncwarp();
+  }
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
       int it = 0;
       for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
         const BlkMeta m = p.gx.meta[blk];
@@ -1602,7 +1663,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_con
 
 int launch_layer_bwd_tc(const CUtensorMap& mgy, const CUtensorMap& w2thi, const CUtensorMap& w2tlo,
                         const CUtensorMap& w1thi, const CUtensorMap& w1tlo, const LayerBwdTcDev& p, int cap_nblk,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, bool pdl) {
   static bool attr_set = false;
   if (!attr_set) {
     const cudaError_t e =
@@ -1617,7 +1678,7 @@ int launch_layer_bwd_tc(const CUtensorMap& mgy, const CUtensorMap& w2thi, const 
   const int nb = cap_nblk > 0 ? cap_nblk : p.gx.nblk;
   int gx = num_sms();
   if (gx > nb) gx = nb;
-  launch_kernel(layer_bwd_tc_kernel, dim3(gx), dim3(LFT_THREADS), lft_smem_bytes(), stream, true, mgy, w2thi, w2tlo, w1thi,
+  launch_kernel(layer_bwd_tc_kernel, dim3(gx), dim3(LFT_THREADS), lft_smem_bytes(), stream, pdl, mgy, w2thi, w2tlo, w1thi,
                 w1tlo, p);
   return check_launch("layer_bwd_tc_kernel");
 }
@@ -2079,7 +2140,7 @@ extern "C" int tcn_layer_fwd_tc(const tcn_layer_fwd_tc_args* a, tcn_stream_t str
   p.y.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
   p.y.drop_seed = a->drop_seed; p.y.drop_stream = a->drop_stream;
   p.masks = a->masks;
-  return launch_layer_fwd_tc(mx, w1h, w1l, w2h, w2l, p, 0, (cudaStream_t)stream);
+  return launch_layer_fwd_tc(mx, w1h, w1l, w2h, w2l, p, 0, (cudaStream_t)stream, false);
 }
 
 extern "C" int tcn_layer_bwd_tc(const tcn_layer_bwd_tc_args* a, tcn_stream_t stream) {
@@ -2108,5 +2169,5 @@ extern "C" int tcn_layer_bwd_tc(const tcn_layer_bwd_tc_args* a, tcn_stream_t str
   p.masks = a->masks;
   p.use_drop = a->drop_p > 0.f ? 1 : 0;
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
-  return launch_layer_bwd_tc(mg, w2h, w2l, w1h, w1l, p, 0, (cudaStream_t)stream);
+  return launch_layer_bwd_tc(mg, w2h, w2l, w1h, w1l, p, 0, (cudaStream_t)stream, false);
 }

@@ -40,13 +40,6 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// TMA prefetch of one box into L2 (no shared-memory destination, no barrier): used a few tiles ahead of the loads so that
-// the loads themselves see L2 latency instead of HBM latency -- the rings are bound by bytes in flight, not by bandwidth
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(reinterpret_cast<uint64_t>(map)),
-               "r"(c0), "r"(c1)
-               : "memory");
-}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -128,6 +121,17 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
       "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
       : "memory");
 }
+// 32 lanes x 16 columns per warp
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
 // kind::tf32 with the A operand in TENSOR MEMORY (row m of A in lane m, K along 32-bit columns; verified on B200 with
@@ -203,7 +207,7 @@ struct LayerTcDev {
   uint32_t* masks;   // nullable: (rows, 4) bit words per frame {h > 0 [0..31], [32..63], dropout keep [0..31], [32..63]}
 };
 int launch_layer_fwd_tc(const CUtensorMap& mx, const CUtensorMap& w1hi, const CUtensorMap& w1lo, const CUtensorMap& w2hi,
-                        const CUtensorMap& w2lo, const LayerTcDev& p, int cap_nblk, cudaStream_t stream);
+                        const CUtensorMap& w2lo, const LayerTcDev& p, int cap_nblk, cudaStream_t stream, bool pdl);
 
 // Fused residual layer input gradient on tcgen05 (gemm_tc.cu: layer_bwd_tc_kernel):
 //   gu = ((keep * gy / (1 - p)) W2) * [h > 0];   gx[t] = gy[t] + sum_k W1_k^T gu[t - s_k]
@@ -218,7 +222,7 @@ struct LayerBwdTcDev {
 };
 int launch_layer_bwd_tc(const CUtensorMap& mgy, const CUtensorMap& w2thi, const CUtensorMap& w2tlo,
                         const CUtensorMap& w1thi, const CUtensorMap& w1tlo, const LayerBwdTcDev& p, int cap_nblk,
-                        cudaStream_t stream);
+                        cudaStream_t stream, bool pdl);
 
 int launch_gemm_tc(const CUtensorMap& mx, const CUtensorMap& mwhi, const CUtensorMap& mwlo, const GemmTcDev& p,
                    int cap_nblk, cudaStream_t stream, const CUtensorMap* mx32 = nullptr);

@@ -843,8 +843,10 @@ static int model_forward(tcn_model* m, const float* x, long x_rows, int training
       p.y.drop_scale = pl > 0.f ? 1.f / (1.f - pl) : 1.f;
       p.y.drop_seed = 0u; p.y.drop_stream = (uint32_t)l;
       p.masks = (save_h && m->fused_bwd) ? m->masks[l] : nullptr;
+      // layer 0 without programmatic launch: a full dependency behind the weight split, which lets every later layer
+      // kernel of the step (forward and backward) fetch its weights before its griddepcontrol.wait
       TCN_CHECK(launch_layer_fwd_tc(xm->second, w1->second.mh, w1->second.ml, w2->second.mh, w2->second.ml, p, m->max_blk,
-                                    st));
+                                    st, l != 0));
     } else if (C == 64 && !(m->use_tc && m->max_blk > 2 * num_sms())) {
       LayerFwdDev p;
       p.X = m->act[l]; p.Y = m->act[l + 1]; p.H = save_h ? m->H[l] : nullptr;
@@ -1038,7 +1040,7 @@ static int model_backward(tcn_model* m, const float* x, long x_rows, const float
         p.use_drop = pl > 0.f ? 1 : 0;
         p.drop_scale = pl > 0.f ? 1.f / (1.f - pl) : 1.f;
         TCN_CHECK(launch_layer_bwd_tc(gm->second, w2->second.mh, w2->second.ml, w1->second.mh, w1->second.ml, p, m->max_blk,
-                                      st));
+                                      st, true));
       } else {
         // gu = (gv W2) * [h > 0],   gv = keep * gy / (1 - p) applied as gy is loaded
         TapGemmDev p = base_tapgemm(m);

@@ -32,7 +32,6 @@ constexpr int WL_HALF = WL_NATOM * WL_ATOM;   // 24576 B raw (= hi) region; the 
 constexpr int WL_STAGE = 2 * WL_HALF;         // 49152 B
 constexpr int WL_STAGES = 4;
 constexpr int WL_SMEM = WL_STAGES * WL_STAGE + 1024 + 256;
-constexpr int WL_PREFETCH = 8;                // slots prefetched into L2 ahead of the TMA loads
 constexpr int WL_TMEM_COLS = 256;             // D_a @ 0 (64 columns), D_b @ 64 (128 columns)
 
 __device__ __forceinline__ uint64_t wl_desc(uint32_t smem_addr) {   // MN-major, SWIZZLE_128B_BASE32B, LBO = one box
@@ -102,39 +101,10 @@ __device__ __forceinline__ void wgrad_layer_body(const WgLayerDev* __restrict__ 
     // ===================== TMA producer =====================
     if (elect_one()) {
       int it = 0;
-      // L2 prefetch WL_PREFETCH valid slots ahead of the loads: x and h of a layer were written in the forward pass and
-      // come from HBM; with 4 x 24 KB of loads in flight per SM the ring is bound by latency, so the latency must be L2's
-      int pf = s_lo, pf_ahead = 0;
-      const int pf_dist = (q.debug >> 8) ? (q.debug >> 8) - 1 : WL_PREFETCH;   // experiments: distance - 1 in bits 8..
-      auto prefetch_more = [&]() {
-        while (pf_ahead < pf_dist && pf < s_hi) {
-          const int pblk = pf >> 3;
-          const int pr0 = pblk * kBlkRows + (pf & 7) * WL_RC;
-          if (pr0 < q.meta[pblk].hi) {
-#pragma unroll
-            for (int tap = 0; tap < 3; ++tap) {
-              const int sh = tap == 0 ? d->shift[0] : (tap == 1 ? d->shift[1] : d->shift[2]);
-              tma_prefetch_2d(&d->mx, 0, pr0 + sh);
-              tma_prefetch_2d(&d->mx, 32, pr0 + sh);
-            }
-            tma_prefetch_2d(&d->mh, 0, pr0);
-            tma_prefetch_2d(&d->mh, 32, pr0);
-            tma_prefetch_2d(&d->mgu, 0, pr0);
-            tma_prefetch_2d(&d->mgu, 32, pr0);
-            tma_prefetch_2d(&d->mgy, 0, pr0);
-            tma_prefetch_2d(&d->mgy, 32, pr0);
-            ++pf_ahead;
-          }
-          ++pf;
-        }
-      };
-      prefetch_more();
       for (int slot = s_lo; slot < s_hi; ++slot) {
         const int blk = slot >> 3;
         const int r0 = blk * kBlkRows + (slot & 7) * WL_RC;
         if (r0 >= q.meta[blk].hi) continue;
-        --pf_ahead;
-        prefetch_more();
         const int s = it % WL_STAGES;
         mbar_wait(&empty_bar[s], ((it / WL_STAGES) & 1) ^ 1);
         uint8_t* st = tiles + s * WL_STAGE;

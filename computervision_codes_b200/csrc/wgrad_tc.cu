@@ -182,8 +182,21 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
 #pragma unroll
       for (int a = 0; a < NGA; ++a) bsum[a] = make_float4(0.f, 0.f, 0.f, 0.f);
       int it = 0;
+      // Dropout2d scale of the four X blocks: a thread always owns the same four columns of a block, and the scale only
+      // changes with the sequence -- fetched once per sequence instead of once per 32-frame chunk
+      float4 csc[4];
+      int csc_seq = -1;
       for (int blk = blk_begin; blk < blk_end; ++blk) {
         const BlkMeta m = p.meta[blk];
+        if (p.colscale != nullptr && m.seq != csc_seq && blk * kBlkRows < m.hi) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = a_cb[j] * 32 + lc * 4;
+            csc[j] = col < p.c_in ? __ldg(reinterpret_cast<const float4*>(p.colscale + (size_t)m.seq * p.colscale_ld + col))
+                                  : make_float4(1.f, 1.f, 1.f, 1.f);
+          }
+          csc_seq = m.seq;
+        }
         for (int ch = 0; ch < 4; ++ch) {
           const int r0 = blk * kBlkRows + ch * WG_RC;
           if (r0 >= m.hi) break;
@@ -206,8 +219,8 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
             if (extras) {
               if (atom < 4) {
                 const int col = a_cb[atom] * 32 + lc * 4;
-                if (p.colscale != nullptr && col < p.c_in) {
-                  const float4 sc = __ldg(reinterpret_cast<const float4*>(p.colscale + (size_t)m.seq * p.colscale_ld + col));
+                if (p.colscale != nullptr) {
+                  const float4 sc = csc[atom < 4 ? atom : 0];
                   v[i].x *= sc.x; v[i].y *= sc.y; v[i].z *= sc.z; v[i].w *= sc.w;
                 }
                 if (p.x_drop_thresh != 0u) {

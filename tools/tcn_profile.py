@@ -18,7 +18,10 @@ D = 2048
 lens = [2250] * 8
 args = types.SimpleNamespace(fpn=True, output=False, feature=False, trans=False, mask=True, hier=False)
 m = VideoNas(args, 11, 10, 3, 64, D, 100).to(dev).train()
-tr = TemporalTrainer(m, lr=1e-2, weight_decay=1e-5, max_frames=sum(lens), max_seqs=8, input_mask_p=0.25)
+if os.environ.get("PROF_CHAN") == "0":
+    m.PG.channel_dropout.p = 0.0
+tr = TemporalTrainer(m, lr=1e-2, weight_decay=1e-5, max_frames=sum(lens), max_seqs=8,
+                     input_mask_p=float(os.environ.get("PROF_MASK", "0.25")))
 x = torch.randn(sum(lens), D, device=dev)
 lab = (torch.rand(sum(lens), 132, device=dev) < 0.05).to(torch.uint8)
 for _ in range(4):
@@ -55,3 +58,16 @@ print(f"steps {N}: span {(t1 - t0) / N / 1e3:.3f} ms/step, GPU busy (union) {bus
       f"sum of kernel times {tot / N / 1e3:.3f} ms/step")
 for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:16]:
     print(f"{k:46s} n/step={n / N:6.1f} total/step={us / N:8.1f} us avg={us / n:7.2f} us share={us / tot:.3f}")
+
+# ---- one step as a timeline: every kernel with its start offset, duration and stream; gaps on the busiest stream
+if os.environ.get("TCN_TIMELINE"):
+    step_evs = [e for e in evs if e.time_range.start >= t0 + (t1 - t0) * 2 / N and e.time_range.end <= t0 + (t1 - t0) * 3 / N + 50]
+    base = step_evs[0].time_range.start
+    last_end = {}
+    print("# start_us dur_us gap_after_prev_on_stream  stream  kernel")
+    for e in step_evs:
+        sid = getattr(e, "stream", None) if hasattr(e, "stream") else None
+        sid = sid if sid is not None else getattr(e, "device_resource_id", 0)
+        gap = e.time_range.start - last_end.get(sid, e.time_range.start)
+        last_end[sid] = e.time_range.end
+        print(f"{e.time_range.start - base:9.1f} {e.time_range.end - e.time_range.start:7.1f} {gap:7.1f}  {sid}  {e.name.split('(')[0].replace('tcn::', '')[:40]}")

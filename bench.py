@@ -401,9 +401,11 @@ def run_cfg2(a, rank, world, local_rank, C, D, tag):
     _lib.load()
     model = build_model(dev, C, D)
     passes, lengths = fold_schedule()
-    max_frames = max(lengths.values()) * V
+    # capacity: V videos per rank, or up to Vcap when the end-to-end arm shards by host-link bandwidth (N > 1, below)
+    Vcap = V if world == 1 else V + V // 2 + 1
+    max_frames = max(lengths.values()) * Vcap
     trainer = TemporalTrainer(model, lr=1e-2, weight_decay=1e-5, process_group=pg, world_size=world,
-                              max_frames=max_frames, max_seqs=max(V, 1), use_graph=not a.no_graph,
+                              max_frames=max_frames, max_seqs=max(Vcap, 1), use_graph=not a.no_graph,
                               input_mask_p=0.25, seed=1234 + rank)  # --mask of Scripts/train_fold1.sh:28
 
     # Global step s takes the next V * world passes of the schedule (cycled) and assigns them to the ranks
@@ -454,7 +456,7 @@ def run_cfg2(a, rank, world, local_rank, C, D, tag):
             barrier()
         return allmax(e0.elapsed_time(e1))
 
-    def timed(run_step):
+    def timed(run_step, batch_fn):
         """W warm-up steps, K probe steps (also warm-up) that size the repeat count R, then K * R timed steps."""
         K, W = a.steps, a.warmup
         for s in range(W):
@@ -463,14 +465,14 @@ def run_cfg2(a, rank, world, local_rank, C, D, tag):
         R = max(1, min(int(math.ceil(a.min_seconds * 1e3 / max(probe_ms, 1e-3))), 2000))
         s0 = W + K
         ms = region(run_step, s0, K * R)
-        frames = allsum(sum(lengths[v] for s in range(s0, s0 + K * R) for v in batch_at(s)))
+        frames = allsum(sum(lengths[v] for s in range(s0, s0 + K * R) for v in batch_fn(s)))
         return ms, R, frames
 
     # ---- arm 1: inputs resident in HBM (the step starts from device tensors)
     def step_resident(s):
         trainer.step_cached(cache, [(v, 0, lengths[v]) for v in batch_at(s)])
 
-    ms_total, R, frames_all = timed(step_resident)
+    ms_total, R, frames_all = timed(step_resident, batch_at)
     value = frames_all / (ms_total * 1e-3)
 
     # ---- arm 2: end to end through the public API with HOST (pinned) inputs: H2D of this step's
@@ -478,9 +480,48 @@ def run_cfg2(a, rank, world, local_rank, C, D, tag):
     loss_host = torch.empty(8, dtype=torch.float32).pin_memory()
     h2d = [0]
     staged = [None]
+    # N > 1: the ranks' host links differ (two host bridges, tools/h2d_concurrent.py) and every step ends with an
+    # all-reduce, so the slowest link would set the pace.  The end-to-end arm measures each rank's pinned-copy bandwidth
+    # with all ranks copying at once, shards the videos of a global step in proportion to it (weighted LPT, at most Vcap
+    # per rank) and normalises the loss by the GLOBAL video count, so that the summed gradient is still the mean over
+    # all V x N videos of the step.  The resident arm keeps equal shares.
+    link_bw = None
+    if world > 1:
+        probe = sorted(host)[:8]
+        dst = [torch.empty_like(host[v][0], device=dev) for v in probe]
+        torch.cuda.synchronize()
+        for rep in range(3):
+            if rep == 1:
+                barrier()
+                t0 = time.perf_counter()
+            for v, d_ in zip(probe, dst):
+                d_.copy_(host[v][0], non_blocking=True)
+            torch.cuda.synchronize()
+        mine = 2 * sum(host[v][0].numel() * 4 for v in probe) / (time.perf_counter() - t0) / 1e9
+        del dst
+        t = torch.zeros(world, device=dev, dtype=torch.float64)
+        t[rank] = mine
+        torch.distributed.all_reduce(t)
+        link_bw = [float(x) for x in t.tolist()]
+        config["e2e_sharding"] = {"pinned_copy_GBps_per_rank_all_ranks_copying": [round(x, 1) for x in link_bw],
+                                  "rule": "videos of a global step assigned longest-first in proportion to the rank's "
+                                          f"link bandwidth (at most {Vcap} per rank); loss normalised by the global video count"}
+    _ecache = {}
+
+    def batch_e2e(s):
+        if link_bw is None:
+            return batch_at(s)
+        b = _ecache.get(s)
+        if b is None:
+            vids = [passes[(s * V * world + j) % len(passes)] for j in range(V * world)]
+            shard = lpt_assign([lengths[v] for v in vids], world, cap=Vcap, weights=link_bw)[rank]
+            b = _ecache[s] = [vids[i] for i in shard]
+        return b
+
+    gseq = None if link_bw is None else V * world
 
     def stage(s):
-        b = batch_at(s)
+        b = batch_e2e(s)
         xs, ls = [host[v][0] for v in b], [host[v][1] for v in b]
         h2d[0] = sum(t.numel() * t.element_size() for t in xs + ls)
         trainer.prefetch(xs, ls, [lengths[v] for v in b])
@@ -492,12 +533,12 @@ def run_cfg2(a, rank, world, local_rank, C, D, tag):
         if trainer._prefetched is None or staged[0] != s:
             trainer._prefetched = None
             stage(s)
-        out = trainer.step()
+        out = trainer.step(global_seqs=gseq)
         stage(s + 1)
         loss_host.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    ms_e2e, R_e2e, frames_e2e = timed(step_e2e)
+    ms_e2e, R_e2e, frames_e2e = timed(step_e2e, batch_e2e)
     trainer._prefetched = None
     torch.cuda.synchronize()
     e2e_value = frames_e2e / (ms_e2e * 1e-3)

@@ -194,6 +194,7 @@ SIGNATURES = {
     "tcn_model_param_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]),
     "tcn_model_bind": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tcn_model_set_loss": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "tcn_model_set_loss_norm": (C.c_int, [C.c_void_p, C.c_int]),
     "tcn_model_set_dropout": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float]),
     "tcn_model_set_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint,
                                       C.c_void_p]),

@@ -62,7 +62,9 @@ constexpr int kBlkRows = 128;
 struct __align__(16) BatchDesc {
   int nblk, rows, num_seqs, frames;
   unsigned seed;  // dropout seed of this step
-  int pad[3];
+  int norm_seqs;  // > 0: the loss / its gradient are normalised by this many sequences instead of num_seqs (data parallel
+                  // with unequal shares: every rank divides by the GLOBAL number of videos, the all-reduce then sums)
+  int pad[2];
 };
 
 // One (weight tensor, orientation) pair of the batched weight preparation.

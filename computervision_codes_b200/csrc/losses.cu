@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256) bce_rows_kernel(const BceDev p) {
   for (int h = 0; h < kMaxHeads; ++h) part[h] = 0.f;
 
   const int nrows = p.dyn ? p.dyn->rows : p.nrows;
-  const float rsc = p.dyn ? 1.f / (float)p.dyn->num_seqs : p.row_scale_const;
+  const float rsc = p.dyn ? 1.f / (float)(p.dyn->norm_seqs > 0 ? p.dyn->norm_seqs : p.dyn->num_seqs) : p.row_scale_const;
   const bool walk = p.nlev > 0 && p.cum_lv[0] != nullptr;   // one warp per row over all levels (gridDim.y == 1)
   const float* logits = p.nlev > 0 ? p.logits_lv[walk ? 0 : blockIdx.y] : p.logits;
   float* dL = p.nlev > 0 ? p.dL_lv[walk ? 0 : blockIdx.y] : p.dL;

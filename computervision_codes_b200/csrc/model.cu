@@ -61,6 +61,7 @@ struct tcn_model {
   float* cum[4] = {nullptr, nullptr, nullptr, nullptr};
   BatchDesc *desc4 = nullptr, *desc3 = nullptr;
   BlkMeta* meta4 = nullptr;
+  int norm_seqs = 0;          // tcn_model_set_loss_norm: sequences the loss is averaged over (0 = those of the batch)
   bool stack_levels = true;   // TCN_NO_STACK=1: one launch per level (A/B)
   // slabs of the deterministic weight-gradient reduction of the heads, the lateral and the projection (wgrad_tc.cu)
   float* slab[3] = {nullptr, nullptr, nullptr};
@@ -724,6 +725,12 @@ extern "C" int tcn_model_set_loss(tcn_model* m, const float* head_weights, const
   return TCN_OK;
 }
 
+extern "C" int tcn_model_set_loss_norm(tcn_model* m, int norm_seqs) {
+  TCN_REQUIRE(m && norm_seqs >= 0, "tcn_model_set_loss_norm: bad arguments");
+  m->norm_seqs = norm_seqs;   // takes effect with the next tcn_model_set_batch
+  return TCN_OK;
+}
+
 extern "C" int tcn_model_set_dropout(tcn_model* m, float input_mask_p, float chan_drop_p, float layer_drop_p) {
   TCN_REQUIRE(m, "tcn_model_set_dropout: null pointer");
   TCN_REQUIRE(input_mask_p >= 0.f && input_mask_p < 1.f && chan_drop_p >= 0.f && chan_drop_p < 1.f &&
@@ -747,6 +754,7 @@ extern "C" int tcn_model_set_batch(tcn_model* m, const int* meta_host, int nblk,
   cudaEventSynchronize(m->slot_done[sl]);
   BatchDesc* d = reinterpret_cast<BatchDesc*>(m->desc_host + (size_t)sl * m->slot_bytes);
   d->nblk = nblk; d->rows = rows; d->num_seqs = num_seqs; d->frames = frames; d->seed = seed;
+  d->norm_seqs = m->norm_seqs; d->pad[0] = d->pad[1] = 0;
   // level-stacked views: level l occupies rows [l * max_rows, (l + 1) * max_rows) of a stack and blocks
   // [l * max_blk, l * max_blk + nblk) of meta4; the blocks in between are empty (hi = 0: every kernel skips them)
   const int MB = m->max_blk, MR = m->cfg.max_rows;

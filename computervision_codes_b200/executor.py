@@ -102,6 +102,11 @@ class ModelExecutor:
         _lib.check(_lib.load().tcn_model_set_dropout(self.h, input_mask_p, chan_drop_p, layer_drop_p),
                    "tcn_model_set_dropout")
 
+    def set_loss_norm(self, norm_seqs: int = 0):
+        """Average the loss over `norm_seqs` sequences (the global number of videos of a data-parallel step) instead of the
+        sequences of this rank's batch; 0 = default.  Takes effect with the next set_batch."""
+        _lib.check(_lib.load().tcn_model_set_loss_norm(self.h, int(norm_seqs)), "tcn_model_set_loss_norm")
+
     def set_batch(self, lay: SeqLayout, seed: int):
         assert lay.rows <= self.max_rows and lay.num_seqs <= self.max_seqs, "batch exceeds the executor capacity"
         meta = np.ascontiguousarray(lay.meta_np)

@@ -67,16 +67,19 @@ class TemporalTrainerEager:
         return out
 
 
-def lpt_assign(lengths, world, cap=None):
+def lpt_assign(lengths, world, cap=None, weights=None):
     """Longest-processing-time-first assignment of videos to ranks (balances frames per rank).
     cap: at most this many videos per rank (equal counts keep "mean over ranks of the per-rank mean" == mean over all
-    videos)."""
+    videos).  weights: relative speed of each rank (e.g. its host-link bandwidth when the inputs come from the host): rank
+    k then gets frames in proportion to weights[k]; the shares are unequal, so the step must normalise by the global
+    video count (TemporalTrainer.step(..., global_seqs=n))."""
     order = sorted(range(len(lengths)), key=lambda i: -lengths[i])
     loads = [0] * world
+    w = [1.0] * world if weights is None else [float(x) for x in weights]
     shards = [[] for _ in range(world)]
     for i in order:
         open_ranks = [k for k in range(world) if cap is None or len(shards[k]) < cap]
-        r = min(open_ranks, key=lambda k: loads[k])
+        r = min(open_ranks, key=lambda k: (loads[k] + lengths[i]) / w[k])
         shards[r].append(i)
         loads[r] += lengths[i]
     return shards
@@ -138,6 +141,7 @@ class TemporalTrainer:
         # {lr, weight_decay, grad_scale} live on the device: the captured graph follows set_lr() / an LR schedule
         self._hyper_host = torch.tensor([lr, weight_decay, 1.0 / max(1, world_size)], dtype=torch.float32).pin_memory()
         self.hyper = self._hyper_host.to(dev)
+        self._global_seqs = 0
 
     def set_lr(self, lr: float):
         """New learning rate for the following steps (no graph re-capture).  The value travels as a kernel argument of
@@ -146,13 +150,24 @@ class TemporalTrainer:
         self._hyper_host[0] = self.lr
         self.hyper[0:1].fill_(self.lr)
 
-    def step_cached(self, cache, items):
+    def _set_global_norm(self, global_seqs):
+        """global_seqs: number of videos of the whole data-parallel step when the ranks hold unequal shares (every rank
+        divides by it, the all-reduce sums: the global mean); None = equal shares (mean per rank, then mean over ranks)."""
+        g = 0 if global_seqs is None else int(global_seqs)
+        if g != self._global_seqs:
+            self._global_seqs = g
+            self.ex.set_loss_norm(g)
+            self._hyper_host[2] = 1.0 if g > 0 else 1.0 / max(1, self.world)
+            self.hyper[2:3].fill_(float(self._hyper_host[2]))   # stream-ordered: the captured SGD reads it from device memory
+
+    def step_cached(self, cache, items, global_seqs=None):
         """One step on clips / videos of a ``data.FeatureCache``: items = [(video, start, length), ...].
         A packed cache (``cache.pack()``) is read in place: no copy, the block table addresses the arena."""
+        self._set_global_norm(global_seqs)
         items = list(items)
         if getattr(cache, "arena_x", None) is None:
             xs, ls, lens = cache.batch(items)
-            return self.step(xs, ls, lens)
+            return self.step(xs, ls, lens, global_seqs=global_seqs)
         lens, starts = [], []
         for vid, start, n in items:
             assert 0 <= start and n > 0 and start + n <= cache.frames(vid), (vid, start, n)
@@ -248,10 +263,11 @@ class TemporalTrainer:
         self.slot_ready2[nxt].record(self.copy_stream2)
         self._prefetched = (nxt, lay)
 
-    def step(self, x_rows=None, labels_u8=None, lengths=None):
+    def step(self, x_rows=None, labels_u8=None, lengths=None, global_seqs=None):
         """One optimizer step.  x_rows / labels_u8: one tensor or a list with one tensor per video (device or pinned
-        host); omit them to consume the batch staged by prefetch().  Returns the device loss vector
-        (loss_ivt, loss_i, loss_v, loss_t, total, 0, 0, 0)."""
+        host); omit them to consume the batch staged by prefetch().  global_seqs: see _set_global_norm (unequal data-
+        parallel shares).  Returns the device loss vector (loss_ivt, loss_i, loss_v, loss_t, total, 0, 0, 0)."""
+        self._set_global_norm(global_seqs)
         cur = torch.cuda.current_stream()
         if x_rows is None:
             assert self._prefetched is not None, "step() without arguments needs a prefetch()"

@@ -232,6 +232,11 @@ int tcn_model_set_loss(tcn_model* m, const float* head_weights, const float* pos
 /* input_mask_p: probability of zeroing an input element (network.py:43-48 uses 0.25), 0 = off;
  * chan_drop_p: Dropout2d over input channels (network.py:117), layer_drop_p: nn.Dropout of the layers */
 int tcn_model_set_dropout(tcn_model* m, float input_mask_p, float chan_drop_p, float layer_drop_p);
+/* Data parallel with unequal shares: average the loss (run.py:190-212 takes the mean over the frames of ONE video per step;
+ * a batch averages over its videos) over `norm_seqs` sequences -- the GLOBAL number of videos of the step -- instead of
+ * the sequences of this rank's batch, so that a plain sum all-reduce of the gradients gives the global mean.  0 restores
+ * the default.  Takes effect with the next tcn_model_set_batch. */
+int tcn_model_set_loss_norm(tcn_model* m, int norm_seqs);
 /* meta_host: HOST int4[nblk]; copied (async) with the batch descriptor into device memory */
 int tcn_model_set_batch(tcn_model* m, const int* meta_host, int nblk, int rows, int num_seqs, int frames,
                         unsigned seed, tcn_stream_t stream);

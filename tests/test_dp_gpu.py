@@ -77,10 +77,10 @@ def test_two_rank_trainer_equals_one_rank_on_the_union(tmp_path, use_graph):
         xs, labs = zip(*[_data(r, s) for r in range(2)])
         out = tr.step(torch.cat(xs).to(dev), torch.cat(labs).to(dev), LENS[0] + LENS[1])
         both = 0.5 * (r0["loss"][s] + r1["loss"][s])   # per-rank loss = mean over its 2 videos
-        assert torch.allclose(out.cpu(), both, rtol=2e-5, atol=1e-6), (s, out.cpu(), both)
+        assert torch.allclose(out.cpu(), both, rtol=1e-4, atol=1e-6), (s, out.cpu(), both)
     ref = tr.flat_p.cpu()
     err = float((ref - r0["p"]).abs().max()) / max(1.0, float(ref.abs().max()))
-    assert err <= 2e-6, err
+    assert err <= 2e-5, err   # different layouts sum in different orders; a wrong normalisation would be off by a factor
 
 
 def test_two_ranks_with_unequal_shares_equal_one_rank_on_the_union(tmp_path):
@@ -104,7 +104,7 @@ def test_two_ranks_with_unequal_shares_equal_one_rank_on_the_union(tmp_path):
         xs, labs = zip(*[_data(r, s, LENS_UNEQUAL) for r in range(2)])
         out = tr.step(torch.cat(xs).to(dev), torch.cat(labs).to(dev), LENS_UNEQUAL[0] + LENS_UNEQUAL[1])
         both = r0["loss"][s] + r1["loss"][s]   # each rank's loss is its videos' sum over the GLOBAL count
-        assert torch.allclose(out.cpu(), both, rtol=2e-5, atol=1e-6), (s, out.cpu(), both)
+        assert torch.allclose(out.cpu(), both, rtol=1e-4, atol=1e-6), (s, out.cpu(), both)
     ref = tr.flat_p.cpu()
     err = float((ref - r0["p"]).abs().max()) / max(1.0, float(ref.abs().max()))
-    assert err <= 2e-6, err
+    assert err <= 2e-5, err   # different layouts sum in different orders; a wrong normalisation would be off by a factor

@@ -132,6 +132,17 @@ class AttnArgs(C.Structure):
     ]
 
 
+class AttnTcArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("ldq", C.c_int), ("k", C.c_void_p), ("ldk", C.c_int), ("v", C.c_void_p), ("ldv", C.c_int),
+        ("o", C.c_void_p), ("ldo", C.c_int), ("p", C.c_void_p),
+        ("dout", C.c_void_p), ("lddo", C.c_int), ("dq", C.c_void_p), ("lddq", C.c_int), ("dk", C.c_void_p),
+        ("lddk", C.c_int), ("dv", C.c_void_p), ("lddv", C.c_int), ("dp", C.c_void_p),
+        ("seq_lo", C.c_void_p), ("seq_len", C.c_void_p), ("nseq", C.c_int), ("rows", C.c_longlong),
+        ("heads", C.c_int), ("head_dim", C.c_int), ("tmax", C.c_int), ("scale", C.c_float),
+    ]
+
+
 class KdAttnArgs(C.Structure):
     _fields_ = [
         ("s", C.c_void_p), ("lds", C.c_int),
@@ -211,6 +222,9 @@ SIGNATURES = {
                                     C.c_void_p]),
     "tcn_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), C.c_void_p]),
     "tcn_attn_bwd": (C.c_int, [C.POINTER(AttnArgs), C.c_void_p]),
+    "tcn_attn_tc_supported": (C.c_int, [C.c_int] * 5),
+    "tcn_attn_fwd_tc": (C.c_int, [C.POINTER(AttnTcArgs), C.c_void_p]),
+    "tcn_attn_bwd_tc": (C.c_int, [C.POINTER(AttnTcArgs), C.c_void_p]),
     "tcn_dwconv_gelu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_void_p]),
     "tcn_dwconv_gelu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -75,6 +75,64 @@ def _attn_args(q, kv, o, lse, lay, heads, dout=None, dq=None, dkv=None, delta=No
     return a
 
 
+def _attn_tc_args(q, kv, o, p, lay, heads, tmax, dout=None, dq=None, dkv=None, dp=None):
+    d = q.shape[1]
+    hd = d // heads
+    a = _lib.AttnTcArgs()
+    a.q, a.ldq = _lib.ptr(q), d
+    a.k, a.ldk = kv.data_ptr(), 2 * d
+    a.v, a.ldv = kv.data_ptr() + d * 4, 2 * d
+    a.o, a.ldo, a.p = _lib.ptr(o), d, _lib.ptr(p)
+    if dout is not None:
+        a.dout, a.lddo = _lib.ptr(dout), d
+        a.dq, a.lddq = _lib.ptr(dq), d
+        a.dk, a.lddk = dkv.data_ptr(), 2 * d
+        a.dv, a.lddv = dkv.data_ptr() + d * 4, 2 * d
+        a.dp = _lib.ptr(dp)
+    a.seq_lo, a.seq_len, a.nseq, a.rows = _lib.ptr(lay.seq_lo), _lib.ptr(lay.seq_len), lay.num_seqs, q.shape[0]
+    a.heads, a.head_dim, a.tmax, a.scale = heads, hd, tmax, float(hd) ** -0.5
+    return a
+
+
+def _attn_tc_ok(q, lay, heads):
+    """tcgen05 path (csrc/attention_tc.cu): windows of at most 256 frames, head dim a multiple of 4."""
+    import os
+
+    if os.environ.get("TCN_NO_ATTN_TC") is not None:
+        return False
+    d = q.shape[1]
+    return bool(_lib.load().tcn_attn_tc_supported(lay.max_len, heads, d // heads, d, 2 * d))
+
+
+class AttentionTcFn(torch.autograd.Function):
+    """o = softmax(q k^T / sqrt(hd)) v per (window, head) on tcgen05: S = q k^T, P = softmax(S) (kept for the backward
+    pass: nseq * heads blocks of tmax x tmax), o = P v; backward dV = P^T dO, dP = dO v^T, dS, dQ = dS k, dK = dS^T q."""
+
+    @staticmethod
+    def forward(ctx, q, kv, lay, heads):
+        lib = _lib.load()
+        q, kv = _c(q), _c(kv)
+        o = _like(q, lay)
+        tmax = (lay.max_len + 31) // 32 * 32
+        p = torch.empty(lay.num_seqs * heads * tmax, tmax, device=q.device, dtype=torch.float32)
+        a = _attn_tc_args(q, kv, o, p, lay, heads, tmax)
+        _lib.check(lib.tcn_attn_fwd_tc(C.byref(a), _lib.stream_ptr()), "tcn_attn_fwd_tc")
+        ctx.save_for_backward(q, kv, p)
+        ctx.lay, ctx.heads, ctx.tmax = lay, heads, tmax
+        return o
+
+    @staticmethod
+    def backward(ctx, go):
+        lib = _lib.load()
+        q, kv, p = ctx.saved_tensors
+        go = _c(go)
+        dq, dkv = _like(q, ctx.lay), _like(kv, ctx.lay)
+        dp = torch.empty_like(p)
+        a = _attn_tc_args(q, kv, dq, p, ctx.lay, ctx.heads, ctx.tmax, go, dq, dkv, dp)
+        _lib.check(lib.tcn_attn_bwd_tc(C.byref(a), _lib.stream_ptr()), "tcn_attn_bwd_tc")
+        return dq, dkv, None, None
+
+
 class AttentionFn(torch.autograd.Function):
     """o = softmax(q k^T / sqrt(hd)) v per (sequence, head); q (rows, d), kv (rows, 2d) = [k | v]."""
 
@@ -103,7 +161,9 @@ class AttentionFn(torch.autograd.Function):
 
 
 def attention(q, kv, lay: SeqLayout, heads: int):
-    return AttentionFn.apply(q, kv, lay, heads)
+    if _attn_tc_ok(q, lay, heads):
+        return AttentionTcFn.apply(q, kv, lay, heads)
+    return AttentionFn.apply(q, kv, lay, heads)   # longer windows / odd head dims: the mma.sync kernels
 
 
 class DwConvGeluFn(torch.autograd.Function):

@@ -328,6 +328,21 @@ typedef struct {
 } tcn_attn_args;
 int tcn_attn_fwd(const tcn_attn_args* args, tcn_stream_t stream);
 int tcn_attn_bwd(const tcn_attn_args* args, tcn_stream_t stream);
+/* The same attention on tcgen05 / TMEM / TMA for windows of at most 256 frames (csrc/attention_tc.cu): the six products
+ * (S = q k^T, o = P v; dV = P^T dO, dP = dO v^T, dQ = dS k, dK = dS^T q) run on one batched tensor-core kernel, the scores of
+ * a (window, head) are materialised once: p (nseq * heads * tmax, tmax) receives P = softmax(scale q k^T) in the forward
+ * pass and is read by the backward pass; dp (same shape) is backward scratch.  tmax: a multiple of 32, >= the longest
+ * window, <= 256; rows: rows of the q / k / v / o buffers.  head_dim and all leading dimensions multiples of 4. */
+typedef struct {
+  const float* q; int ldq; const float* k; int ldk; const float* v; int ldv;
+  float* o; int ldo; float* p;
+  const float* dout; int lddo; float* dq; int lddq; float* dk; int lddk; float* dv; int lddv; float* dp;
+  const int* seq_lo; const int* seq_len; int nseq; long long rows;
+  int heads; int head_dim; int tmax; float scale;
+} tcn_attn_tc_args;
+int tcn_attn_tc_supported(int max_len, int heads, int head_dim, int ldq, int ldkv);
+int tcn_attn_fwd_tc(const tcn_attn_tc_args* args, tcn_stream_t stream);
+int tcn_attn_bwd_tc(const tcn_attn_tc_args* args, tcn_stream_t stream);
 /* Local_Relational_Block depthwise Conv1d(k=3, pad=1, groups=C) over time + GELU (:13-14,36-39), x / y (rows, C);
  * w: (C, 1, 3) torch layout.  Backward: du (scratch, rows x C), dx, dw += , db += . */
 int tcn_dwconv_gelu_fwd(const float* x, float* y, const float* w, const float* b, const int* meta, int nrows,

@@ -22,10 +22,9 @@ constexpr int BG_THREADS = 320;
 constexpr int BG_KC = 32;                       // k elements per stage
 constexpr int BG_A = 128 * BG_KC * 4;           // 16384 B: A tile (either majorness)
 constexpr int BG_BMAX = 256 * BG_KC * 4;        // 32768 B: largest B tile
-constexpr int BG_HALF = BG_A + BG_BMAX;         // raw (= hi) region of a stage; the lo region follows
-constexpr int BG_STAGE = 2 * BG_HALF;           // 98304 B
-constexpr int BG_STAGES = 2;
-constexpr int BG_SMEM = BG_STAGES * BG_STAGE + 1024 + 256;
+constexpr int BG_STAGES = 3;                    // barrier slots; a launch uses 2 stages of 96 KB (256-row B tiles) or 3 of 64 KB
+constexpr int BG_TILES = 2 * 2 * (BG_A + BG_BMAX);   // 196608 B of operand tiles either way
+constexpr int BG_SMEM = BG_TILES + 1024 + 256;
 constexpr int BG_BOX = 32 * 128;                // 4096 B: one MN-major box (32 k rows x 32 columns)
 
 struct BgDev {
@@ -69,10 +68,14 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int npad = (nvalid + 15) & ~15;
   const int nboxb = (npad + 31) >> 5;                       // MN-major B: 32-column boxes
   const int bbytes = b_mn ? nboxb * BG_BOX : BG_BMAX;
+  // stage = [A raw | B raw | A lo | B lo]; MN-major B tiles are at most 16 KB (head dim <= 128): three 64 KB stages
+  const int bcap = (b_mn && nboxb <= 4) ? BG_A : BG_BMAX;
+  const int BG_HALF = BG_A + bcap, BG_STAGE = 2 * BG_HALF;
+  const int nst = bcap == BG_A ? 3 : 2;
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + BG_STAGES * BG_STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + BG_TILES);
   uint64_t* full_bar = bars;
   uint64_t* ready_bar = bars + BG_STAGES;
   uint64_t* empty_bar = bars + 2 * BG_STAGES;
@@ -106,8 +109,8 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       if (elect_one()) {
         const int srow = prob * p.tmax;   // first row of this (window, head) block in the score buffer
         for (int kc = 0; kc < nk; ++kc) {
-          const int s = kc % BG_STAGES;
-          mbar_wait(&empty_bar[s], ((kc / BG_STAGES) & 1) ^ 1);
+          const int s = kc % nst;
+          mbar_wait(&empty_bar[s], ((kc / nst) & 1) ^ 1);
           uint8_t* st = tiles + s * BG_STAGE;
           mbar_arrive_expect_tx(&full_bar[s], BG_A + bbytes);
           if (p.shape == 0) {
@@ -130,8 +133,8 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       // ===================== MMA issuer =====================
       const uint32_t idesc = bg_idesc(npad, a_mn, b_mn);
       for (int kc = 0; kc < nk; ++kc) {
-        const int s = kc % BG_STAGES;
-        mbar_wait(&ready_bar[s], (kc / BG_STAGES) & 1);
+        const int s = kc % nst;
+        mbar_wait(&ready_bar[s], (kc / nst) & 1);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_hi = base + s * BG_STAGE, a_lo = a_hi + BG_HALF;
@@ -156,8 +159,8 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       // ===================== operand split (warps 2..9): lo halves, zeros outside the window / head =====================
       const int ct = threadIdx.x - 64;   // 0..255
       for (int kc = 0; kc < nk; ++kc) {
-        const int s = kc % BG_STAGES;
-        if (lane == 0) mbar_wait(&full_bar[s], (kc / BG_STAGES) & 1);
+        const int s = kc % nst;
+        if (lane == 0) mbar_wait(&full_bar[s], (kc / nst) & 1);
         __syncwarp();
         float4* raw = reinterpret_cast<float4*>(tiles + s * BG_STAGE);
         float4* lov = raw + BG_HALF / 16;

@@ -122,16 +122,40 @@ __global__ void dwconv_gelu_bwd_du_kernel(const float* __restrict__ x, const flo
   for (int c = threadIdx.x + blockIdx.y * blockDim.x; c < C; c += blockDim.x * gridDim.y) {
     const float w0 = w[c * 3], w1 = w[c * 3 + 1], w2 = w[c * 3 + 2], bb = b[c];
     float g0 = 0.f, g1 = 0.f, g2 = 0.f, gb = 0.f;
-    for (int row = r_begin; row < r_end; ++row) {
-      const BlkMeta m = meta[row / kBlkRows];
-      if (row >= m.hi) continue;
-      const float xc = x[(size_t)row * C + c];
-      const float xm = (row - 1 >= m.lo) ? x[(size_t)(row - 1) * C + c] : 0.f;
-      const float xp = (row + 1 < m.hi) ? x[(size_t)(row + 1) * C + c] : 0.f;
-      const float u = w0 * xm + w1 * xc + w2 * xp + bb;
-      const float d = dy[(size_t)row * C + c] * gelu_grad_f(u);
-      du[(size_t)row * C + c] = d;
-      g0 += d * xm; g1 += d * xc; g2 += d * xp; gb += d;
+    // walk the rows block by block (one block table entry per 128 rows); x[t-1], x[t], x[t+1] rotate through registers so
+    // that a row costs one load of x and one of dy, issued four rows ahead of their use
+    for (int blk0 = r_begin; blk0 < r_end; blk0 = (blk0 / kBlkRows + 1) * kBlkRows) {
+      const BlkMeta m = meta[blk0 / kBlkRows];
+      const int lo_r = blk0, hi_r = min(min(r_end, (blk0 / kBlkRows + 1) * kBlkRows), m.hi);
+      if (lo_r >= hi_r) continue;
+      float xm = (lo_r - 1 >= m.lo) ? x[(size_t)(lo_r - 1) * C + c] : 0.f;
+      float xc = x[(size_t)lo_r * C + c];
+      int row = lo_r;
+      for (; row + 4 <= hi_r; row += 4) {
+        float xn[4], dyv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          xn[e] = (row + e + 1 < m.hi) ? x[(size_t)(row + e + 1) * C + c] : 0.f;
+          dyv[e] = dy[(size_t)(row + e) * C + c];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float xp = xn[e];
+          const float u = w0 * xm + w1 * xc + w2 * xp + bb;
+          const float d = dyv[e] * gelu_grad_f(u);
+          du[(size_t)(row + e) * C + c] = d;
+          g0 += d * xm; g1 += d * xc; g2 += d * xp; gb += d;
+          xm = xc; xc = xp;
+        }
+      }
+      for (; row < hi_r; ++row) {
+        const float xp = (row + 1 < m.hi) ? x[(size_t)(row + 1) * C + c] : 0.f;
+        const float u = w0 * xm + w1 * xc + w2 * xp + bb;
+        const float d = dy[(size_t)row * C + c] * gelu_grad_f(u);
+        du[(size_t)row * C + c] = d;
+        g0 += d * xm; g1 += d * xc; g2 += d * xp; gb += d;
+        xm = xc; xc = xp;
+      }
     }
     atomicAdd(dw + c * 3, g0);
     atomicAdd(dw + c * 3 + 1, g1);

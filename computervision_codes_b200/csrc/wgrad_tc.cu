@@ -178,6 +178,7 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
       // every 16-byte chunk this thread touches has the same position inside its 32 x 32 block up to a row offset:
       const int lc = ((((ct & 7) >> 1) ^ ((ct >> 3) & 3)) << 1) | (ct & 1);  // logical 16-byte column chunk (swizzle undone)
       const bool extras = p.colscale != nullptr || p.x_drop_thresh != 0u || p.g_drop_thresh != 0u;
+      const bool raw_is_hi = NGA >= 4;   // measured: pays off for the 128 x 128 tiles of MS-TCT, not for the 128 x 64 ones
       float4 bsum[NGA];
 #pragma unroll
       for (int a = 0; a < NGA; ++a) bsum[a] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -206,6 +207,7 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
           float4* raw = reinterpret_cast<float4*>(tiles + s * WG_STAGE);
           float4* lo = reinterpret_cast<float4*>(tiles + s * WG_STAGE + WG_RAW);
           float4 v[NCH];
+          bool dirty[NCH];   // the tile entry differs from what TMA delivered: the hi half must be stored back
 #pragma unroll
           for (int i = 0; i < NCH; ++i) v[i] = raw[ct + i * WG_SPLIT];
 #pragma unroll
@@ -215,7 +217,8 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
             int src = r0 + r;
             if (atom < 4) src += a_tap[atom] == 0 ? p.shift[0] : (a_tap[atom] == 1 ? p.shift[1] : p.shift[2]);
             // select, not multiply: a pad row may hold anything (0 * NaN would poison the accumulator)
-            if (!(src >= m.lo && src < m.hi)) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            dirty[i] = extras;
+            if (!(src >= m.lo && src < m.hi)) { v[i] = make_float4(0.f, 0.f, 0.f, 0.f); dirty[i] = true; }
             if (extras) {
               if (atom < 4) {
                 const int col = a_cb[atom] * 32 + lc * 4;
@@ -248,7 +251,8 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
             h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u); l.y = v[i].y - h.y;
             h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u); l.z = v[i].z - h.z;
             h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u); l.w = v[i].w - h.w;
-            raw[ct + i * WG_SPLIT] = h;
+            // tcgen05.mma kind::tf32 ignores the low 13 mantissa bits: an untouched raw tile IS the hi operand
+            if (dirty[i] || !raw_is_hi) raw[ct + i * WG_SPLIT] = h;
             lo[ct + i * WG_SPLIT] = l;
           }
           fence_proxy_async();

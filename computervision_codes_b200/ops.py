@@ -412,11 +412,8 @@ class DilatedResidualFn(torch.autograd.Function):
         gb2 = torch.zeros(Cc, device=gy.device, dtype=torch.float32)
         wgrad(gy, h, lay, Cc, Cc, (0,), gw2, gb2, g_drop_p=p, seed=ctx.seed, stream_id=ctx.stream_id)
         gx = None
-        if ctx.masks is not None:  # one fused launch for gu and gx (tcgen05 / TMEM)
-            gu, gx = layer_bwd_tc(gy, ctx.masks, w1, w2, lay, shifts, p)
-        else:
-            gu = tapgemm(gy, prep_weight(w2, transpose=True), lay, Cc, Cc, (0,), relu_mask=h, in_drop_p=p,
-                         seed=ctx.seed, stream_id=ctx.stream_id)
+        gu = tapgemm(gy, prep_weight(w2, transpose=True), lay, Cc, Cc, (0,), relu_mask=h, in_drop_p=p,
+                     seed=ctx.seed, stream_id=ctx.stream_id)
         gw1 = torch.zeros(Cc, Cc, 3, device=gy.device, dtype=torch.float32)
         gb1 = torch.zeros(Cc, device=gy.device, dtype=torch.float32)
         wgrad(gu, x, lay, Cc, Cc, shifts, gw1, gb1)

@@ -994,7 +994,9 @@ static int wide_bn(const GemmTcDev& p, int nb) {
     forced = e ? atoi(e) : -1;
   }
   if (forced >= 0) return (forced == 128 || forced == 256) && p.N > 64 ? forced : 0;
-  if (p.N < 128 || p.ntaps * p.kbp < 4) return 0;
+  // short contractions stay on the persistent kernel (weights resident) unless they need three or more 64-column tiles:
+  // the heads (N = 131, K = 64) split and load every frame tile once per 64 columns there -- one 256-column tile is faster
+  if (p.N < 128 || (p.ntaps * p.kbp < 4 && p.N <= 128)) return 0;
   const int sms = num_sms();
   long best = -1;
   int best_bn = 0;

@@ -786,8 +786,10 @@ static int model_forward(tcn_model* m, const float* x, long x_rows, int training
   const int C = m->C, D = m->D, L = m->L;
   m->fwd_training = training != 0;
   const float pl = training ? m->layer_drop_p : 0.f;
-  // 0. weights -> fragment order (one launch)
-  TCN_CHECK(launch_prep_batched(m->jobs_dev, m->njobs, m->params, m->wf, m->prep_total_f4, st));
+  // 0. weights -> fragment order (one launch) for the mma.sync kernels; nothing reads them when every contraction of the
+  // model runs on the tcgen05 kernels (split hi / lo weights below)
+  const bool all_tc = m->use_tc && m->proj_tc && !(C == 64 && !m->fused_tc);
+  if (!all_tc) TCN_CHECK(launch_prep_batched(m->jobs_dev, m->njobs, m->params, m->wf, m->prep_total_f4, st));
   if (m->use_tc)
     TCN_CHECK(launch_split_batched(m->sjobs_dev, m->nsjobs, m->params, m->tc_whi, m->tc_wlo, m->split_total, st));
   // 1. stage-input projection (network.py:113,122-129), input mask + channel dropout folded into the load

@@ -201,6 +201,15 @@ def _ref_tenco():
     return ref_import.tenco_network()
 
 
+def _quiet(fn, *args, **kw):
+    """Run fn with stdout captured: the reference's BaseCausalTCN.__init__ prints its layer count (network.py:111), and
+    this program's stdout carries exactly one JSON line."""
+    import io
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*args, **kw)
+
+
 def _ref_loss(outs, labels):
     """train_loop's loss (Temporal_tenco/run.py:190-212): BCEWithLogitsLoss (mean over T x K) of sample 0, summed over
     the four FPN levels, 0.1 (i + v + t) + ivt.  labels = (y_i, y_v, y_t, y_ivt) float (T, K)."""
@@ -239,7 +248,7 @@ def cpu_arm(steps, V, C, D, budget_s=150.0, sweep_budget_s=20.0):
     kind = "reference"
     if net is not None:
         torch.manual_seed(0)
-        model = net.VideoNas(model_args(), *LAYERS, C, D, HEADS[0]).train()
+        model = _quiet(net.VideoNas, model_args(), *LAYERS, C, D, HEADS[0]).train()
         opt = torch.optim.SGD(model.parameters(), lr=1e-2, weight_decay=1e-5)
 
         def one(x, labels):
@@ -326,7 +335,7 @@ def eager_gpu_baseline(dev, C, D, nvid=12):
             torch.backends.cudnn.allow_tf32 = tf32
             torch.backends.cuda.matmul.allow_tf32 = tf32
             torch.manual_seed(0)
-            model = net.VideoNas(model_args(mask=True), *LAYERS, C, D, HEADS[0]).to(dev).train()
+            model = _quiet(net.VideoNas, model_args(mask=True), *LAYERS, C, D, HEADS[0]).to(dev).train()
             opt = torch.optim.SGD(model.parameters(), lr=1e-2, weight_decay=1e-5)
 
             def one(x, labels):

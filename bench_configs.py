@@ -14,7 +14,7 @@ import warnings
 
 import torch
 
-from bench import METRIC, ClockSampler, hbm_peak, model_args
+from bench import METRIC, ClockSampler, _quiet, hbm_peak, model_args
 
 
 def _events(fn, steps, warmup, min_seconds=1.0):
@@ -98,7 +98,7 @@ def _line(a, workload, frames, ms, reps, region_s, clocks, extra):
 
 # ------------------------------------------------------------------------------------------------ cfg1
 def _ref_stage_models(net, K, causal, dev):
-    pg = net.BaseCausalTCN(10, 64, 2048, K)
+    pg = _quiet(net.BaseCausalTCN, 10, 64, 2048, K)
     rf = net.Refinement(types.SimpleNamespace(output=False, hier=False), 10, 64, K, K, None)
     if causal:   # the layer the reference defines (network.py:165-183) but never instantiates
         for st in (pg, rf):

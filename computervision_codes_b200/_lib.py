@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libtcn_b200.so")
+LIB_PATH = os.environ.get("TCN_LIB_PATH") or os.path.join(_HERE, "csrc", "libtcn_b200.so")  # override: A/B builds (tools/exp)
 
 _lib = None
 
@@ -202,6 +202,7 @@ SIGNATURES = {
     "tcn_model_destroy": (None, [C.c_void_p]),
     "tcn_model_num_params": (C.c_longlong, [C.c_void_p]),
     "tcn_model_num_tensors": (C.c_int, [C.c_void_p]),
+    "tcn_model_debug_ptr": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "tcn_model_param_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]),
     "tcn_model_bind": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tcn_model_set_loss": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

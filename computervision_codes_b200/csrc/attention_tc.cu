@@ -247,6 +247,7 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
     }
   }
+  pdl_exit_fence();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(256u));

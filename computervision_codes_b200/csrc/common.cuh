@@ -14,6 +14,7 @@ int check_launch(const char* what);  // cudaGetLastError() -> TCN_ERR_CUDA; coun
 long long launch_count();
 int num_sms();
 bool pdl_enabled();  // TCN_NO_PDL=1 turns programmatic dependent launch off
+bool pdl_allowed_on(cudaStream_t stream);  // ... and it is used on capturing streams only (runtime.cu)
 
 // Launch with (optionally) the programmatic-stream-serialization attribute.
 template <typename... KArgs, typename... Args>
@@ -28,7 +29,7 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  cfg.numAttrs = (pdl && pdl_allowed_on(stream)) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -96,7 +97,25 @@ __device__ __forceinline__ void cp_async_wait() {
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may start
 // while its stream predecessor is still running; it must execute pdl_wait() before it touches anything the
 // predecessor wrote.  pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as soon as SMs free up.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+// Experiment switches (tools/exp/build_variant.sh -DTCN_PDL_FIX=n): bit 0 = proxy fence after the wait, bit 1 = a
+// __threadfence() before a producer CTA exits.  Neither removed the eager-launch stale reads described in runtime.cu
+// (1 of 40 first forwards still differed with both) and together they cost 6 % of the step, so both are off.
+#ifndef TCN_PDL_FIX
+#define TCN_PDL_FIX 0
+#endif
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+#if TCN_PDL_FIX & 1
+  // what the predecessor stored through the generic proxy is read below by TMA (async proxy)
+  asm volatile("fence.proxy.async;\n" ::: "memory");
+#endif
+}
+// Last statement of every thread that stored results a programmatically launched successor will read.
+__device__ __forceinline__ void pdl_exit_fence() {
+#if TCN_PDL_FIX & 2
+  __threadfence();
+#endif
+}
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 
 // fp32 -> (big, small) tf32 pair, big + small == x to ~2^-21 relative (the 3xTF32 split).

@@ -581,6 +581,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       }
     }
   }
+  pdl_exit_fence();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(256u));
@@ -763,6 +764,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       ++tcount;
     }
   }
+  pdl_exit_fence();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(128u));
@@ -959,6 +961,7 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       ++tcount;
     }
   }
+  pdl_exit_fence();
   tc_fence_before();
   __syncthreads();
   if (warp == 1)
@@ -1351,6 +1354,7 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       ++tcount;
     }
   }
+  pdl_exit_fence();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u));
@@ -1658,6 +1662,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_con
       ++tcount;
     }
   }
+  pdl_exit_fence();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u));
@@ -1876,6 +1881,7 @@ gemm_tc_slab_kernel(const __grid_constant__ CUtensorMap map_x32, const __grid_co
       ++tcount;
     }
   }
+  pdl_exit_fence();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(128u));

@@ -678,6 +678,13 @@ extern "C" void tcn_model_destroy(tcn_model* m) {
 }
 
 extern "C" long long tcn_model_num_params(const tcn_model* m) { return m ? m->n_params : 0; }
+// diagnostics (include/tcn_b200.h): kind 0 = input of layer idx (idx = L: last output), 1 = h of layer idx
+extern "C" int tcn_model_debug_ptr(tcn_model* m, int kind, int idx, void** out) {
+  if (!m || !out || idx < 0 || idx > m->L || (kind == 1 && idx >= m->L)) return TCN_ERR_INVALID_ARG;
+  *out = kind == 0 ? (void*)m->act[idx] : (void*)m->H[idx];
+  return TCN_OK;
+}
+
 extern "C" int tcn_model_num_tensors(const tcn_model* m) { return m ? (int)m->slots.size() : 0; }
 
 extern "C" int tcn_model_param_layout(const tcn_model* m, long long* offsets, long long* sizes, int n) {

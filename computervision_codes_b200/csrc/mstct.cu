@@ -39,7 +39,11 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 }
 
 // dx = rstd * (g*dy - mean_c(g*dy) - xhat * mean_c(g*dy*xhat));  dgamma += sum_r dy*xhat, dbeta += sum_r dy
-// (column sums: per-CTA partials in shared memory, then one atomic per column and CTA)
+// Column sums: KMAX > 0 (C <= 32 KMAX): every lane keeps the partial sums of its columns c = lane + 32 k in registers over
+// all rows of its warp, the eight warps of the CTA are added through shared memory once, then one atomic per column and
+// CTA -- the first version added every element to shared memory with atomics (8 warps on the same addresses: 73 us per
+// call at cfg3).  KMAX == 0: that version, for very wide rows.
+template <int KMAX>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, int ldx,
                                                             const float* __restrict__ dy, int lddy,
                                                             float* __restrict__ dx, int lddx,
@@ -53,11 +57,41 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sm[c] = 0.f;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int KR = KMAX > 0 ? KMAX : 1;
+  float ag[KR], ab[KR];
+#pragma unroll
+  for (int k = 0; k < KR; ++k) { ag[k] = 0.f; ab[k] = 0.f; }
   for (int row = blockIdx.x * 8 + warp; row < nrows; row += gridDim.x * 8) {
     if (meta != nullptr && row >= meta[row / kBlkRows].hi) continue;
     const float* xr = x + (size_t)row * ldx;
     const float* gr = dy + (size_t)row * lddy;
     const float mu = mean[row], rs = rstd[row];
+    float* dr = dx + (size_t)row * lddx;
+    if (KMAX > 0) {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < KR; ++k) {
+        const int c = lane + 32 * k;
+        if (c < C) {
+          const float xh = (xr[c] - mu) * rs, gg = gr[c] * __ldg(gamma + c);
+          s1 += gg;
+          s2 += gg * xh;
+        }
+      }
+      s1 = warp_sum(s1) / (float)C;
+      s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+      for (int k = 0; k < KR; ++k) {   // second pass over the row (L1-resident): dx and the register column sums
+        const int c = lane + 32 * k;
+        if (c < C) {
+          const float xh = (xr[c] - mu) * rs, g = gr[c];
+          dr[c] = rs * (g * __ldg(gamma + c) - s1 - xh * s2);
+          ag[k] += g * xh;
+          ab[k] += g;
+        }
+      }
+      continue;
+    }
     float s1 = 0.f, s2 = 0.f;
     for (int c = lane; c < C; c += 32) {
       const float xh = (xr[c] - mu) * rs, gg = gr[c] * __ldg(gamma + c);
@@ -66,12 +100,21 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     }
     s1 = warp_sum(s1) / (float)C;
     s2 = warp_sum(s2) / (float)C;
-    float* dr = dx + (size_t)row * lddx;
     for (int c = lane; c < C; c += 32) {
       const float xh = (xr[c] - mu) * rs, g = gr[c];
       dr[c] = rs * (g * __ldg(gamma + c) - s1 - xh * s2);
       atomicAdd(&sg[c], g * xh);
       atomicAdd(&sb[c], g);
+    }
+  }
+  if (KMAX > 0) {
+#pragma unroll
+    for (int k = 0; k < KR; ++k) {
+      const int c = lane + 32 * k;
+      if (c < C) {
+        atomicAdd(&sg[c], ag[k]);   // eight warps, once per CTA
+        atomicAdd(&sb[c], ab[k]);
+      }
     }
   }
   __syncthreads();
@@ -218,7 +261,11 @@ extern "C" int tcn_layernorm_bwd(const float* x, int ldx, const float* dy, int l
   TCN_REQUIRE(x && dy && dx && gamma && mean && rstd && dgamma && dbeta && nrows > 0 && channels > 0,
               "tcn_layernorm_bwd: bad arguments");
   TCN_REQUIRE(channels <= 8192, "tcn_layernorm_bwd: too many channels");
-  layernorm_bwd_kernel<<<cap_grid(nrows, 64, num_sms() * 2), 256, 2 * channels * sizeof(float), (cudaStream_t)stream>>>(
+  const dim3 lg(cap_grid(nrows, 64, num_sms() * 2));
+  const size_t lsm = 2 * channels * sizeof(float);
+  auto kern = channels <= 256 ? layernorm_bwd_kernel<8> : (channels <= 512 ? layernorm_bwd_kernel<16>
+                              : (channels <= 1024 ? layernorm_bwd_kernel<32> : layernorm_bwd_kernel<0>));
+  kern<<<lg, 256, lsm, (cudaStream_t)stream>>>(
       x, ldx, dy, lddy, dx, lddx, gamma, mean, rstd, dgamma, dbeta, reinterpret_cast<const BlkMeta*>(meta), nrows,
       channels);
   return check_launch("layernorm_bwd_kernel");

@@ -36,6 +36,24 @@ bool pdl_enabled() {
   return v == 1;
 }
 
+// Programmatic dependent launch is used inside captured graphs only (the whole step is submitted at once).  On eager
+// stream launches round 2 measured rare stale reads (1-40 frames of one layer's input, in 3-30 % of first forwards that
+// started while earlier work was still draining): the dependent kernel's TMA read of its predecessor's output
+// overtook the predecessor's last stores at the point where the GPU caught up with the host's submissions --
+// tools/exp/test_hunt.py, DESIGN.md section 5.  TCN_PDL_EAGER=1 restores it for experiments.
+bool pdl_allowed_on(cudaStream_t stream) {
+  if (!pdl_enabled()) return false;
+  static int eager = -1;
+  if (eager < 0) eager = (getenv("TCN_PDL_EAGER") != nullptr) ? 1 : 0;
+  if (eager == 1) return true;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return st == cudaStreamCaptureStatusActive;
+}
+
 int num_sms() {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;

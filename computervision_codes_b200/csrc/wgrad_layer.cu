@@ -299,6 +299,7 @@ __device__ __forceinline__ void wgrad_layer_body(const WgLayerDev* __restrict__ 
       for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
   }
+  pdl_exit_fence();
   tc_fence_before();
   __syncthreads();
   if (warp == 1)

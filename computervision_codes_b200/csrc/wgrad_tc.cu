@@ -308,6 +308,7 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap* map_xp, const C
       }
     }
   }
+  pdl_exit_fence();
   tc_fence_before();
   __syncthreads();
   if (warp == 1)

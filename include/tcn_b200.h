@@ -226,6 +226,10 @@ void tcn_model_destroy(tcn_model* m);
 long long tcn_model_num_params(const tcn_model* m);
 int tcn_model_num_tensors(const tcn_model* m);
 int tcn_model_param_layout(const tcn_model* m, long long* offsets, long long* sizes, int n);
+/* Diagnostics: device pointer of a saved activation of the last forward, (max_rows, channels) fp32.
+ * kind 0 = input of residual layer idx (idx = number of layers: the last output), kind 1 = relu output h of layer idx.
+ * (No reference counterpart: the reference keeps these inside autograd.) */
+int tcn_model_debug_ptr(tcn_model* m, int kind, int idx, void** out);
 int tcn_model_bind(tcn_model* m, float* params, float* grads);
 /* head_weights[4] for (ivt, i, v, t); pos_w: HOST array of sum(head_sizes) floats or NULL */
 int tcn_model_set_loss(tcn_model* m, const float* head_weights, const float* pos_w_host);

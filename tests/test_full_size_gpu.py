@@ -24,6 +24,7 @@ DEV = "cuda"
 def _no_tf32_in_any_torch_reference():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True  # the live-reference legs: same cuDNN algorithms every run
     yield
 
 
@@ -37,6 +38,17 @@ def _t(a):
 
 def _maxabs(a, b):
     return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
+
+
+def _assert_argmax_consistent(got, ref, dim, tie=2e-3):
+    """Identical predictions, except where the live reference's own top two logits are closer than `tie` (twice the
+    logit tolerance): the reference on cuDNN is not run-to-run deterministic, so a near-tie may resolve either way."""
+    ga, ra = got.argmax(dim), ref.argmax(dim)
+    bad = ga != ra
+    if bool(bad.any()):
+        top2 = ref.detach().topk(2, dim=dim).values
+        gap = (top2.select(dim, 0) - top2.select(dim, 1)).abs()
+        assert float(gap[bad].max()) <= tie, f"{int(bad.sum())} predictions differ, widest reference gap {float(gap[bad].max()):.3e}"
 
 
 def _check_digest(grad, ref_dig, idx, rel, name):
@@ -269,7 +281,7 @@ def test_videonas_against_live_reference_on_gpu(C, D, T):
             assert _maxabs(a, r) <= 1e-3
     for a_list, r_list in zip(o_got[:4], o_ref[:4]):
         for a, r in zip(a_list, r_list):
-            assert torch.equal(a.argmax(1), r.argmax(1))
+            _assert_argmax_consistent(a, r, 1)
     assert abs(float(l_got) - float(l_ref)) <= 1e-4 * abs(float(l_ref))
     pr = dict(ref.named_parameters())
     for k, v in m.named_parameters():
@@ -314,7 +326,7 @@ def test_mstct_cfg3_against_live_reference_on_gpu():
     lg = losses.bce_with_logits(y.reshape(B * T, K), lab.reshape(B * T, K))
     lg.backward()
     assert _maxabs(y, yr) <= 1e-3
-    assert torch.equal(y.argmax(-1), yr.argmax(-1))
+    _assert_argmax_consistent(y, yr, -1)
     assert abs(float(lg) - float(lr)) <= 1e-4 * abs(float(lr))
     for (a, b) in ((enc, r_enc), (mix, r_mix), (cls, r_cls)):
         pr = dict(b.named_parameters())

@@ -105,7 +105,10 @@ __device__ __forceinline__ void cp_async_wait() {
 #endif
 __device__ __forceinline__ void pdl_wait() {
   asm volatile("griddepcontrol.wait;\n" ::: "memory");
-#if TCN_PDL_FIX & 1
+#if TCN_PDL_FIX & 4
+  asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+#endif
+#if TCN_PDL_FIX & 5
   // what the predecessor stored through the generic proxy is read below by TMA (async proxy)
   asm volatile("fence.proxy.async;\n" ::: "memory");
 #endif
@@ -116,7 +119,11 @@ __device__ __forceinline__ void pdl_exit_fence() {
   __threadfence();
 #endif
 }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if !(TCN_PDL_FIX & 8)
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+#endif
+}
 
 // fp32 -> (big, small) tf32 pair, big + small == x to ~2^-21 relative (the 3xTF32 split).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {

@@ -1308,7 +1308,7 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           }
           if (row < m.hi) *reinterpret_cast<uint2*>(p.masks + (size_t)row * 4 + 2) = make_uint2(w[0], w[1]);
         }
-        __threadfence_block();
+        __threadfence();   // device scope: the v -> y warps read the words back with ld.global.cg (L2), not through L1
         atomicAdd(kcount, 1u);
       }
     }

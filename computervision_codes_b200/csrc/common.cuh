@@ -97,11 +97,22 @@ __device__ __forceinline__ void cp_async_wait() {
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may start
 // while its stream predecessor is still running; it must execute pdl_wait() before it touches anything the
 // predecessor wrote.  pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as soon as SMs free up.
-// Experiment switches (tools/exp/build_variant.sh -DTCN_PDL_FIX=n): bit 0 = proxy fence after the wait, bit 1 = a
-// __threadfence() before a producer CTA exits.  Neither removed the eager-launch stale reads described in runtime.cu
-// (1 of 40 first forwards still differed with both) and together they cost 6 % of the step, so both are off.
+// No kernel of this library triggers its dependents early (TCN_PDL_TRIGGER 0): a programmatically launched kernel is
+// scheduled when the last CTA of its predecessor has exited -- without the full inter-kernel drain -- runs its prologue
+// (barriers, TMEM allocation, step-constant weights) and then waits in griddepcontrol.wait for the predecessor's memory.
+// Round 2 first triggered at the very top of every kernel (TCN_PDL_TRIGGER 2: up to nine 15-CTA grids of the 41-layer
+// chain resident at once, each spinning in its wait), then right after the wait (1).  With either, a layer occasionally
+// computed 1-40 frames from input its predecessor had not stored yet: tools/exp/pdl_graph_check.py (same weights, same
+// batches, graph replay) diverges from a serialised run after 10-1000 steps, tools/exp/test_hunt.py shows it on 3-30 %
+// of eager first forwards; without the trigger both behave like a run without programmatic launch.  Fences did not help
+// (TCN_PDL_FIX bit 0: proxy fence after the wait, bit 1: __threadfence() before a producer CTA exits, bit 2: acquire
+// fence after the wait -- all still diverged and cost up to 6 %).  The trigger was worth 2.6 % of the step
+// (1.772 -> 1.819 ms in the probe; no programmatic launch at all: 1.883 ms).  DESIGN.md section 3.
 #ifndef TCN_PDL_FIX
 #define TCN_PDL_FIX 0
+#endif
+#ifndef TCN_PDL_TRIGGER
+#define TCN_PDL_TRIGGER 0
 #endif
 __device__ __forceinline__ void pdl_wait() {
   asm volatile("griddepcontrol.wait;\n" ::: "memory");
@@ -109,18 +120,20 @@ __device__ __forceinline__ void pdl_wait() {
   asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
 #endif
 #if TCN_PDL_FIX & 5
-  // what the predecessor stored through the generic proxy is read below by TMA (async proxy)
   asm volatile("fence.proxy.async;\n" ::: "memory");
 #endif
+#if TCN_PDL_TRIGGER == 1
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+#endif
 }
-// Last statement of every thread that stored results a programmatically launched successor will read.
 __device__ __forceinline__ void pdl_exit_fence() {
 #if TCN_PDL_FIX & 2
   __threadfence();
 #endif
 }
+// Call sites sit at the top of the kernels, before pdl_wait() (the original order); a no-op unless TCN_PDL_TRIGGER is 2.
 __device__ __forceinline__ void pdl_launch_dependents() {
-#if !(TCN_PDL_FIX & 8)
+#if TCN_PDL_TRIGGER == 2
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
 #endif
 }

@@ -36,11 +36,11 @@ bool pdl_enabled() {
   return v == 1;
 }
 
-// Programmatic dependent launch is used inside captured graphs only (the whole step is submitted at once).  On eager
-// stream launches round 2 measured rare stale reads (1-40 frames of one layer's input, in 3-30 % of first forwards that
-// started while earlier work was still draining): the dependent kernel's TMA read of its predecessor's output
-// overtook the predecessor's last stores at the point where the GPU caught up with the host's submissions --
-// tools/exp/test_hunt.py, DESIGN.md section 5.  TCN_PDL_EAGER=1 restores it for experiments.
+// Programmatic dependent launch is used inside captured graphs only.  Round 2 measured rare stale reads (1-40 frames of
+// one layer's input) with the early trigger the kernels carried then (common.cuh: TCN_PDL_TRIGGER); they were far more
+// frequent on eager launches (3-30 % of first forwards submitted while earlier work was still draining) than under
+// graph replay.  The trigger is gone; eager launches keep a full stream dependency on top of that -- they are bound by
+// the host's dispatch anyway.  TCN_PDL_EAGER=1 lifts the restriction for experiments (tools/exp/test_hunt.py).
 bool pdl_allowed_on(cudaStream_t stream) {
   if (!pdl_enabled()) return false;
   static int eager = -1;

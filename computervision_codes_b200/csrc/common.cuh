@@ -106,7 +106,8 @@ __device__ __forceinline__ void cp_async_wait() {
 // batches, graph replay) diverges from a serialised run after 10-1000 steps, tools/exp/test_hunt.py shows it on 3-30 %
 // of eager first forwards; without the trigger both behave like a run without programmatic launch.  Fences did not help
 // (TCN_PDL_FIX bit 0: proxy fence after the wait, bit 1: __threadfence() before a producer CTA exits, bit 2: acquire
-// fence after the wait -- all still diverged and cost up to 6 %).  The trigger was worth 2.6 % of the step
+// fence after the wait, bit 4: proxy fence on the writer side before a producer CTA exits -- all still diverged and cost up
+// to 6 %).  The trigger was worth 2.6 % of the step
 // (1.772 -> 1.819 ms in the probe; no programmatic launch at all: 1.883 ms).  DESIGN.md section 3.
 #ifndef TCN_PDL_FIX
 #define TCN_PDL_FIX 0
@@ -129,6 +130,9 @@ __device__ __forceinline__ void pdl_wait() {
 __device__ __forceinline__ void pdl_exit_fence() {
 #if TCN_PDL_FIX & 2
   __threadfence();
+#endif
+#if TCN_PDL_FIX & 16
+  asm volatile("fence.proxy.async;\n" ::: "memory");   // writer side: generic stores -> a successor's TMA (async proxy) loads
 #endif
 }
 // Call sites sit at the top of the kernels, before pdl_wait() (the original order); a no-op unless TCN_PDL_TRIGGER is 2.

@@ -28,3 +28,19 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _gpu_test_isolation(request):
+    """GPU tests start and end on an idle device: asynchronous work of one test must not overlap the first launches of the
+    next (the one test that wants a backlog, test_first_forward_behind_queued_work_equals_the_second, queues its own)."""
+    if "gpu" not in request.keywords:
+        yield
+        return
+    import torch
+
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    yield
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()

@@ -377,7 +377,10 @@ def run_cfg2(a, rank, world, local_rank, C, D, tag):
                                    "the next V x N passes, so at N = 8 one step spans two folds' worth of videos",
               "parallelism": f"dp{world}-by-video, videos of a global step assigned longest-first (LPT), equal count per rank",
               "l2": "inputs cycle through the 0.8 GB feature set (>> 126 MB L2); no explicit flush",
-              "resident_inputs": "one HBM feature arena (FeatureCache.pack), read in place by the step"}
+              "resident_inputs": "one HBM feature arena (FeatureCache.pack), read in place by the step",
+              "launch_mode": "one CUDA graph per step; programmatic dependent launch inside the graph with "
+                             "griddepcontrol.wait and NO early trigger (DESIGN.md section 3: the early trigger, worth "
+                             "4.6 % of the step, let a layer read frames its predecessor had not stored yet)"}
 
     if a.impl == "reference":
         if rank != 0:

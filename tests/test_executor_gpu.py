@@ -1,4 +1,5 @@
 """Native whole-model executor (csrc/model.cu) against the oracle, eval and train mode.  GPU only."""
+import os
 import types
 
 import pytest
@@ -257,6 +258,44 @@ def test_trainer_steps_are_bit_reproducible():
         torch.cuda.synchronize()
         outs.append(tr.flat_p.clone())
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.skipif(os.environ.get("TCN_LONG_TESTS") is None,
+                    reason="long run (set TCN_LONG_TESTS=1): the detector of DESIGN.md section 3")
+def test_graph_replayed_training_is_bit_reproducible_over_many_steps():
+    """tools/exp/pdl_graph_check.py as a test: two trainers, same weights / seeds / eight cycling ragged batches at the
+    BASELINE width, 400 graph-replayed steps each -- identical parameters at every mark.  With an early programmatic-launch
+    trigger in the kernels this failed within 10-200 steps; the shipped build (no trigger) passed 800+ in every probe, but
+    a rarer unexplained divergence (one per 2000-3000 steps) exists, hence opt-in."""
+    import hashlib
+
+    from computervision_codes_b200.tcn import VideoNas
+    from computervision_codes_b200.trainer import TemporalTrainer
+
+    args = types.SimpleNamespace(fpn=True, output=False, feature=False, trans=False, mask=True, hier=False)
+    g = torch.Generator().manual_seed(2)
+    batches = []
+    for _ in range(8):
+        lens = [int(t) for t in torch.randint(900, 3600, (8,), generator=g)]
+        x = torch.randn(sum(lens), 2048, generator=g).to(DEV)
+        lab = (torch.rand(sum(lens), 132, generator=g) < 0.05).to(torch.uint8).to(DEV)
+        batches.append((x, lab, lens))
+    marks, digests = (1, 10, 100, 200, 400), []
+    for _ in range(2):
+        torch.manual_seed(1)
+        m = VideoNas(args, 11, 10, 3, 64, 2048, 100).to(DEV).train()
+        tr = TemporalTrainer(m, lr=1e-3, weight_decay=1e-5, max_frames=8 * 3600 + 8 * 128, max_seqs=8, seed=5,
+                             input_mask_p=0.25)
+        out = []
+        for s in range(1, marks[-1] + 1):
+            x, lab, lens = batches[s % 8]
+            tr.step(x, lab, lens)
+            if s in marks:
+                torch.cuda.synchronize()
+                out.append(hashlib.sha256(tr.flat_p.cpu().numpy().tobytes()).hexdigest())
+        digests.append(out)
+        tr.close()
+    assert digests[0] == digests[1]
 
 
 @pytest.mark.parametrize("causal", [False, True])

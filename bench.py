@@ -474,7 +474,8 @@ def run_cfg2(a, rank, world, local_rank, C, D, tag):
         for s in range(W):
             run_step(s)
         probe_ms = region(run_step, W, K)
-        R = max(1, min(int(math.ceil(a.min_seconds * 1e3 / max(probe_ms, 1e-3))), 2000))
+        # 5 % head-room: the probe region carries the tail of the warm-up and runs a little slower than the timed one
+        R = max(1, min(int(math.ceil(1.05 * a.min_seconds * 1e3 / max(probe_ms, 1e-3))), 2000))
         s0 = W + K
         ms = region(run_step, s0, K * R)
         frames = allsum(sum(lengths[v] for s in range(s0, s0 + K * R) for v in batch_fn(s)))
